@@ -1,0 +1,118 @@
+/* mcd_b200.h -- C ABI of the B200 (sm_100a) neuron->concept scoring kernels.
+ *
+ * This is the drop-in boundary for the scoring path of Mammo-CLIP Dissect.  The
+ * reference implements the path as PyTorch calls inside
+ *   concept_vit/similarity.py            (soft_wpmi :49-73, wpmi :75-97, cos* :7-47)
+ *   concept_vit/utils.py:27-52           (get_activation pooling hook)
+ *   concept_vit/utils.py:570-594         (row-normalise + I @ T.T)
+ * and selects it with eval("similarity.<name>") (describe_clip_neurons.py:41).  The host
+ * mirror of that Python surface lives in mammo_clip_dissect_b200/similarity.py and binds
+ * these entry points with ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer on the current CUDA device unless named host_*;
+ *   - matrices are row-major fp32 with an explicit leading dimension in ELEMENTS;
+ *   - `stream` is a cudaStream_t (torch.cuda.current_stream().cuda_stream); calls only
+ *     enqueue work: no allocation, no synchronisation, re-entrant per stream;
+ *   - return value 0 = success, negative = error (mcd_strerror), never throws;
+ *   - N = probe images, K = neurons (columns of the activation matrix), C = concepts,
+ *     k = top_k, D = embedding width.
+ */
+#ifndef MCD_B200_H
+#define MCD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCD_ABI_VERSION 1
+
+#define MCD_OK 0
+#define MCD_ERR_INVALID_ARGUMENT (-1)
+#define MCD_ERR_UNSUPPORTED (-2)
+#define MCD_ERR_WORKSPACE (-3)
+#define MCD_ERR_CUDA (-4)
+#define MCD_ERR_NO_DEVICE (-5)
+
+#define MCD_LSE_BLOCK 256 /* neurons per log-sum-exp partial; fixed so results do not depend on sharding */
+
+typedef void *mcd_stream_t; /* cudaStream_t */
+
+typedef enum { MCD_F32 = 0, MCD_F16 = 1, MCD_BF16 = 2 } mcd_dtype_t;
+typedef enum { MCD_POOL_MEAN = 0, MCD_POOL_MAX = 1 } mcd_pool_t;
+
+/* ---- library ------------------------------------------------------------------------- */
+int mcd_abi_version(void);
+const char *mcd_strerror(int code);
+const char *mcd_build_info(void);      /* "sm_100a nvcc <ver> ..." */
+uint64_t mcd_launch_count(void);       /* kernels launched by this library so far (monotonic) */
+int mcd_device_check(void);            /* 0 iff the current device is compute capability 10.x */
+int mcd_set_tunable(const char *name, int64_t value); /* bench/test knobs: "topk_splits", "accum_tile", ... */
+
+/* ---- K1b: S = softmax(a * P, dim=1)          replaces similarity.py:54 / :80 ---------- */
+/* P [n_rows, n_cols] (ldp), S [n_rows, lds]; columns n_cols..lds-1 of S are written as 0. */
+int mcd_softmax_rows_f32(const float *P, int64_t ldp, float *S, int64_t lds,
+                         int64_t n_rows, int64_t n_cols, float a, mcd_stream_t stream);
+
+/* ---- K1: row-normalise I and T, P = I T^T, S = softmax(a P)    replaces utils.py:577-594
+ *      (+ similarity.py:54).  I [N,D] (ldi), T [C,D] (ldt).  P_out and/or S_out may be NULL.
+ *      Tensor-core path: tcgen05 kind::tf32 with a 3-term hi/lo split (fp32-grade result). */
+size_t mcd_gemm_nt_softmax_workspace_bytes(int64_t N, int64_t C, int64_t D);
+int mcd_gemm_nt_softmax_f32(const float *I, int64_t ldi, const float *T, int64_t ldt,
+                            int64_t N, int64_t C, int64_t D, int normalize_rows, float a,
+                            float *P_out, int64_t ldp, float *S_out, int64_t lds,
+                            void *workspace, size_t workspace_bytes, mcd_stream_t stream);
+
+/* ---- K2: per-column top-k over the probe-image axis   replaces torch.topk(A, dim=0, k)
+ *      (similarity.py:55, :82, :107).  Total order: value desc, image index asc, NaN largest,
+ *      -0.0 == +0.0.  A [N,K] (lda).  Any of idx64_out / idx32_out / vals_out [k,K] may be NULL. */
+size_t mcd_topk_cols_workspace_bytes(int64_t N, int64_t K, int64_t k);
+int mcd_topk_cols_f32(const float *A, int64_t lda, int64_t N, int64_t K, int64_t k,
+                      int64_t *idx64_out, int32_t *idx32_out, float *vals_out,
+                      void *workspace, size_t workspace_bytes, mcd_stream_t stream);
+
+/* ---- K3: L[j,c] = sum_r log(1 + p[r] (S[idx[r,j],c] - 1) + min_prob)   (soft-WPMI body,
+ *      similarity.py:59-65); p == NULL gives sum_r log(S[idx[r,j],c] + min_prob) (WPMI body,
+ *      similarity.py:85-89).  S [N,C] (lds), idx [k,K] int32 (ld = K), p [k], L [K,C] (ldl). */
+int mcd_wpmi_accum_f32(const float *S, int64_t lds, int64_t N, int64_t C,
+                       const int32_t *idx, int64_t K, int64_t k, const float *p, float min_prob,
+                       float *L, int64_t ldl, mcd_stream_t stream);
+
+/* ---- K3b: log p(d) and the final subtraction          replaces similarity.py:67-72 / :91-96
+ *      partials [ceil(K/256), 2, C]: per 256-neuron block (max_c, sum_j exp(L[j,c]-max_c)).
+ *      finalize combines `n_blocks_total` partials IN ORDER (fp64), so a neuron-sharded run
+ *      that concatenates every shard's partials in global block order is bit-identical to
+ *      the unsharded run:  out = L - lam * (lse - log(K_total)).  out may alias L. */
+int mcd_col_lse_partials_f32(const float *L, int64_t ldl, int64_t K, int64_t C,
+                             float *partials, mcd_stream_t stream);
+int mcd_pmi_finalize_f32(const float *L, int64_t ldl, int64_t K, int64_t C,
+                         const float *partials_all, int64_t n_blocks_total, int64_t K_total,
+                         float lam, float *prob_d_out /* [C] scratch+result */,
+                         float *out, int64_t ldo, mcd_stream_t stream);
+
+/* ---- K4: spatial pooling of a hooked NCHW activation   replaces utils.py:38 / :47 -------
+ *      x [B,C,H,W] contiguous, dtype f32/f16/bf16; out [B,C] same dtype (fp32 accumulation).
+ *      workspace: mcd_pool_nchw_workspace_bytes (partials for planes split across CTAs). */
+size_t mcd_pool_nchw_workspace_bytes(int64_t B, int64_t C, int64_t H, int64_t W);
+int mcd_pool_nchw(const void *x, mcd_dtype_t dtype, int64_t B, int64_t C, int64_t H, int64_t W,
+                  mcd_pool_t mode, void *out, void *workspace, size_t workspace_bytes,
+                  mcd_stream_t stream);
+
+/* ---- cosine similarities (similarity.py:7-47), next rows of the scope table -------------
+ *      column statistics of X [N,M]: cubed: mean[m] and norm[m] = max(||(x-mean)^3||_2, min_norm);
+ *      plain: norm[m] = ||x||_2 (mean_out may be NULL). */
+int mcd_col_stats_f32(const float *X, int64_t ldx, int64_t N, int64_t M, int cubed, float min_norm,
+                      float *mean_out, float *norm_out, mcd_stream_t stream);
+/* out[j,c] = sum_i f(A[i,j]) * f(P[i,c]),  f(x) = (x-mean)^3 / norm (cubed) or x / norm */
+int mcd_cos_matmul_f32(const float *A, int64_t lda, const float *meanA, const float *normA,
+                       const float *P, int64_t ldp, const float *meanP, const float *normP,
+                       int64_t N, int64_t K, int64_t C, int cubed,
+                       float *out, int64_t ldo, mcd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCD_B200_H */

@@ -1,0 +1,91 @@
+// K3b -- log p(d) over the neurons of a call and the final subtraction
+// (replaces torch.logsumexp(L, dim=0) - log(K) and `L - lam * prob_d`,
+//  concept_vit/similarity.py:67-72 and :91-96).
+//
+// The log-sum-exp over neurons is the one place where neurons are coupled, so it is also the one
+// exchange point of the neuron-sharded multi-GPU path.  To make results independent of how the
+// neurons are sharded it is computed in fixed blocks of MCD_LSE_BLOCK = 256 neurons:
+//   partial[b] = ( m_b[c] = max_j L[j,c],  s_b[c] = sum_j exp(L[j,c] - m_b[c]) )   (fp32, j in block order)
+// and the partials of ALL blocks are combined in global block order in fp64:
+//   lse[c] = M + log( sum_b s_b * exp(m_b - M) ),  M = max_b m_b.
+#include "common.cuh"
+
+namespace mcd {
+
+constexpr int kLseThreads = 128;
+
+__global__ void __launch_bounds__(kLseThreads)
+col_lse_partials_kernel(const float *__restrict__ L, int64_t ldl, int64_t K, int C, float *__restrict__ partials) {
+    const int c = blockIdx.x * kLseThreads + threadIdx.x;
+    const int64_t b = blockIdx.y;
+    if (c >= C) return;
+    const int64_t j0 = b * MCD_LSE_BLOCK;
+    const int64_t j1 = min(K, j0 + MCD_LSE_BLOCK);
+    const float *col = L + c;
+    float m = -INFINITY;
+    for (int64_t j = j0; j < j1; ++j) m = fmaxf(m, col[j * ldl]);
+    const float ms = (m == -INFINITY) ? 0.f : m;
+    float s = 0.f;
+    for (int64_t j = j0; j < j1; ++j) s += expf(col[j * ldl] - ms);
+    partials[(b * 2 + 0) * C + c] = m;
+    partials[(b * 2 + 1) * C + c] = s;
+}
+
+__global__ void __launch_bounds__(kLseThreads)
+lse_combine_kernel(const float *__restrict__ partials, int64_t n_blocks, int C, double log_count,
+                   float *__restrict__ prob_d) {
+    const int c = blockIdx.x * kLseThreads + threadIdx.x;
+    if (c >= C) return;
+    double big = -INFINITY;
+    for (int64_t b = 0; b < n_blocks; ++b) big = fmax(big, double(partials[(b * 2) * C + c]));
+    const double bs = isinf(big) ? 0.0 : big;
+    double total = 0.0;
+    for (int64_t b = 0; b < n_blocks; ++b)
+        total += double(partials[(b * 2 + 1) * C + c]) * exp(double(partials[(b * 2) * C + c]) - bs);
+    prob_d[c] = static_cast<float>(bs + log(total) - log_count);
+}
+
+__global__ void __launch_bounds__(256)
+pmi_finalize_kernel(const float *__restrict__ L, int64_t ldl, int64_t K, int C, const float *__restrict__ prob_d,
+                    float lam, float *__restrict__ out, int64_t ldo) {
+    const int64_t total = K * int64_t(C);
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
+        const int64_t j = i / C;
+        const int c = static_cast<int>(i - j * C);
+        out[j * ldo + c] = __fsub_rn(L[j * ldl + c], __fmul_rn(lam, prob_d[c]));
+    }
+}
+
+}  // namespace mcd
+
+extern "C" int mcd_col_lse_partials_f32(const float *L, int64_t ldl, int64_t K, int64_t C, float *partials,
+                                        mcd_stream_t stream) {
+    using namespace mcd;
+    if (!L || !partials || K < 1 || C < 1 || ldl < C || C > (1 << 24)) return MCD_ERR_INVALID_ARGUMENT;
+    const int64_t nb = ceil_div<int64_t>(K, MCD_LSE_BLOCK);
+    if (nb > 65535) return MCD_ERR_UNSUPPORTED;
+    dim3 grid(static_cast<unsigned>(ceil_div<int64_t>(C, kLseThreads)), static_cast<unsigned>(nb));
+    col_lse_partials_kernel<<<grid, kLseThreads, 0, static_cast<cudaStream_t>(stream)>>>(L, ldl, K, int(C), partials);
+    return check_launch();
+}
+
+extern "C" int mcd_pmi_finalize_f32(const float *L, int64_t ldl, int64_t K, int64_t C, const float *partials_all,
+                                    int64_t n_blocks_total, int64_t K_total, float lam, float *prob_d_out,
+                                    float *out, int64_t ldo, mcd_stream_t stream) {
+    using namespace mcd;
+    if (!L || !partials_all || !prob_d_out || !out || K < 1 || C < 1 || ldl < C || ldo < C || n_blocks_total < 1 ||
+        K_total < 1 || C > (1 << 24))
+        return MCD_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    lse_combine_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(C, kLseThreads)), kLseThreads, 0, st>>>(
+        partials_all, n_blocks_total, int(C), log(double(K_total)), prob_d_out);
+    int rc = check_launch();
+    if (rc != MCD_OK) return rc;
+    const int64_t total = K * C;
+    int64_t blocks = ceil_div<int64_t>(total, 256 * 4);
+    const int64_t cap = int64_t(num_sms()) * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    pmi_finalize_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(L, ldl, K, int(C), prob_d_out, lam, out, ldo);
+    return check_launch();
+}

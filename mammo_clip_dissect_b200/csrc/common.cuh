@@ -1,0 +1,131 @@
+// Shared helpers for the sm_100a kernels behind include/mcd_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mcd_b200.h"
+
+namespace mcd {
+
+constexpr int kNumSMsB200 = 148;
+
+// ---- launch accounting / error plumbing -----------------------------------------------------
+void count_launch(int n = 1);          // abi.cu
+int64_t tunable(int which);            // abi.cu
+enum Tunable { kTopkSplits = 0, kAccumTile = 1, kTopkVariant = 2, kAccumUnroll = 3, kNumTunables = 8 };
+int num_sms();                         // abi.cu (cached cudaDevAttrMultiProcessorCount)
+
+inline int check_launch(int n = 1) {
+    count_launch(n);
+    return cudaPeekAtLastError() == cudaSuccess ? MCD_OK : MCD_ERR_CUDA;
+}
+
+template <typename T>
+__host__ __device__ constexpr T ceil_div(T a, T b) { return (a + b - 1) / b; }
+
+// ---- ordered keys for the top-k total order ---------------------------------------------------
+// value desc, index asc, NaN largest, -0.0 == +0.0.  key(v) is a u32 that sorts like v under
+// that rule; 0 is reserved as the "empty slot" sentinel (no finite/inf/NaN value maps to it).
+__device__ __forceinline__ uint32_t ordered_key(float v) {
+    if (v != v) return 0xFFFFFFFFu;
+    uint32_t b = __float_as_uint(v + 0.0f);             // -0.0 + 0.0 == +0.0
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+// A float t such that `!(v <= t)` holds for every v whose key exceeds `key` (and may hold for
+// equal keys only when key is the sentinel / NaN, where t = NaN admits everything).
+__device__ __forceinline__ float key_to_threshold(uint32_t key) {
+    if (key == 0u || key == 0xFFFFFFFFu) return __uint_as_float(0x7FC00000u);
+    uint32_t b = (key & 0x80000000u) ? (key ^ 0x80000000u) : ~key;
+    return __uint_as_float(b);
+}
+__device__ __forceinline__ unsigned long long pack_key(uint32_t hi, uint32_t lo) {
+    return (static_cast<unsigned long long>(hi) << 32) | lo;
+}
+
+// ---- PTX: mbarrier + bulk async copy (TMA engine, 1-D) ----------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar,
+                                         uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
+// ---- loads ------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg_nc_v4(const float *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float4 ldg_nc_v4_hint(const float *p, uint64_t policy) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p), "l"(policy));
+    return r;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float r;
+    asm("lg2.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace mcd

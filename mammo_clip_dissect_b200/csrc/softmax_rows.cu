@@ -1,0 +1,94 @@
+// K1b -- S = softmax(a * P, dim=1) for the concept-probability matrix
+// (replaces torch.nn.functional.softmax(a*clip_feats, dim=1), concept_vit/similarity.py:54 / :80).
+//
+// One warp per probe image.  The row (C = 763 floats) is read once into registers, the scaled
+// logits use a separately rounded multiply (a*x as the reference computes it), exp is the
+// full-precision expf and the normalisation is a true division, so each element goes through the
+// reference's operation sequence; only the order of the row sum (warp tree) differs.
+// S is written with its own leading dimension (the product pads rows to a multiple of 4 floats
+// so K3 can gather with aligned 16-byte loads); padding columns are zero-filled.
+#include "common.cuh"
+
+namespace mcd {
+
+constexpr int kSoftmaxWarps = 8;
+
+template <int PER>   // register-resident rows up to 32*PER columns
+__global__ void __launch_bounds__(kSoftmaxWarps * 32)
+softmax_rows_kernel(const float *__restrict__ P, int64_t ldp, float *__restrict__ S, int64_t lds, int64_t n_rows,
+                    int n_cols, float a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = int64_t(blockIdx.x) * kSoftmaxWarps + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const float *src = P + row * ldp;
+    float *dst = S + row * lds;
+    float x[PER];
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int c = lane + 32 * i;
+        x[i] = c < n_cols ? __fmul_rn(a, __ldg(src + c)) : -INFINITY;
+        m = fmaxf(m, x[i]);
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int c = lane + 32 * i;
+        x[i] = c < n_cols ? expf(__fsub_rn(x[i], m)) : 0.f;
+        sum += x[i];
+    }
+    sum = warp_sum(sum);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int c = lane + 32 * i;
+        if (c < n_cols) dst[c] = __fdiv_rn(x[i], sum);
+        else if (c < lds) dst[c] = 0.f;
+    }
+    for (int c = 32 * PER + lane; c < lds; c += 32) dst[c] = 0.f;
+}
+
+// any width: three passes over the row (it stays in L1/L2)
+__global__ void __launch_bounds__(kSoftmaxWarps * 32)
+softmax_rows_wide_kernel(const float *__restrict__ P, int64_t ldp, float *__restrict__ S, int64_t lds,
+                         int64_t n_rows, int64_t n_cols, float a) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = int64_t(blockIdx.x) * kSoftmaxWarps + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const float *src = P + row * ldp;
+    float *dst = S + row * lds;
+    float m = -INFINITY;
+    for (int64_t c = lane; c < n_cols; c += 32) m = fmaxf(m, __fmul_rn(a, src[c]));
+    m = warp_max(m);
+    float sum = 0.f;
+    for (int64_t c = lane; c < n_cols; c += 32) {
+        const float e = expf(__fsub_rn(__fmul_rn(a, src[c]), m));
+        dst[c] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    for (int64_t c = lane; c < n_cols; c += 32) dst[c] = __fdiv_rn(dst[c], sum);
+    for (int64_t c = n_cols + lane; c < lds; c += 32) dst[c] = 0.f;
+}
+
+}  // namespace mcd
+
+extern "C" int mcd_softmax_rows_f32(const float *P, int64_t ldp, float *S, int64_t lds, int64_t n_rows,
+                                    int64_t n_cols, float a, mcd_stream_t stream) {
+    using namespace mcd;
+    if (!P || !S || n_rows < 1 || n_cols < 1 || ldp < n_cols || lds < n_cols) return MCD_ERR_INVALID_ARGUMENT;
+    if (P == S) return MCD_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned grid = static_cast<unsigned>(ceil_div<int64_t>(n_rows, kSoftmaxWarps));
+    const int threads = kSoftmaxWarps * 32;
+    const int nc = static_cast<int>(n_cols);
+    if (n_cols <= 32 * 4)
+        softmax_rows_kernel<4><<<grid, threads, 0, st>>>(P, ldp, S, lds, n_rows, nc, a);
+    else if (n_cols <= 32 * 24)
+        softmax_rows_kernel<24><<<grid, threads, 0, st>>>(P, ldp, S, lds, n_rows, nc, a);
+    else if (n_cols <= 32 * 64)
+        softmax_rows_kernel<64><<<grid, threads, 0, st>>>(P, ldp, S, lds, n_rows, nc, a);
+    else
+        softmax_rows_wide_kernel<<<grid, threads, 0, st>>>(P, ldp, S, lds, n_rows, n_cols, a);
+    return check_launch();
+}

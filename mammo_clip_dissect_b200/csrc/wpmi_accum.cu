@@ -1,0 +1,171 @@
+// K3 -- fused gather + rank-weighted log-sum: the body of soft-WPMI / WPMI
+// (replaces the per-neuron Python loop of concept_vit/similarity.py:59-65 and :85-89).
+//
+//   L[j,c] = sum_r log( 1 + p[r] * (S[idx[r,j], c] - 1) + min_prob )        (soft-WPMI)
+//   L[j,c] = sum_r log( S[idx[r,j], c] + min_prob )                         (WPMI, p == NULL)
+//
+// The per-element operation order is the reference's (sub, mul, add, add -- no FMA contraction)
+// so the rounding of `S - 1`, which dominates the reference's own fp32 noise, is reproduced; the
+// log is MUFU lg2 accumulated in the log2 domain and scaled by ln2 once per output.
+//
+// Work decomposition: a CTA of 192 threads handles NPB = 192/TPN neurons for one tile of
+// 4*TPN concepts; each thread owns 4 adjacent concepts (one 16-byte load per gathered row) and
+// walks the k gathered rows with kU independent loads in flight.  Concept tiles are the slowest
+// grid dimension so that, when a tile's slice of S fits in L2, the gathers of all neurons hit it
+// before the next slice is touched (S is 305 MB at N=100k: larger than the 126 MB L2).
+#include "common.cuh"
+
+namespace mcd {
+
+constexpr int kAccumThreads = 192;
+constexpr int kAccumMaxK = 512;
+
+template <bool SOFT>
+__device__ __forceinline__ float term_lg2(float s, float w, float eps) {
+    float v;
+    if (SOFT) {
+        v = __fsub_rn(s, 1.0f);
+        v = __fmul_rn(w, v);
+        v = __fadd_rn(1.0f, v);
+        v = __fadd_rn(v, eps);
+    } else {
+        v = __fadd_rn(s, eps);
+    }
+    return lg2_approx(v);
+}
+
+template <int TPN, int U, bool SOFT, bool VEC>
+__global__ void __launch_bounds__(kAccumThreads)
+wpmi_accum_kernel(const float *__restrict__ S, int64_t lds, int C, const int32_t *__restrict__ idx, int64_t K, int k,
+                  const float *__restrict__ p, float eps, float *__restrict__ L, int64_t ldl, int n_groups) {
+    constexpr int NPB = kAccumThreads / TPN;
+    __shared__ int32_t s_idx[NPB][kAccumMaxK];
+    __shared__ float s_p[kAccumMaxK];
+
+    const int tile = blockIdx.x / n_groups;
+    const int group = blockIdx.x - tile * n_groups;
+    const int64_t j0 = int64_t(group) * NPB;
+    const int tid = threadIdx.x;
+
+    for (int i = tid; i < NPB * k; i += kAccumThreads) {
+        const int n = i / k, r = i - n * k;
+        const int64_t j = j0 + n;
+        s_idx[n][r] = j < K ? idx[int64_t(r) * K + j] : 0;
+    }
+    if (SOFT)
+        for (int r = tid; r < k; r += kAccumThreads) s_p[r] = p[r];
+    __syncthreads();
+
+    const int n = tid / TPN;
+    const int tl = tid - n * TPN;
+    const int64_t j = j0 + n;
+    const int c0 = (tile * TPN + tl) * 4;
+    if (j >= K || c0 >= C) return;
+    const int nvalid = min(4, C - c0);
+    // a vector load may run past C only inside the row's padding (c0 + 4 <= lds is guaranteed by
+    // the host when VEC); the scalar path loads exactly the valid columns
+    const float *base = S + c0;
+    const int32_t *my_idx = s_idx[n];
+
+    float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+    int r = 0;
+    for (; r + U <= k; r += U) {
+        float4 s[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float *row = base + int64_t(my_idx[r + u]) * lds;
+            if (VEC) {
+                s[u] = ldg_nc_v4(row);
+            } else {
+                s[u].x = __ldg(row);
+                s[u].y = nvalid > 1 ? __ldg(row + 1) : 0.f;
+                s[u].z = nvalid > 2 ? __ldg(row + 2) : 0.f;
+                s[u].w = nvalid > 3 ? __ldg(row + 3) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const float w = SOFT ? s_p[r + u] : 0.f;
+            float *acc = (u & 1) ? acc1 : acc0;
+            acc[0] += term_lg2<SOFT>(s[u].x, w, eps);
+            acc[1] += term_lg2<SOFT>(s[u].y, w, eps);
+            acc[2] += term_lg2<SOFT>(s[u].z, w, eps);
+            acc[3] += term_lg2<SOFT>(s[u].w, w, eps);
+        }
+    }
+    for (; r < k; ++r) {
+        const float *row = base + int64_t(my_idx[r]) * lds;
+        float4 s;
+        if (VEC) {
+            s = ldg_nc_v4(row);
+        } else {
+            s.x = __ldg(row);
+            s.y = nvalid > 1 ? __ldg(row + 1) : 0.f;
+            s.z = nvalid > 2 ? __ldg(row + 2) : 0.f;
+            s.w = nvalid > 3 ? __ldg(row + 3) : 0.f;
+        }
+        const float w = SOFT ? s_p[r] : 0.f;
+        acc0[0] += term_lg2<SOFT>(s.x, w, eps);
+        acc0[1] += term_lg2<SOFT>(s.y, w, eps);
+        acc0[2] += term_lg2<SOFT>(s.z, w, eps);
+        acc0[3] += term_lg2<SOFT>(s.w, w, eps);
+    }
+    constexpr float kLn2 = 0.693147180559945309417f;
+    float *out = L + j * ldl + c0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+        if (e < nvalid) out[e] = (acc0[e] + acc1[e]) * kLn2;
+}
+
+template <int TPN, bool SOFT, bool VEC>
+static int launch_accum(const float *S, int64_t lds, int C, const int32_t *idx, int64_t K, int k, const float *p,
+                        float eps, float *L, int64_t ldl, cudaStream_t st) {
+    constexpr int NPB = kAccumThreads / TPN;
+    const int n_tiles = ceil_div(C, TPN * 4);
+    const int64_t n_groups = ceil_div<int64_t>(K, NPB);
+    const int64_t blocks = n_groups * n_tiles;
+    if (blocks > 0x7FFFFFFFll) return MCD_ERR_UNSUPPORTED;
+    wpmi_accum_kernel<TPN, 8, SOFT, VEC><<<static_cast<unsigned>(blocks), kAccumThreads, 0, st>>>(
+        S, lds, C, idx, K, k, p, eps, L, ldl, static_cast<int>(n_groups));
+    return check_launch();
+}
+
+template <bool SOFT, bool VEC>
+static int dispatch_tile(int tpn, const float *S, int64_t lds, int C, const int32_t *idx, int64_t K, int k,
+                         const float *p, float eps, float *L, int64_t ldl, cudaStream_t st) {
+    switch (tpn) {
+        case 192: return launch_accum<192, SOFT, VEC>(S, lds, C, idx, K, k, p, eps, L, ldl, st);
+        case 96: return launch_accum<96, SOFT, VEC>(S, lds, C, idx, K, k, p, eps, L, ldl, st);
+        case 64: return launch_accum<64, SOFT, VEC>(S, lds, C, idx, K, k, p, eps, L, ldl, st);
+        case 48: return launch_accum<48, SOFT, VEC>(S, lds, C, idx, K, k, p, eps, L, ldl, st);
+        default: return launch_accum<32, SOFT, VEC>(S, lds, C, idx, K, k, p, eps, L, ldl, st);
+    }
+}
+
+}  // namespace mcd
+
+extern "C" int mcd_wpmi_accum_f32(const float *S, int64_t lds, int64_t N, int64_t C, const int32_t *idx, int64_t K,
+                                  int64_t k, const float *p, float min_prob, float *L, int64_t ldl,
+                                  mcd_stream_t stream) {
+    using namespace mcd;
+    if (!S || !idx || !L || N < 1 || C < 1 || K < 1 || k < 1 || lds < C || ldl < C) return MCD_ERR_INVALID_ARGUMENT;
+    if (k > kAccumMaxK || C > (1 << 24)) return MCD_ERR_UNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // 16-byte loads need aligned rows and must stay inside a row (padding included)
+    const bool vec = (lds % 4 == 0) && (reinterpret_cast<uintptr_t>(S) % 16 == 0) && (ceil_div<int64_t>(C, 4) * 4 <= lds);
+    // threads per neuron: tunable "accum_tile" = concepts per tile (multiple of 4), default: whole row
+    int64_t tile_c = tunable(kAccumTile);
+    int tpn;
+    if (tile_c <= 0) tile_c = C;
+    const int64_t want = ceil_div<int64_t>(tile_c, 4);
+    if (want > 96) tpn = 192;
+    else if (want > 64) tpn = 96;
+    else if (want > 48) tpn = 64;
+    else if (want > 32) tpn = 48;
+    else tpn = 32;
+    const int Ci = static_cast<int>(C), ki = static_cast<int>(k);
+    if (p) return vec ? dispatch_tile<true, true>(tpn, S, lds, Ci, idx, K, ki, p, min_prob, L, ldl, st)
+                      : dispatch_tile<true, false>(tpn, S, lds, Ci, idx, K, ki, p, min_prob, L, ldl, st);
+    return vec ? dispatch_tile<false, true>(tpn, S, lds, Ci, idx, K, ki, p, min_prob, L, ldl, st)
+               : dispatch_tile<false, false>(tpn, S, lds, Ci, idx, K, ki, p, min_prob, L, ldl, st);
+}

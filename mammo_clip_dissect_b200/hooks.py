@@ -1,0 +1,66 @@
+"""The activation-summary forward hook with the reference's factory signature
+(``get_activation(outputs, mode)`` -> ``hook(model, input, output)``; reference
+concept_vit/utils.py:27-52 = og_utils.py:31-56 = CLIP_og_utils.py:13-36).
+
+4-D (NCHW) activations are pooled by the sm_100a kernel K4 (include/mcd_b200.h: mcd_pool_nchw);
+[B,T,D] activations yield the CLS token and [B,D] activations pass through, exactly as in the
+reference (those two branches move no arithmetic).  As in the reference, ``avg`` unwraps tuple
+outputs and ``max`` does not.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+_DTYPES = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
+
+
+def pool_nchw(x: torch.Tensor, mode: str) -> torch.Tensor:
+    """[B,C,H,W] CUDA tensor -> [B,C] spatial mean ('avg') or max ('max'), same dtype."""
+    if x.dim() != 4:
+        raise RuntimeError("pool_nchw expects a 4-D tensor")
+    if not x.is_cuda:
+        raise RuntimeError("mammo_clip_dissect_b200 has no CPU path: the hooked activation lives on %s" % x.device)
+    if x.dtype not in _DTYPES:
+        raise RuntimeError("pool_nchw supports float32/float16/bfloat16, got %s" % x.dtype)
+    B, C, H, W = x.shape
+    if B * C == 0 or H * W == 0:
+        raise RuntimeError("pool_nchw: empty activation %s" % (tuple(x.shape),))
+    x = x.detach()
+    if not x.is_contiguous():
+        x = x.contiguous()          # channels_last / sliced activations: one repack, then the NCHW kernel
+    lib = _lib.lib()
+    out = torch.empty((B, C), dtype=x.dtype, device=x.device)
+    need = lib.mcd_pool_nchw_workspace_bytes(B, C, H, W)
+    ws = torch.empty(max(int(need), 16), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        stream = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        code = lib.mcd_pool_nchw(ctypes.c_void_p(x.data_ptr()), _DTYPES[x.dtype], B, C, H, W,
+                                 _lib.POOL_MEAN if mode == "avg" else _lib.POOL_MAX,
+                                 ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(ws.data_ptr()), ws.numel(), stream)
+    _lib.check(code, "mcd_pool_nchw")
+    return out
+
+
+def get_activation(outputs, mode):
+    '''
+    mode: how to pool activations: one of avg, max
+    for fc or ViT neurons does no pooling
+    '''
+    if mode not in ("avg", "max"):
+        raise ValueError("mode must be 'avg' or 'max', got %r" % (mode,))
+
+    def hook(model, input, output):
+        if mode == "avg" and type(output) is tuple:
+            output = output[0]
+        ndim = len(output.shape)
+        if ndim == 4:      # CNN layers
+            outputs.append(pool_nchw(output, mode))
+        elif ndim == 3:    # ViT: CLS token
+            outputs.append(output[:, 0].clone())
+        elif ndim == 2:    # FC layers
+            outputs.append(output.detach())
+    return hook

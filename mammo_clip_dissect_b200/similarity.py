@@ -1,0 +1,252 @@
+"""B200-native neuron->concept scoring ops with the call surface of the reference's
+``concept_vit/similarity.py`` (same names, positional order, defaults and return shape), so
+``eval("similarity.<name>")`` in the reference drivers (describe_clip_neurons.py:41) resolves to
+these functions unchanged.
+
+    soft_wpmi            reference similarity.py:49-73
+    wpmi                 reference similarity.py:75-97
+    cos_similarity_cubed reference similarity.py:7-31
+    cos_similarity       reference similarity.py:33-47
+
+The arithmetic runs in hand-written sm_100a kernels behind the C ABI of include/mcd_b200.h
+(ctypes, see _lib.py).  PyTorch is used for device buffers and the current stream only.
+There is no CPU path: ``device`` must name a CUDA device and the library must be built.
+
+Differences from the reference, all supersets or stated rules:
+  * top-k ties: value desc, then probe-image index asc; NaN largest; -0.0 == +0.0
+    (torch.topk leaves both tie order and tie membership unspecified);
+  * ``top_k`` is accepted and ignored by the cos functions (the reference's utils.py:602 passes it
+    to every similarity function and its cos functions raise TypeError on it);
+  * nothing is printed, no tqdm bar, no empty_cache() calls.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+__all__ = ["soft_wpmi", "wpmi", "cos_similarity", "cos_similarity_cubed", "cos_similarity_cubed_single",
+           "topk_cols", "concept_probabilities", "pmi_scores"]
+
+_S_ALIGN = 32  # leading dimension of the probability matrix: rows start on 128-byte boundaries
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _cuda_device(device):
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError(
+            "mammo_clip_dissect_b200 has no CPU path: device=%r; pass a CUDA device (B200, sm_100a)" % (device,))
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def _as_f32_matrix(t, dev, name):
+    """fp32, on `dev`, unit stride along the last axis (any row stride). Never modifies the input."""
+    if t.dim() != 2:
+        raise RuntimeError("%s must be 2-D, got shape %s" % (name, tuple(t.shape)))
+    if t.device != dev:
+        t = t.to(dev, non_blocking=True)
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.stride(1) != 1 or (t.shape[0] > 1 and t.stride(0) < t.shape[1]):
+        t = t.contiguous()
+    return t
+
+
+def _ld(t):
+    return t.stride(0) if t.shape[0] > 1 else max(t.shape[1], 1)
+
+
+def _workspace(nbytes, dev):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
+
+
+# ------------------------------------------------------------------------------------------------
+# building blocks (also used by the multi-GPU path and the tests)
+# ------------------------------------------------------------------------------------------------
+def concept_probabilities(clip_feats, a, device="cuda"):
+    """S = softmax(a * clip_feats, dim=1) as a [N, C] view of a row-padded buffer (K1b)."""
+    dev = _cuda_device(device)
+    P = _as_f32_matrix(clip_feats, dev, "clip_feats")
+    N, C = P.shape
+    if N < 1 or C < 1:
+        raise RuntimeError("clip_feats must be non-empty")
+    lds = (C + _S_ALIGN - 1) // _S_ALIGN * _S_ALIGN
+    buf = torch.empty((N, lds), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().mcd_softmax_rows_f32(_ptr(P), _ld(P), _ptr(buf), lds, N, C, float(a), _stream(dev)),
+                   "mcd_softmax_rows_f32")
+    return buf[:, :C]
+
+
+def topk_cols(target_feats, k, device="cuda", want_values=False, want_int32=False):
+    """Per-column top-k over axis 0 (K2).  Returns int64 indices [k, K] (like torch.topk(..., dim=0)[1]);
+    optionally (values, indices) and/or an extra int32 copy used by the accumulate kernel."""
+    dev = _cuda_device(device)
+    A = _as_f32_matrix(target_feats, dev, "target_feats")
+    N, K = A.shape
+    k = int(k)
+    if k < 1 or k > N:
+        raise RuntimeError("selected index k out of range")   # torch.topk's message for k > N
+    if K < 1:
+        raise RuntimeError("target_feats has no neurons")
+    lib = _lib.lib()
+    idx64 = torch.empty((k, K), dtype=torch.int64, device=dev)
+    idx32 = torch.empty((k, K), dtype=torch.int32, device=dev) if want_int32 else None
+    vals = torch.empty((k, K), dtype=torch.float32, device=dev) if want_values else None
+    need = lib.mcd_topk_cols_workspace_bytes(N, K, k)
+    if need == 0:
+        raise RuntimeError("top_k=%d is outside the supported range of the column top-k kernel (<= 496)" % k)
+    ws = _workspace(need, dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.mcd_topk_cols_f32(_ptr(A), _ld(A), N, K, k, _ptr(idx64), _ptr(idx32), _ptr(vals), _ptr(ws),
+                                         ws.numel(), _stream(dev)), "mcd_topk_cols_f32")
+    out = (vals, idx64) if want_values else idx64
+    return (out, idx32) if want_int32 else out
+
+
+def _topk_int32(A, k, dev):
+    """int32 indices only (what K3 consumes)."""
+    N, K = A.shape
+    if k < 1 or k > N:
+        raise RuntimeError("selected index k out of range")
+    lib = _lib.lib()
+    idx32 = torch.empty((k, K), dtype=torch.int32, device=dev)
+    need = lib.mcd_topk_cols_workspace_bytes(N, K, k)
+    if need == 0:
+        raise RuntimeError("top_k=%d is outside the supported range of the column top-k kernel (<= 496)" % k)
+    ws = _workspace(need, dev)
+    _lib.check(lib.mcd_topk_cols_f32(_ptr(A), _ld(A), N, K, k, None, _ptr(idx32), None, _ptr(ws), ws.numel(),
+                                     _stream(dev)), "mcd_topk_cols_f32")
+    return idx32
+
+
+def _reference_ramp(top_k, p_start, p_end):
+    """The rank weights with the reference's exact fp32 rounding sequence (similarity.py:58);
+    evaluated with the same host-side tensor expression, then shipped to the device."""
+    steps = torch.arange(start=0, end=top_k) / top_k * (p_start - p_end)
+    return (p_start - steps).to(torch.float32).contiguous()
+
+
+def log_sums(S, idx32, weights, min_prob, out=None):
+    """K3: L[j,c] = sum_r log(1 + w_r (S[idx[r,j],c]-1) + eps)  (weights=None: sum_r log(S+eps))."""
+    dev = S.device
+    N, C = S.shape
+    k, K = idx32.shape
+    if out is None:
+        out = torch.empty((K, C), dtype=torch.float32, device=dev)
+    _lib.check(_lib.lib().mcd_wpmi_accum_f32(_ptr(S), _ld(S), N, C, _ptr(idx32), K, k, _ptr(weights), float(min_prob),
+                                             _ptr(out), _ld(out), _stream(dev)), "mcd_wpmi_accum_f32")
+    return out
+
+
+def lse_partials(L):
+    """K3b part 1: per-256-neuron-block (max, sum exp) partials [nb, 2, C]."""
+    K, C = L.shape
+    nb = (K + _lib.LSE_BLOCK - 1) // _lib.LSE_BLOCK
+    part = torch.empty((nb, 2, C), dtype=torch.float32, device=L.device)
+    _lib.check(_lib.lib().mcd_col_lse_partials_f32(_ptr(L), _ld(L), K, C, _ptr(part), _stream(L.device)),
+               "mcd_col_lse_partials_f32")
+    return part
+
+
+def pmi_finalize(L, partials_all, K_total, lam, out=None):
+    """K3b part 2: out = L - lam * (logsumexp over ALL blocks - log K_total).  In place by default."""
+    K, C = L.shape
+    if out is None:
+        out = L
+    prob_d = torch.empty((C,), dtype=torch.float32, device=L.device)
+    _lib.check(_lib.lib().mcd_pmi_finalize_f32(_ptr(L), _ld(L), K, C, _ptr(partials_all), partials_all.shape[0],
+                                               int(K_total), float(lam), _ptr(prob_d), _ptr(out), _ld(out),
+                                               _stream(L.device)), "mcd_pmi_finalize_f32")
+    return out, prob_d
+
+
+def pmi_scores(clip_feats, target_feats, top_k, a, lam, device, min_prob, ramp, return_parts=False):
+    """Shared body of soft_wpmi / wpmi on one device."""
+    dev = _cuda_device(device)
+    with torch.no_grad(), torch.cuda.device(dev):
+        A = _as_f32_matrix(target_feats, dev, "target_feats")
+        if clip_feats.dim() != 2 or clip_feats.shape[0] != A.shape[0]:
+            raise RuntimeError("clip_feats %s and target_feats %s must share the probe-image axis"
+                               % (tuple(clip_feats.shape), tuple(A.shape)))
+        top_k = int(top_k)
+        S = concept_probabilities(clip_feats, a, dev)
+        idx32 = _topk_int32(A, top_k, dev)
+        weights = ramp.to(dev) if ramp is not None else None
+        L = log_sums(S, idx32, weights, min_prob)
+        if return_parts:
+            raw = L.clone()
+        part = lse_partials(L)
+        out, _ = pmi_finalize(L, part, A.shape[1], lam)
+    if return_parts:
+        return out, raw, idx32
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's call surface
+# ------------------------------------------------------------------------------------------------
+def soft_wpmi(clip_feats, target_feats, top_k=100, a=10, lam=1, device='cuda',
+              min_prob=1e-7, p_start=0.998, p_end=0.97):
+    """Soft-WPMI neuron x concept scores [K, C] on `device` (reference similarity.py:49-73)."""
+    return pmi_scores(clip_feats, target_feats, top_k, a, lam, device, min_prob,
+                      _reference_ramp(int(top_k), p_start, p_end))
+
+
+def wpmi(clip_feats, target_feats, top_k=28, a=2, lam=0.6, device='cuda', min_prob=1e-7):
+    """WPMI neuron x concept scores [K, C] on `device` (reference similarity.py:75-97)."""
+    return pmi_scores(clip_feats, target_feats, top_k, a, lam, device, min_prob, None)
+
+
+def _cos(clip_feats, target_feats, device, cubed, min_norm):
+    dev = _cuda_device(device)
+    lib = _lib.lib()
+    with torch.no_grad(), torch.cuda.device(dev):
+        P = _as_f32_matrix(clip_feats, dev, "clip_feats")
+        A = _as_f32_matrix(target_feats, dev, "target_feats")
+        if P.shape[0] != A.shape[0]:
+            raise RuntimeError("clip_feats and target_feats must share the probe-image axis")
+        N, C = P.shape
+        K = A.shape[1]
+        st = _stream(dev)
+        stats = torch.empty((2, C + K), dtype=torch.float32, device=dev)
+        meanP, normP, meanA, normA = stats[0, :C], stats[1, :C], stats[0, C:], stats[1, C:]
+        _lib.check(lib.mcd_col_stats_f32(_ptr(P), _ld(P), N, C, int(cubed), float(min_norm), _ptr(meanP), _ptr(normP),
+                                         st), "mcd_col_stats_f32")
+        _lib.check(lib.mcd_col_stats_f32(_ptr(A), _ld(A), N, K, int(cubed), float(min_norm), _ptr(meanA), _ptr(normA),
+                                         st), "mcd_col_stats_f32")
+        out = torch.empty((K, C), dtype=torch.float32, device=dev)
+        _lib.check(lib.mcd_cos_matmul_f32(_ptr(A), _ld(A), _ptr(meanA), _ptr(normA), _ptr(P), _ld(P), _ptr(meanP),
+                                          _ptr(normP), N, K, C, int(cubed), _ptr(out), _ld(out), st),
+                   "mcd_cos_matmul_f32")
+    return out
+
+
+def cos_similarity_cubed(clip_feats, target_feats, device='cuda', batch_size=10000, min_norm=1e-3, top_k=None):
+    """Reference similarity.py:7-31.  `batch_size` only blocked the reference's matmul; ignored."""
+    return _cos(clip_feats, target_feats, device, True, min_norm)
+
+
+def cos_similarity(clip_feats, target_feats, device='cuda', top_k=None):
+    """Reference similarity.py:33-47 (zero columns give NaN, as there)."""
+    return _cos(clip_feats, target_feats, device, False, 0.0)
+
+
+def cos_similarity_cubed_single(clip_feats, target_feats, device='cuda', min_norm=1e-3):
+    """NOT in the reference tree (named by BASELINE.json's north_star; see SURVEY.md section 8 a-note).
+    Convenience: the matched-pair (diagonal) cos^3 similarity for equally-shaped inputs."""
+    if tuple(clip_feats.shape) != tuple(target_feats.shape):
+        raise RuntimeError("cos_similarity_cubed_single needs equally shaped inputs")
+    return torch.diagonal(_cos(clip_feats, target_feats, device, True, min_norm)).clone()

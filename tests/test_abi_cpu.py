@@ -1,0 +1,107 @@
+"""CPU-side checks of the boundary: the C-ABI library loads, exports every symbol that
+include/mcd_b200.h declares, and the host mirror refuses to run without CUDA (no fallback).
+No kernel is launched here."""
+import ctypes
+import inspect
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+from mammo_clip_dissect_b200 import _lib, hooks, similarity
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    return _lib.lib()
+
+
+def test_header_and_bindings_agree():
+    assert _lib.declared_symbols() == sorted(_lib.SIGNATURES)
+
+
+def test_library_exports_every_declared_symbol(lib):
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in _lib.declared_symbols():
+        assert hasattr(raw, name), name
+    assert lib.mcd_abi_version() == 1
+    assert b"sm_100a" in lib.mcd_build_info()
+    assert lib.mcd_strerror(0) == b"ok" and lib.mcd_strerror(-3) == b"workspace too small"
+
+
+def test_cubin_is_sm100a_only():
+    out = subprocess.run(["cuobjdump", "--list-elf", _lib.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump unavailable")
+    archs = {ln.split(".")[-2] for ln in out.stdout.splitlines() if ".cubin" in ln}
+    assert archs == {"sm_100a"}, archs
+
+
+def test_workspace_queries_are_pure_host_functions(lib):
+    # headline shape: 100k probes x 32768 neurons, k = 100
+    ws = lib.mcd_topk_cols_workspace_bytes(100_000, 32_768, 100)
+    assert ws > 0 and ws % (100 * 32_768 * 8) == 0
+    assert lib.mcd_topk_cols_workspace_bytes(50, 8, 100) == 0          # k > N
+    assert lib.mcd_topk_cols_workspace_bytes(10_000, 8, 1000) == 0     # beyond the heap kernels
+    assert lib.mcd_pool_nchw_workspace_bytes(4, 24, 760, 456) > 0      # large planes are split
+    assert lib.mcd_pool_nchw_workspace_bytes(4, 512, 48, 29) == 0      # warp-per-plane
+    assert lib.mcd_gemm_nt_softmax_workspace_bytes(2000, 763, 512) >= (2000 + 763) * 4
+
+
+def test_argument_validation_happens_before_any_launch(lib):
+    n0 = lib.mcd_launch_count()
+    assert lib.mcd_softmax_rows_f32(None, 4, None, 4, 1, 4, 1.0, None) == -1
+    assert lib.mcd_topk_cols_f32(None, 4, 10, 4, 2, None, None, None, None, 0, None) == -1
+    assert lib.mcd_wpmi_accum_f32(None, 4, 4, 4, None, 1, 1, None, 1e-7, None, 4, None) == -1
+    assert lib.mcd_pool_nchw(None, 0, 1, 1, 1, 1, 0, None, None, 0, None) == -1
+    assert lib.mcd_set_tunable(b"no_such_knob", 1) == -1
+    assert lib.mcd_launch_count() == n0
+
+
+def test_reference_call_surface():
+    """Names, positional order and defaults of reference concept_vit/similarity.py."""
+    def params(fn):
+        return [(p.name, p.default) for p in inspect.signature(fn).parameters.values()]
+    E = inspect.Parameter.empty
+    assert params(similarity.soft_wpmi) == [("clip_feats", E), ("target_feats", E), ("top_k", 100), ("a", 10),
+                                            ("lam", 1), ("device", "cuda"), ("min_prob", 1e-7),
+                                            ("p_start", 0.998), ("p_end", 0.97)]
+    assert params(similarity.wpmi) == [("clip_feats", E), ("target_feats", E), ("top_k", 28), ("a", 2),
+                                       ("lam", 0.6), ("device", "cuda"), ("min_prob", 1e-7)]
+    assert params(similarity.cos_similarity_cubed)[:5] == [("clip_feats", E), ("target_feats", E), ("device", "cuda"),
+                                                           ("batch_size", 10000), ("min_norm", 1e-3)]
+    assert params(similarity.cos_similarity)[:3] == [("clip_feats", E), ("target_feats", E), ("device", "cuda")]
+    assert params(hooks.get_activation) == [("outputs", E), ("mode", E)]
+
+
+def test_no_cpu_fallback():
+    P, A = torch.zeros(8, 3), torch.zeros(8, 2)
+    for fn in (similarity.soft_wpmi, similarity.wpmi, similarity.cos_similarity, similarity.cos_similarity_cubed):
+        with pytest.raises(RuntimeError, match="no CPU path"):
+            fn(P, A, device="cpu")
+    got = []
+    hook = hooks.get_activation(got, "avg")
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        hook(None, None, torch.zeros(2, 3, 4, 5))
+    hook(None, None, torch.ones(2, 5, 4))          # ViT / FC branches move no arithmetic
+    hook(None, None, (torch.ones(2, 7), "x"))
+    assert got[0].shape == (2, 4) and got[1].shape == (2, 7)
+    with pytest.raises(ValueError):
+        hooks.get_activation([], "median")
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.dirname(_lib.__file__)
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in text and "from oracle" not in text, f
+    code = "import sys; import mammo_clip_dissect_b200.similarity, mammo_clip_dissect_b200.hooks, " \
+           "mammo_clip_dissect_b200.features; sys.exit(any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules))"
+    assert subprocess.run([sys.executable, "-c", code], cwd=os.path.dirname(pkg)).returncode == 0

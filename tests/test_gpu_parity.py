@@ -1,0 +1,341 @@
+"""GPU parity: the CUDA path (through the C ABI, via the host mirror of the reference surface)
+against the CPU oracle and the golden fixtures produced by the reference itself.
+
+Tolerances (SURVEY.md section 8a / DESIGN.md "Numerics"):
+  * top-k indices: bit-exact under the stated total order;
+  * pre-normalisation scores L: |L - L_ref| <= 1e-5 * |L_ref| element-wise;
+  * final scores: |out - out_ref| <= 1e-5 * max|L|  (out is a difference of O(|L|) numbers);
+  * per-neuron top concept: identical wherever the fp64 top-1/top-2 gap exceeds that noise.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import similarity_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def sim():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    from mammo_clip_dissect_b200 import _lib, similarity
+    assert _lib.lib().mcd_device_check() == 0, "not an sm_100 device"
+    return similarity
+
+
+def gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def check_scores(out, L, ref_out, ref_L, f64_out=None, label=""):
+    out, L = out.cpu(), L.cpu()
+    scale = ref_L.abs().max().item()
+    relL = ((L - ref_L).abs() / ref_L.abs().clamp_min(1e-30)).max().item()
+    assert relL <= 1e-5, "%s: L rel err %.3g" % (label, relL)
+    err = (out - ref_out).abs().max().item()
+    assert err <= 1e-5 * scale, "%s: out abs err %.3g > %.3g" % (label, err, 1e-5 * scale)
+    # top concept per neuron: mismatches are only acceptable inside the fp32 noise band
+    mism = (out.argmax(1) != ref_out.argmax(1)).nonzero().flatten()
+    truth = f64_out if f64_out is not None else ref_out.double()
+    for j in mism.tolist():
+        top2 = truth[j].topk(2).values
+        assert (top2[0] - top2[1]).item() <= 2e-5 * scale, "%s: neuron %d top concept differs outside noise" % (label, j)
+    return err, len(mism)
+
+
+# ------------------------------------------------------------------------------------------------
+# K2: column top-k
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,K,k", [(2000, 256, 100), (777, 33, 28), (300, 7, 1), (130, 33, 130), (5000, 40, 10),
+                                   (1024, 64, 48), (1500, 129, 112), (3000, 68, 200), (4000, 36, 300),
+                                   (2048, 12, 496), (64, 4, 64)])
+def test_topk_tie_free(sim, N, K, k):
+    A = torch.randn(N, K, generator=gen(N + K + k))
+    vals, idx = sim.topk_cols(A, k, device=DEV, want_values=True)
+    rv, ri = orc.topk_cols(A, k)
+    assert torch.equal(idx.cpu(), ri)
+    assert torch.equal(vals.cpu(), rv)
+    assert torch.equal(ri, torch.topk(A, k, dim=0)[1])         # tie-free: the rule coincides with torch.topk
+
+
+@pytest.mark.parametrize("kind", ["round1", "relu", "const", "nan_inf", "signed_zero", "sorted_up", "sorted_down"])
+def test_topk_ties_and_specials(sim, kind):
+    N, K, k = 3000, 96, 100
+    A = torch.randn(N, K, generator=gen(5))
+    if kind == "round1":
+        A = (A * 10).round() / 10
+    elif kind == "relu":
+        A = torch.relu(A - 1.5)                    # ~93 % exact zeros: the k-th value is a tie
+    elif kind == "const":
+        A = torch.full((N, K), 0.25)
+    elif kind == "nan_inf":
+        m = torch.rand(N, K, generator=gen(6))
+        A[m < 0.01] = float("nan")
+        A[(m >= 0.01) & (m < 0.02)] = float("inf")
+        A[(m >= 0.02) & (m < 0.03)] = float("-inf")
+        A[:, 3] = float("nan")
+        A[:, 4] = float("-inf")
+    elif kind == "signed_zero":
+        A = torch.where(torch.rand(N, K, generator=gen(7)) < 0.5, torch.tensor(-0.0), torch.tensor(0.0))
+        A[::7] = -1.0
+    elif kind == "sorted_up":
+        A = torch.sort(A, dim=0).values            # every element beats the running threshold
+    elif kind == "sorted_down":
+        A = torch.sort(A, dim=0, descending=True).values
+    idx = sim.topk_cols(A, k, device=DEV)
+    assert torch.equal(idx.cpu(), orc.topk_cols(A, k)[1]), kind
+
+
+def test_topk_strided_unaligned_and_forced_splits(sim):
+    from mammo_clip_dissect_b200 import _lib
+    base = torch.randn(2500, 203, generator=gen(9)).to(DEV)
+    A = base[:, 3:200]                             # row stride 203, 12-byte offset: element-copy producer path
+    ref = orc.topk_cols(A.cpu(), 100)[1]
+    assert torch.equal(sim.topk_cols(A, 100, device=DEV).cpu(), ref)
+    B = torch.randn(6000, 260, generator=gen(10))
+    refB = orc.topk_cols(B, 100)[1]
+    try:
+        for splits in (1, 2, 7, 15):
+            _lib.set_tunable("topk_splits", splits)
+            assert torch.equal(sim.topk_cols(B, 100, device=DEV).cpu(), refB), splits
+    finally:
+        _lib.set_tunable("topk_splits", 0)
+
+
+def test_topk_errors(sim):
+    A = torch.randn(50, 4)
+    with pytest.raises(RuntimeError):
+        sim.topk_cols(A, 51, device=DEV)
+    with pytest.raises(RuntimeError):
+        sim.topk_cols(A, 0, device=DEV)
+    with pytest.raises(RuntimeError):
+        sim.soft_wpmi(torch.randn(50, 9), A, top_k=100, device=DEV)    # reference: torch.topk raises when k > N
+
+
+# ------------------------------------------------------------------------------------------------
+# K1b softmax, K3 accumulate, K3b log-sum-exp, and the two scoring functions end to end
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,C,a", [(257, 763, 10.0), (64, 37, 2.0), (33, 128, 10.0), (9, 1500, 4.0), (5, 2500, 1.0)])
+def test_softmax_rows(sim, N, C, a):
+    P = torch.randn(N, C, generator=gen(C)) * 0.2
+    S = sim.concept_probabilities(P, a, device=DEV)
+    ref = torch.softmax(a * P, dim=1)
+    assert S.shape == (N, C)
+    assert ((S.cpu() - ref).abs() <= 4e-7 * ref + 1e-12).all()
+    assert S.stride(0) % 32 == 0 and float(S.cpu().sum(1).sub(1).abs().max()) < 1e-5
+
+
+def test_golden_kat(sim, golden):
+    g = golden("kat_8x3.npz")
+    cf, tg = g["clip_feats"], g["target_feats"]
+    assert torch.allclose(sim.soft_wpmi(cf, tg, top_k=4, device=DEV).cpu(), g["soft_wpmi_k4"], rtol=0, atol=5e-6)
+    assert torch.allclose(sim.wpmi(cf, tg, top_k=4, device=DEV).cpu(), g["wpmi_k4"], rtol=0, atol=5e-6)
+    assert torch.allclose(sim.cos_similarity_cubed(cf, tg, device=DEV).cpu(), g["cos_cubed"], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(sim.cos_similarity(cf, tg, device=DEV).cpu(), g["cos"], rtol=1e-5, atol=1e-6)
+
+
+def test_golden_c1_slice(sim, golden):
+    """The reference's own outputs (fp32 and fp64 runs) on a 256 x 763 x 48 slice of config c1."""
+    g = golden("c1_slice_256x763x48.npz")
+    P, A = g["clip_feats"], g["target_feats"]
+    out, L, idx = sim.pmi_scores(P, A, 100, 10, 1, DEV, 1e-7, sim._reference_ramp(100, 0.998, 0.97), return_parts=True)
+    assert torch.equal(idx.cpu().long(), g["topk100"])
+    _, refL, _ = orc.soft_wpmi(P, A, return_parts=True)
+    err, mism = check_scores(out, L, g["soft_wpmi"], refL, g["soft_wpmi_f64"], "c1 slice soft_wpmi")
+    ours_vs_truth = (out.cpu().double() - g["soft_wpmi_f64"]).abs().max().item()
+    ref_vs_truth = (g["soft_wpmi"].double() - g["soft_wpmi_f64"]).abs().max().item()
+    print("soft_wpmi vs fp64 truth: ours %.3g, reference fp32 %.3g; vs reference %.3g; argmax mismatches %d"
+          % (ours_vs_truth, ref_vs_truth, err, mism))
+    assert ours_vs_truth <= 3 * ref_vs_truth + 1e-4
+    for key, kw in (("wpmi", {}), ("wpmi_k100", dict(top_k=100))):
+        w = sim.wpmi(P, A, device=DEV, **kw).cpu()
+        scale = orc.wpmi(P, A, return_parts=True, **kw)[1].abs().max().item()
+        assert (w - g[key]).abs().max().item() <= 1e-5 * scale, key
+    assert torch.allclose(sim.cos_similarity_cubed(P, A, device=DEV).cpu(), g["cos_cubed"], rtol=1e-4, atol=2e-6)
+    assert torch.allclose(sim.cos_similarity(P, A, device=DEV).cpu(), g["cos"], rtol=1e-4, atol=2e-6)
+
+
+@pytest.mark.parametrize("key,kw", [
+    ("soft_wpmi_k10", dict(top_k=10)),
+    ("soft_wpmi_k1", dict(top_k=1)),
+    ("soft_wpmi_kN", dict(top_k=130)),
+    ("soft_wpmi_params", dict(top_k=17, a=4, lam=0.5, min_prob=1e-6, p_start=0.9, p_end=0.6)),
+])
+def test_golden_odd_sizes(sim, golden, key, kw):
+    g = golden("odd_130x37x33.npz")
+    P, A = g["clip_feats"], g["target_feats"]
+    scale = orc.soft_wpmi(P, A, return_parts=True, **kw)[1].abs().max().item()
+    got = sim.soft_wpmi(P, A, device=DEV, **kw).cpu()
+    assert (got - g[key]).abs().max().item() <= 1e-5 * max(scale, 1.0), key
+
+
+def test_golden_odd_misc(sim, golden):
+    g = golden("odd_130x37x33.npz")
+    P, A = g["clip_feats"], g["target_feats"]
+    k1 = sim.soft_wpmi(P, A[:, :1], top_k=10, device=DEV).cpu()          # a single neuron: log p(d) == its own score
+    assert k1.shape == (1, 37) and (k1 - g["soft_wpmi_K1"]).abs().max().item() <= 1e-4
+    assert (sim.wpmi(P, A, device=DEV).cpu() - g["wpmi_default"]).abs().max().item() <= 2e-3
+    assert (sim.wpmi(P, A, top_k=5, a=7, lam=1.5, min_prob=1e-5, device=DEV).cpu() - g["wpmi_params"]).abs().max().item() <= 1e-3
+
+
+def test_config_c1_full(sim):
+    """BASELINE config c1: clip_feats 2000 x 763, target_feats 2000 x 2048, top_k = 100."""
+    I = torch.randn(2000, 512, generator=gen(0))
+    T = torch.randn(763, 512, generator=gen(1))
+    P = orc.similarity_matrix(I, T)
+    A = torch.randn(2000, 2048, generator=gen(2))
+    out, L, idx = sim.pmi_scores(P, A, 100, 10, 1, DEV, 1e-7, sim._reference_ramp(100, 0.998, 0.97), return_parts=True)
+    ref, refL, ridx = orc.soft_wpmi_fast(P, A, return_parts=True)
+    assert torch.equal(idx.cpu().long(), ridx)
+    f64 = orc.soft_wpmi_fast(P, A, dtype=torch.float64)
+    err, mism = check_scores(out, L, ref, refL, f64, "c1")
+    print("c1: max |out - oracle| = %.3g, argmax mismatches within noise: %d / 2048" % (err, mism))
+    # device-resident, non-contiguous and half-precision inputs go through the same path
+    out2 = sim.soft_wpmi(P.to(DEV), A.to(DEV), device=DEV)
+    assert torch.equal(out2, out)
+    wide = torch.zeros(2000, 2100)
+    wide[:, 10:2058] = A
+    assert torch.equal(sim.soft_wpmi(P, wide[:, 10:2058], device=DEV), out)
+    h = sim.soft_wpmi(P, A.half(), device=DEV).cpu()
+    assert (h - orc.soft_wpmi_fast(P, A.half().float())).abs().max().item() <= 1e-5 * refL.abs().max().item()
+    assert A.dtype == torch.float32 and torch.equal(A, torch.randn(2000, 2048, generator=gen(2)))   # inputs untouched
+
+
+@pytest.mark.parametrize("tile", [0, 128, 192, 256, 384])
+def test_accumulate_concept_tiles(sim, tile):
+    from mammo_clip_dissect_b200 import _lib
+    P = torch.randn(500, 763, generator=gen(3)) * 0.05
+    A = torch.randn(500, 70, generator=gen(4))
+    ref, refL, _ = orc.soft_wpmi_fast(P, A, top_k=50, return_parts=True)
+    try:
+        _lib.set_tunable("accum_tile", tile)
+        out = sim.soft_wpmi(P, A, top_k=50, device=DEV).cpu()
+    finally:
+        _lib.set_tunable("accum_tile", 0)
+    assert (out - ref).abs().max().item() <= 1e-5 * refL.abs().max().item()
+
+
+def test_tied_activations_use_the_stated_rule(sim):
+    """relu activations: scores must match the oracle run with the stated tie order spliced in."""
+    P = torch.randn(800, 763, generator=gen(12)) * 0.05
+    A = torch.relu(torch.randn(800, 64, generator=gen(13)) - 1.0)
+    ref, refL, ridx = orc.soft_wpmi_fast(P, A, return_parts=True)
+    out, L, idx = sim.pmi_scores(P, A, 100, 10, 1, DEV, 1e-7, sim._reference_ramp(100, 0.998, 0.97), return_parts=True)
+    assert torch.equal(idx.cpu().long(), ridx)
+    check_scores(out, L, ref, refL, None, "relu ties")
+
+
+def test_lse_blocks_are_sharding_invariant(sim):
+    """Concatenating per-shard partials in block order reproduces the unsharded result bit for bit."""
+    L = (-400 - 60 * torch.rand(1280, 763, generator=gen(14))).to(DEV)
+    full = sim.lse_partials(L)
+    halves = torch.cat([sim.lse_partials(L[:512].contiguous()), sim.lse_partials(L[512:].contiguous())])
+    assert torch.equal(full, halves)
+    out_full, pd = sim.pmi_finalize(L.clone(), full, 1280, 1.0)
+    out_a, _ = sim.pmi_finalize(L[:512].clone(), halves, 1280, 1.0)
+    out_b, _ = sim.pmi_finalize(L[512:].clone(), halves, 1280, 1.0)
+    assert torch.equal(out_full, torch.cat([out_a, out_b]))
+    ref_pd = torch.logsumexp(L.double().cpu(), dim=0) - np.log(1280)
+    assert (pd.cpu().double() - ref_pd).abs().max().item() < 1e-4
+    assert torch.allclose(orc.lse_block_partials(L.cpu())[:, 0], full.cpu()[:, 0])
+
+
+# ------------------------------------------------------------------------------------------------
+# K1 similarity matrix, K4 hook
+# ------------------------------------------------------------------------------------------------
+def test_similarity_matrix(sim, golden):
+    from mammo_clip_dissect_b200 import features
+    g = golden("itt_40x29.npz")
+    I, T = g["image_features"], g["text_features"]
+    keepI = I.clone()
+    P = features.similarity_matrix(I, T, device=DEV)
+    assert torch.allclose(P.cpu(), g["clip_feats"], rtol=0, atol=2e-6)
+    assert torch.equal(I, keepI)                                   # the reference normalises in place; we must not
+    I2 = torch.randn(1000, 512, generator=gen(20))
+    T2 = torch.randn(763, 512, generator=gen(21))
+    P2, S2 = features.similarity_matrix(I2, T2, device=DEV, softmax_scale=10)
+    ref = orc.similarity_matrix(I2.double(), T2.double()) if False else (
+        (I2.double() / I2.double().norm(dim=-1, keepdim=True)) @ (T2.double() / T2.double().norm(dim=-1, keepdim=True)).T)
+    assert (P2.cpu().double() - ref).abs().max().item() <= 2e-6
+    refS = torch.softmax(10 * ref, dim=1)
+    assert ((S2.cpu().double() - refS).abs() / refS).max().item() <= 1e-5
+
+
+def test_hook_matches_reference(sim, golden):
+    from mammo_clip_dissect_b200.hooks import get_activation
+    g = golden("hook_cases.npz")
+    for mode, n in (("avg", 4), ("max", 3)):
+        got = []
+        hook = get_activation(got, mode)
+        hook(None, None, g["x4"].to(DEV)); hook(None, None, g["x3"].to(DEV)); hook(None, None, g["x2"].to(DEV))
+        if mode == "avg":
+            hook(None, None, (g["x4"].to(DEV), "ignored"))
+        assert len(got) == n
+        for i, t in enumerate(got):
+            want = g["%s_%d" % (mode, i)]
+            assert t.shape == want.shape and t.is_cuda
+            assert torch.allclose(t.cpu(), want, rtol=0, atol=1e-6 if mode == "avg" else 0)
+    with pytest.raises(Exception):
+        get_activation([], "max")(None, None, (g["x4"].to(DEV),))
+
+
+@pytest.mark.parametrize("shape", [(4, 24, 760, 456), (3, 40, 380, 228), (5, 128, 95, 57), (7, 304, 48, 29),
+                                   (2, 3, 1, 1), (1, 5, 7, 9), (2, 512, 33, 31)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+def test_pooling_shapes(sim, shape, dtype):
+    from mammo_clip_dissect_b200.hooks import pool_nchw
+    if dtype != torch.float32 and shape[2] > 400:
+        pytest.skip("large planes: fp32 only")
+    x = (torch.randn(*shape, generator=gen(sum(shape))) + 0.3).to(dtype)
+    xd = x.to(DEV)
+    mean = pool_nchw(xd, "avg").cpu()
+    ref = x.double().mean(dim=[2, 3])
+    tol = 1e-5 * x.double().abs().mean().item() if dtype == torch.float32 else 4e-3
+    assert mean.dtype == dtype and (mean.double() - ref).abs().max().item() <= tol
+    mx = pool_nchw(xd, "max").cpu()
+    assert torch.equal(mx, x.amax(dim=[2, 3]))
+    # views: channels_last and a sliced batch go through the same kernel after one repack
+    assert torch.equal(pool_nchw(xd.to(memory_format=torch.channels_last), "max").cpu(), mx)
+    if shape[0] > 1:
+        assert torch.equal(pool_nchw(xd[1:], "max").cpu(), mx[1:])
+
+
+def test_pooling_nan_propagates(sim):
+    from mammo_clip_dissect_b200.hooks import pool_nchw
+    x = torch.randn(2, 4, 50, 50, generator=gen(30))
+    x[0, 1, 7, 9] = float("nan")
+    got = pool_nchw(x.to(DEV), "max").cpu()
+    assert torch.isnan(got[0, 1]) and torch.equal(torch.isnan(got), torch.isnan(x.amax(dim=[2, 3])))
+
+
+# ------------------------------------------------------------------------------------------------
+# size-independent properties at a larger shape (the oracle would take minutes here)
+# ------------------------------------------------------------------------------------------------
+def test_properties_at_scale(sim):
+    N, K, C, k = 20000, 4096, 763, 100
+    A = torch.randn(N, K, generator=gen(40)).to(DEV)
+    P = (torch.randn(N, C, generator=gen(41)) * 0.05).to(DEV)
+    vals, idx = sim.topk_cols(A, k, device=DEV, want_values=True)
+    assert torch.equal(vals, A.gather(0, idx))                               # values are the selected elements
+    assert bool((vals[:-1] >= vals[1:]).all())                               # sorted descending
+    assert bool((idx.sort(dim=0).values[1:] != idx.sort(dim=0).values[:-1]).all())   # no index twice
+    kth = vals[-1]
+    assert int((A > kth).sum(0).max()) <= k - 1 and bool(((A >= kth).sum(0) >= k).all())   # exactly the top k
+    assert torch.equal(idx[:5], torch.topk(A, 5, dim=0)[1])                  # caller-side topk(A, 5, 0) falls out
+    out = sim.soft_wpmi(P, A, device=DEV)
+    # permuting neurons permutes rows (log p(d) is order-free up to the fixed-block summation order)
+    perm = torch.randperm(K, generator=gen(42)).to(DEV)
+    out_p = sim.soft_wpmi(P, A[:, perm], device=DEV)
+    assert (out_p - out[perm]).abs().max().item() <= 2e-3
+    # lam = 0 switches the coupling off: rows equal the raw log-sums, and a sub-layer reproduces them exactly
+    raw = sim.soft_wpmi(P, A, lam=0, device=DEV)
+    sub = sim.soft_wpmi(P, A[:, 1000:1300], lam=0, device=DEV)
+    assert torch.equal(sub, raw[1000:1300])
+    # out = raw - lam * prob_d with a per-concept prob_d
+    d = raw - out
+    assert (d - d[0:1]).abs().max().item() <= 1e-3
+    assert bool(torch.isfinite(out).all())
