@@ -32,6 +32,39 @@ __all__ = ["soft_wpmi", "wpmi", "cos_similarity", "cos_similarity_cubed", "cos_s
 
 _S_ALIGN = 32  # leading dimension of the probability matrix: rows start on 128-byte boundaries
 
+# Optional per-stage timing for bench.py: set PROFILE = [] and every stage of pmi_scores records a pair
+# of CUDA events on the current stream (no synchronisation); profile_summary() reads them back.
+PROFILE = None
+
+
+class _Stage:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.append((self.name, self.e0, e1))
+        return False
+
+
+def profile_summary():
+    """Mean milliseconds per stage over everything recorded since PROFILE was set."""
+    if not PROFILE:
+        return {}
+    torch.cuda.synchronize()
+    acc = {}
+    for name, e0, e1 in PROFILE:
+        acc.setdefault(name, []).append(e0.elapsed_time(e1))
+    return {k: sum(v) / len(v) for k, v in acc.items()}
+
 
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
@@ -182,14 +215,18 @@ def pmi_scores(clip_feats, target_feats, top_k, a, lam, device, min_prob, ramp, 
             raise RuntimeError("clip_feats %s and target_feats %s must share the probe-image axis"
                                % (tuple(clip_feats.shape), tuple(A.shape)))
         top_k = int(top_k)
-        S = concept_probabilities(clip_feats, a, dev)
-        idx32 = _topk_int32(A, top_k, dev)
+        with _Stage("softmax_rows"):
+            S = concept_probabilities(clip_feats, a, dev)
+        with _Stage("topk_cols"):
+            idx32 = _topk_int32(A, top_k, dev)
         weights = ramp.to(dev) if ramp is not None else None
-        L = log_sums(S, idx32, weights, min_prob)
+        with _Stage("wpmi_accum"):
+            L = log_sums(S, idx32, weights, min_prob)
         if return_parts:
             raw = L.clone()
-        part = lse_partials(L)
-        out, _ = pmi_finalize(L, part, A.shape[1], lam)
+        with _Stage("lse_finalize"):
+            part = lse_partials(L)
+            out, _ = pmi_finalize(L, part, A.shape[1], lam)
     if return_parts:
         return out, raw, idx32
     return out

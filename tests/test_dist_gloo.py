@@ -1,0 +1,94 @@
+"""world_size-2 (and 3) CPU tests of the neuron-sharded path over gloo.  The exchange logic of
+mammo_clip_dissect_b200.distributed is driven with an oracle-backed compute backend (test-only:
+the product backend is CUDA); the sharded result must equal the unsharded one bit for bit."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from mammo_clip_dissect_b200 import distributed as mdist
+from oracle import similarity_oracle as orc
+
+
+class OracleBackend:
+    def log_sums(self, clip_feats, target_shard, top_k, a, min_prob, ramp):
+        probs = torch.softmax(a * clip_feats, dim=1)
+        inds = orc.topk_cols(target_shard, int(top_k))[1]
+        w = ramp.reshape(-1, 1) if ramp is not None else None
+        return orc.log_sums_chunked(probs, inds, w, min_prob)
+
+    def lse_partials(self, L):
+        return orc.lse_block_partials(L)
+
+    def finalize(self, L, partials_all, K_total, lam):
+        prob_d = (orc.lse_combine(partials_all) - torch.log(torch.tensor(float(K_total), dtype=torch.float64))).float()
+        return L - lam * prob_d
+
+
+def _inputs(K):
+    g = torch.Generator().manual_seed(3)
+    return torch.randn(300, 41, generator=g) * 0.1, torch.randn(300, K, generator=g)
+
+
+def _unsharded(P, A, soft):
+    from mammo_clip_dissect_b200.similarity import _reference_ramp
+    be = OracleBackend()
+    ramp = _reference_ramp(20, 0.998, 0.97) if soft else None
+    L = be.log_sums(P, A, 20, 10 if soft else 2, 1e-7, ramp)
+    return be.finalize(L, be.lse_partials(L), A.shape[1], 1 if soft else 0.6)
+
+
+def _worker(rank, world, port, K, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        P, A = _inputs(K)
+        b = mdist.shard_bounds(K, world)
+        sizes = [b[i + 1] - b[i] for i in range(world)]
+        shard = A[:, b[rank]:b[rank + 1]].contiguous()
+        full = mdist.soft_wpmi_sharded(P, shard, sizes, top_k=20, backend=OracleBackend())
+        local = mdist.soft_wpmi_sharded(P, shard, sizes, top_k=20, backend=OracleBackend(), gather_scores=False)
+        w = mdist.wpmi_sharded(P, shard, sizes, top_k=20, backend=OracleBackend())
+        q.put((rank, full.numpy(), local.numpy(), w.numpy(), b))      # numpy: no shared-memory handles to outlive the child
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("world,K", [(2, 1024), (2, 700), (3, 1300)])
+def test_sharded_equals_unsharded(world, K):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, K, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    P, A = _inputs(K)
+    want, want_w = _unsharded(P, A, True), _unsharded(P, A, False)
+    for rank, full, local, w, b in got:
+        full, local, w = torch.from_numpy(full), torch.from_numpy(local), torch.from_numpy(w)
+        assert torch.equal(full, want), rank                       # G-invariant, bit for bit
+        assert torch.equal(local, want[b[rank]:b[rank + 1]])
+        assert torch.equal(w, want_w)
+    # and the block-LSE formulation agrees with the reference's logsumexp formulation
+    ref = orc.soft_wpmi_fast(P, A, top_k=20)
+    assert (want - ref).abs().max().item() < 1e-3
+
+
+def test_shard_bounds():
+    assert mdist.shard_bounds(32768, 8) == [4096 * i for i in range(9)]
+    b = mdist.shard_bounds(1300, 3)
+    assert b[0] == 0 and b[-1] == 1300 and all(x % 256 == 0 for x in b[1:-1]) and b == sorted(b)
+    assert mdist.shard_bounds(100, 4) == [0, 100, 100, 100, 100]
