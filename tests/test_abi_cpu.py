@@ -45,7 +45,7 @@ def test_cubin_is_sm100a_only():
 def test_workspace_queries_are_pure_host_functions(lib):
     # headline shape: 100k probes x 32768 neurons, k = 100
     ws = lib.mcd_topk_cols_workspace_bytes(100_000, 32_768, 100)
-    assert ws > 0 and ws % (100 * 32_768 * 8) == 0
+    assert ws >= 100 * 32_768 * 8
     assert lib.mcd_topk_cols_workspace_bytes(50, 8, 100) == 0          # k > N
     assert lib.mcd_topk_cols_workspace_bytes(10_000, 8, 1000) == 0     # beyond the heap kernels
     assert lib.mcd_pool_nchw_workspace_bytes(4, 24, 760, 456) > 0      # large planes are split
