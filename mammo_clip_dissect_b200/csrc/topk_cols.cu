@@ -44,93 +44,157 @@ constexpr int kListCap = 8;                          // pending slots per (quart
 constexpr int kPendCap = kQuads * kListCap;          // pending slots per column
 constexpr int kRowsPerQuad = kSubRows / kQuads;      // a step adds at most this many entries to a list
 constexpr int kMaxStages = 8;
-constexpr int kGroup = 16;                           // kept set: groups of kGroup entries + one minimum per group
+constexpr int kMaxGroups = 8;                        // kept set: at most 8 groups (their minima live in registers)
 enum FeedMode { kFeedElements = 0, kFeedTensorTile = 2 };
 
 // one TMA instruction per [kTileRows x 32] tile; out-of-range rows / columns are zero-filled
-__device__ __forceinline__ void tma_tile_g2s(void *smem_dst, const CUtensorMap *tmap, int x, int y, uint64_t *bar,
+__device__ __forceinline__ void tma_tile_g2s(uint32_t smem_dst, const CUtensorMap *tmap, int x, int y, uint32_t bar,
                                              uint64_t policy) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
         " [%0], [%1, {%2, %3}], [%4], %5;"
-        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar)), "l"(policy)
+        ::"r"(smem_dst), "l"(tmap), "r"(x), "r"(y), "r"(bar), "l"(policy)
         : "memory");
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t a, uint32_t b) {
+    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
 
 // Shared memory of a scan warp (arrays are [slot][32], so the warp's 32 columns hit distinct banks):
-//   ring   nstage x [kTileRows x 32] fp32 tiles of A
-//   pend   kPendCap pending entries (value bits, row) per column; the list of quarter-warp q starts at slot
+//   ring   nstage x [kTileRows x 32] fp32 tiles of A (only nstage of the kMaxStages are allocated)
+//   pend   kPendCap pending entries {value bits, row} per column; the list of quarter-warp q starts at slot
 //          q * kListCap
 //   tau    current threshold per column;  pcnt  entries per (quarter, column) list, published before a fold
-// Global memory (workspace, one region per warp, [slot][32] 64-bit words; touched only by the folds, it stays
-// in L2 because A is streamed with evict-first):
-//   kept   per column the kept set: G = ceil(k/kGroup) groups of kGroup (key, ~row) words, UNSORTED (slots
-//          >= k of the last group hold the all-ones word and are never touched), then the G group minima
+// Global memory (workspace, one region per warp; touched only by the folds, it stays in L2 because A is
+// streamed with evict-first):
+//   kept   per column the kept set as two [slot][32] u32 arrays (ordered key, ~row): G = ceil(k/GROUP) groups
+//          of GROUP entries, UNSORTED; slots >= k of the last group hold all-ones and are never the minimum
 struct ScanSmem {
     float ring[kMaxStages][kTileRows][kUnitCols];
-    unsigned long long pend[kPendCap][kUnitCols];
+    uint2 pend[kPendCap][kUnitCols];
     float tau[kUnitCols];
     int pcnt[kQuads][kUnitCols];
+    uint32_t gmh[kMaxGroups][kUnitCols], gml[kMaxGroups][kUnitCols];   // per group: its minimum entry (key, ~row)
+    int gms[kMaxGroups][kUnitCols];                                     // ... and the slot holding it
     uint64_t full[kMaxStages];
 };
-
-__host__ __device__ inline int scan_groups(int k) { return (k + kGroup - 1) / kGroup; }
-__host__ __device__ inline int kept_slots(int k) { return scan_groups(k) * (kGroup + 1); }
 __host__ __device__ inline size_t scan_smem_bytes(int nstage) {
     return sizeof(ScanSmem) - size_t(kMaxStages - nstage) * kTileRows * kUnitCols * 4;
 }
+__host__ __device__ inline int kept_group_size(int k) { return k <= 128 ? 16 : (k <= 256 ? 32 : 64); }
+__host__ __device__ inline int kept_slots(int k) {
+    const int g = kept_group_size(k);
+    return (k + g - 1) / g * g;
+}
 
-// The kept set of a column is a two-level min structure instead of a heap: replacing the current minimum
-// (root, known to live in group rg) costs one pass over that group (find the slot holding root, take the
-// group's new minimum) and one pass over the G group minima -- kGroup + G independent loads instead of a
-// chain of log2(k) dependent ones.
-__device__ __forceinline__ void kept_replace_min(unsigned long long *kept, int G, int col, unsigned long long e,
-                                                 unsigned long long &root, int &rg) {
-    unsigned long long *grp = kept + (rg * kGroup) * kUnitCols + col;
-    unsigned long long x[kGroup];
-#pragma unroll
-    for (int i = 0; i < kGroup; ++i) x[i] = grp[i * kUnitCols];
-    unsigned long long gmin = e;
-    int hit = -1;
-#pragma unroll
-    for (int i = 0; i < kGroup; ++i) {
-        const bool is_root = (hit < 0) && (x[i] == root);
-        if (is_root) hit = i;
-        else gmin = x[i] < gmin ? x[i] : gmin;
+__device__ __forceinline__ bool key_gt(uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl) {
+    return ah > bh || (ah == bh && al > bl);
+}
+
+// The kept set of one column (owned by one lane) is a two-level min structure instead of a heap: G groups of
+// GROUP unsorted entries in global memory, and per group the minimum entry (key, ~row, slot) in registers.
+// Replacing the overall minimum costs one pass over one group (GROUP independent 4-byte loads, one L2 round
+// trip) plus a register-only pass over the <= 8 group minima.
+template <int GROUP>
+struct Kept {
+    uint32_t *hi, *lo;          // this lane's column: element [slot] is hi[slot * 32]
+    uint32_t *gmh, *gml;        // shared memory: group g's minimum is gmh[g * 32], gml[g * 32], slot gms[g * 32]
+    int *gms;
+    uint32_t root_hi, root_lo;  // current overall minimum (the column's k-th best so far)
+    int rg, rs;                 // its group and slot within the group
+
+    __device__ __forceinline__ void init(uint32_t *hi_, uint32_t *lo_, ScanSmem &s, int lane, int G) {
+        hi = hi_;
+        lo = lo_;
+        gmh = &s.gmh[0][lane];
+        gml = &s.gml[0][lane];
+        gms = &s.gms[0][lane];
+        root_hi = root_lo = 0u;
+        rg = rs = 0;
+        for (int g = 0; g < kMaxGroups; ++g) {
+            gmh[g * kUnitCols] = gml[g * kUnitCols] = g < G ? 0u : 0xFFFFFFFFu;
+            gms[g * kUnitCols] = 0;
+        }
     }
-    grp[hit * kUnitCols] = e;
-    unsigned long long *gm = kept + (G * kGroup) * kUnitCols + col;
-    gm[rg * kUnitCols] = gmin;
-    unsigned long long best = gmin;
-    int bg = rg;
-    if (G <= kGroup) {
-        // all group minima with independent loads (one L2 round trip), then the reduction
-        unsigned long long m[kGroup];
+
+    // precondition: (eh, el) > root.  Overwrites the root entry with (eh, el) and re-establishes the minima.
+    __device__ __forceinline__ void replace_min(uint32_t eh, uint32_t el) {
+        uint32_t *gh = hi + rg * (GROUP * kUnitCols);
+        uint32_t *gl = lo + rg * (GROUP * kUnitCols);
+        gh[rs * kUnitCols] = eh;
+        gl[rs * kUnitCols] = el;
+        uint32_t h[GROUP];
 #pragma unroll
-        for (int g = 0; g < kGroup; ++g) m[g] = (g < G && g != rg) ? gm[g * kUnitCols] : ~0ull;
+        for (int i = 0; i < GROUP; ++i) h[i] = gh[i * kUnitCols];
 #pragma unroll
-        for (int g = 0; g < kGroup; ++g)
-            if (g != rg && (m[g] < best || (m[g] == best && g < bg))) {
-                best = m[g];
-                bg = g;
+        for (int i = 0; i < GROUP; ++i) h[i] = (i == rs) ? eh : h[i];       // do not depend on the store above
+        uint32_t mh = h[0];
+#pragma unroll
+        for (int i = 1; i < GROUP; ++i) mh = min(mh, h[i]);
+        int ms = -1, nmatch = 0;
+#pragma unroll
+        for (int i = GROUP - 1; i >= 0; --i)
+            if (h[i] == mh) {
+                ms = i;
+                ++nmatch;
             }
-    } else {
-        for (int g = 0; g < G; ++g) {
-            const unsigned long long m = (g == rg) ? gmin : gm[g * kUnitCols];
-            if (m < best || (m == best && g < bg)) {
-                best = m;
+        uint32_t ml;
+        if (nmatch == 1 || mh == 0u) {
+            ml = (ms == rs) ? el : gl[ms * kUnitCols];     // empty-slot sentinels are all (0, 0): take the first
+        } else {
+            // equal keys inside the group (tied activation values): the minimum has the smallest ~row.
+            // Rare path: re-read the keys from memory (indexing h[] dynamically would put it on the stack).
+            ml = 0xFFFFFFFFu;
+            ms = -1;
+            for (int i = 0; i < GROUP; ++i) {
+                const uint32_t hv = (i == rs) ? eh : gh[i * kUnitCols];
+                if (hv == mh) {
+                    const uint32_t l = (i == rs) ? el : gl[i * kUnitCols];
+                    if (ms < 0 || l < ml) {
+                        ml = l;
+                        ms = i;
+                    }
+                }
+            }
+        }
+        gmh[rg * kUnitCols] = mh;
+        gml[rg * kUnitCols] = ml;
+        gms[rg * kUnitCols] = ms;
+        // overall minimum over the group minima (the changed group's values are taken from registers)
+        uint32_t bh = 0xFFFFFFFFu, bl = 0xFFFFFFFFu;
+        int bg = 0;
+        uint32_t xh[kMaxGroups], xl[kMaxGroups];
+#pragma unroll
+        for (int g = 0; g < kMaxGroups; ++g) {
+            xh[g] = gmh[g * kUnitCols];
+            xl[g] = gml[g * kUnitCols];
+        }
+#pragma unroll
+        for (int g = kMaxGroups - 1; g >= 0; --g) {
+            const uint32_t ah = (g == rg) ? mh : xh[g], al = (g == rg) ? ml : xl[g];
+            if (!key_gt(ah, al, bh, bl)) {       // <= : on equal (sentinel) minima the lowest group wins
+                bh = ah;
+                bl = al;
                 bg = g;
             }
         }
+        const int bs = (bg == rg) ? ms : gms[bg * kUnitCols];
+        root_hi = bh;
+        root_lo = bl;
+        rg = bg;
+        rs = bs;
     }
-    root = best;
-    rg = bg;
-}
+};
 
 // whole warp: lane c folds the kQuads pending lists of column c into the column's kept set and publishes
 // the new threshold
-__device__ __forceinline__ void fold_pending(ScanSmem &s, unsigned long long *kept, int G, int lane,
-                                             unsigned long long &root, int &rg) {
+template <int GROUP>
+__device__ __forceinline__ void fold_pending(ScanSmem &s, Kept<GROUP> &kept, int lane) {
     int c[kQuads], total = 0;
 #pragma unroll
     for (int q = 0; q < kQuads; ++q) {
@@ -147,26 +211,44 @@ __device__ __forceinline__ void fold_pending(ScanSmem &s, unsigned long long *ke
                     e -= c[qq];
                     q = qq + 1;
                 }
-            const unsigned long long raw = s.pend[q * kListCap + e][lane];
-            const float v = __uint_as_float(static_cast<uint32_t>(raw >> 32));
-            const unsigned long long cand = pack_key(ordered_key(v), ~static_cast<uint32_t>(raw));
-            if (cand > root) kept_replace_min(kept, G, lane, cand, root, rg);
+            const uint2 raw = s.pend[q * kListCap + e][lane];
+            const uint32_t ch = ordered_key(__uint_as_float(raw.x)), cl = ~raw.y;
+            if (key_gt(ch, cl, kept.root_hi, kept.root_lo)) kept.replace_min(ch, cl);
         }
     }
-    s.tau[lane] = key_to_threshold(static_cast<uint32_t>(root >> 32));
+    s.tau[lane] = key_to_threshold(kept.root_hi);
+}
+
+constexpr uint32_t kSlotBytes = kUnitCols * 8;       // one pending slot row
+
+template <int GROUP>
+__device__ __forceinline__ void publish_and_fold(ScanSmem &s, Kept<GROUP> &kept, int lane, int q, int colq,
+                                                 uint32_t list_first, uint32_t &p0, uint32_t &p1, uint32_t &p2,
+                                                 uint32_t &p3, float4 &tau4) {
+    s.pcnt[q][colq + 0] = static_cast<int>((p0 - list_first) / kSlotBytes);
+    s.pcnt[q][colq + 1] = static_cast<int>((p1 - list_first) / kSlotBytes);
+    s.pcnt[q][colq + 2] = static_cast<int>((p2 - list_first) / kSlotBytes);
+    s.pcnt[q][colq + 3] = static_cast<int>((p3 - list_first) / kSlotBytes);
+    __syncwarp();
+    fold_pending<GROUP>(s, kept, lane);
+    __syncwarp();
+    tau4 = *reinterpret_cast<const float4 *>(&s.tau[colq]);
+    p0 = list_first; p1 = list_first + 8; p2 = list_first + 16; p3 = list_first + 24;
 }
 
 // One warp per CTA: 32 adjacent neuron columns x one slice of the image axis.  The warp feeds itself: lane 0
 // re-arms a ring stage with the next TMA tile as soon as the warp has the stage's rows in registers, so a warp
 // that is busy folding only pauses its own stream; the other warps resident on the SM keep HBM busy.
+template <int GROUP>
 __global__ void __launch_bounds__(kScanThreads)
 topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ A, int64_t lda, int64_t N,
                  int64_t K, int k, int nstage, int64_t rows_per_split, unsigned long long *__restrict__ cand,
-                 unsigned long long *__restrict__ kept_ws, int feed) {
+                 uint32_t *__restrict__ kept_ws, int feed) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // the ring is declared with kMaxStages but only nstage stages are allocated: everything behind it moves up
     ScanSmem &s = *reinterpret_cast<ScanSmem *>(smem_raw - size_t(kMaxStages - nstage) * kTileRows * kUnitCols * 4);
     float(*ring)[kTileRows][kUnitCols] = reinterpret_cast<float(*)[kTileRows][kUnitCols]>(smem_raw);
+    constexpr uint32_t kTileBytes = kTileRows * kUnitCols * 4;
 
     const int lane = threadIdx.x;
     const int64_t c0 = int64_t(blockIdx.x) * kUnitCols;
@@ -175,8 +257,11 @@ topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
     const int64_t row0 = int64_t(split) * rows_per_split;
     const int nrows = static_cast<int>(min(N, row0 + rows_per_split) - row0);
     const int ntiles = nrows > 0 ? (nrows + kTileRows - 1) / kTileRows : 0;
-    const int G = scan_groups(k);
+    const int G = (k + GROUP - 1) / GROUP;
     const uint64_t policy = l2_policy_evict_first();
+    const uint32_t ring_addr = smem_u32(smem_raw);
+    const uint32_t full_addr = smem_u32(&s.full[0]);
+    const int tx = static_cast<int>(c0), ty0 = static_cast<int>(row0);
 
     if (lane == 0) {
         for (int i = 0; i < nstage; ++i) mbar_init(&s.full[i], 1);
@@ -186,16 +271,23 @@ topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
     // prologue: start the stream before touching anything else
     if (feed == kFeedTensorTile && lane == 0) {
         for (int t = 0; t < nstage && t < ntiles; ++t) {
-            mbar_arrive_expect_tx(&s.full[t], kTileRows * kUnitCols * 4u);
-            tma_tile_g2s(&ring[t][0][0], &tmap, static_cast<int>(c0), static_cast<int>(row0 + int64_t(t) * kTileRows),
-                         &s.full[t], policy);
+            mbar_arrive_expect_tx(&s.full[t], kTileBytes);
+            tma_tile_g2s(ring_addr + t * kTileBytes, &tmap, tx, ty0 + t * kTileRows, full_addr + t * 8, policy);
         }
     }
-    // kept sets start as k sentinels (word 0 sorts below every real entry); NaN threshold admits everything
-    unsigned long long *kept = kept_ws + (size_t(blockIdx.y) * gridDim.x + blockIdx.x) * size_t(kept_slots(k)) * kUnitCols;
-    for (int slot = 0; slot < kept_slots(k); ++slot)
-        kept[slot * kUnitCols + lane] = (slot >= k && slot < G * kGroup) ? ~0ull : 0ull;   // padding: never the minimum
-    s.tau[lane] = lane < ncols ? __uint_as_float(0x7FC00000u) : INFINITY;                 // columns past K never pass
+    // kept sets start as k empty-slot sentinels (0, 0) that sort below every real entry; the NaN threshold
+    // admits everything until a column has seen k elements
+    const int nslots = G * GROUP;
+    uint32_t *kept_hi = kept_ws + (size_t(blockIdx.y) * gridDim.x + blockIdx.x) * size_t(2 * nslots) * kUnitCols + lane;
+    uint32_t *kept_lo = kept_hi + nslots * kUnitCols;
+    for (int slot = 0; slot < nslots; ++slot) {
+        const uint32_t fill = slot >= k ? 0xFFFFFFFFu : 0u;    // padding of the last group: never the minimum
+        kept_hi[slot * kUnitCols] = fill;
+        kept_lo[slot * kUnitCols] = fill;
+    }
+    Kept<GROUP> kept;
+    kept.init(kept_hi, kept_lo, s, lane, G);
+    s.tau[lane] = lane < ncols ? __uint_as_float(0x7FC00000u) : INFINITY;   // columns past K never pass
     __syncwarp();
 
     // A lane reads 4 adjacent columns of one row with one LDS.128; quarter-warp q takes rows q, q+4, q+8, q+12
@@ -204,14 +296,17 @@ topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
     const int q = lane >> 3;
     const int colq = (lane & 7) * 4;                 // first of this lane's 4 columns
     float4 tau4 = *reinterpret_cast<const float4 *>(&s.tau[colq]);
-    unsigned long long root = 0ull;                  // current minimum of the kept set of column `lane`, and its group
-    int rg = 0;
-    unsigned long long *const list_first = &s.pend[q * kListCap][colq];
-    unsigned long long *const list_limit = list_first + (kListCap - kRowsPerQuad) * kUnitCols;   // beyond: a step may overflow
-    unsigned long long *p0 = list_first, *p1 = list_first + 1, *p2 = list_first + 2, *p3 = list_first + 3;
+    const uint32_t list_first = smem_u32(&s.pend[q * kListCap][colq]);
+    const uint32_t list_limit = list_first + (kListCap - kRowsPerQuad) * kSlotBytes;   // beyond: a step may overflow
+    uint32_t p0 = list_first, p1 = list_first + 8, p2 = list_first + 16, p3 = list_first + 24;
+    const uint32_t lane_off = uint32_t(q * kUnitCols + colq) * 4u;   // this lane's first element inside a tile
 
     int stage = 0, use = 0;
+    uint32_t row_step = static_cast<uint32_t>(row0) + q;       // row index of this lane's first row in the next step
+    static_assert(kTileRows == 2 * kSubRows, "a tile is scanned as two 16-row steps");
+#pragma unroll 1
     for (int t = 0; t < ntiles; ++t) {
+        const uint32_t tile_addr = ring_addr + stage * kTileBytes;
         if (feed == kFeedTensorTile) {
             mbar_wait(&s.full[stage], use & 1);
         } else {
@@ -221,67 +316,72 @@ topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
                 ring[stage][r][lane] = lane < ncols ? __ldg(A + (row0 + int64_t(t) * kTileRows + r) * lda + c0 + lane) : 0.f;
             __syncwarp();
         }
-        const int rows_tile = min(kTileRows, nrows - t * kTileRows);
-        float4 v[kTileRows / kSubRows][kRowsPerQuad];
-#pragma unroll
-        for (int h = 0; h < kTileRows / kSubRows; ++h)
+        const bool full_tile = (t + 1) * kTileRows <= nrows;
+        const int rows_left_tile = nrows - t * kTileRows - q;      // > r  <=>  this lane's row r of the tile exists
+        float4 va[kRowsPerQuad], vb[kRowsPerQuad];                 // rows of the first / second 16-row step
+        if (full_tile) {
 #pragma unroll
             for (int i = 0; i < kRowsPerQuad; ++i) {
-                const int r = h * kSubRows + q + kQuads * i;
-                v[h][i] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-                if (r < rows_tile) v[h][i] = *reinterpret_cast<const float4 *>(&ring[stage][r][colq]);
+                va[i] = lds_v4(tile_addr + lane_off + uint32_t(kQuads * i) * (kUnitCols * 4));
+                vb[i] = lds_v4(tile_addr + lane_off + uint32_t(kSubRows + kQuads * i) * (kUnitCols * 4));
             }
-        __syncwarp();                                    // every lane has its rows in registers
+        } else {
+            // last, partial tile: rows past the end read as -inf (and are masked by `valid` below, because
+            // -inf still passes an unfilled NaN threshold)
+#pragma unroll
+            for (int i = 0; i < kRowsPerQuad; ++i) {
+                va[i] = vb[i] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+                if (kQuads * i < rows_left_tile) va[i] = lds_v4(tile_addr + lane_off + uint32_t(kQuads * i) * (kUnitCols * 4));
+                if (kSubRows + kQuads * i < rows_left_tile)
+                    vb[i] = lds_v4(tile_addr + lane_off + uint32_t(kSubRows + kQuads * i) * (kUnitCols * 4));
+            }
+        }
+        __syncwarp();                                    // every lane has the tile's rows in registers
         if (feed == kFeedTensorTile && lane == 0 && t + nstage < ntiles) {
             fence_proxy_async();                         // generic-proxy reads before the async-proxy refill
-            mbar_arrive_expect_tx(&s.full[stage], kTileRows * kUnitCols * 4u);
-            tma_tile_g2s(&ring[stage][0][0], &tmap, static_cast<int>(c0),
-                         static_cast<int>(row0 + int64_t(t + nstage) * kTileRows), &s.full[stage], policy);
+            mbar_arrive_expect_tx(&s.full[stage], kTileBytes);
+            tma_tile_g2s(tile_addr, &tmap, tx, ty0 + (t + nstage) * kTileRows, full_addr + stage * 8, policy);
         }
         if (++stage == nstage) {
             stage = 0;
             ++use;
         }
+        // the two steps share one copy of the append / fold code (instruction-cache footprint)
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half, row_step += kSubRows) {
+            float4 v[kRowsPerQuad];
 #pragma unroll
-        for (int h = 0; h < kTileRows / kSubRows; ++h) {
+            for (int i = 0; i < kRowsPerQuad; ++i) {
+                v[i].x = half ? vb[i].x : va[i].x;
+                v[i].y = half ? vb[i].y : va[i].y;
+                v[i].z = half ? vb[i].z : va[i].z;
+                v[i].w = half ? vb[i].w : va[i].w;
+            }
             bool any = false;
 #pragma unroll
             for (int i = 0; i < kRowsPerQuad; ++i)
-                any |= !(v[h][i].x <= tau4.x) | !(v[h][i].y <= tau4.y) | !(v[h][i].z <= tau4.z) | !(v[h][i].w <= tau4.w);
-            if (!__any_sync(0xffffffffu, any)) continue;
+                any |= !(v[i].x <= tau4.x) | !(v[i].y <= tau4.y) | !(v[i].z <= tau4.z) | !(v[i].w <= tau4.w);
+            if (__any_sync(0xffffffffu, any)) {
+                const int rows_left = rows_left_tile - half * kSubRows;
 #pragma unroll
-            for (int i = 0; i < kRowsPerQuad; ++i) {
-                const int r = h * kSubRows + q + kQuads * i;
-                const bool valid = r < rows_tile;    // rows past the end read as -inf, which passes an unfilled (NaN) threshold
-                const uint32_t row = static_cast<uint32_t>(row0) + uint32_t(t * kTileRows + r);
-                if (valid && !(v[h][i].x <= tau4.x)) { *p0 = pack_key(__float_as_uint(v[h][i].x), row); p0 += kUnitCols; }
-                if (valid && !(v[h][i].y <= tau4.y)) { *p1 = pack_key(__float_as_uint(v[h][i].y), row); p1 += kUnitCols; }
-                if (valid && !(v[h][i].z <= tau4.z)) { *p2 = pack_key(__float_as_uint(v[h][i].z), row); p2 += kUnitCols; }
-                if (valid && !(v[h][i].w <= tau4.w)) { *p3 = pack_key(__float_as_uint(v[h][i].w), row); p3 += kUnitCols; }
-            }
-            const bool want = (p0 > list_limit) | (p1 > list_limit + 1) | (p2 > list_limit + 2) | (p3 > list_limit + 3);
-            if (__any_sync(0xffffffffu, want)) {
-                s.pcnt[q][colq + 0] = static_cast<int>(p0 - list_first) / kUnitCols;
-                s.pcnt[q][colq + 1] = static_cast<int>(p1 - list_first - 1) / kUnitCols;
-                s.pcnt[q][colq + 2] = static_cast<int>(p2 - list_first - 2) / kUnitCols;
-                s.pcnt[q][colq + 3] = static_cast<int>(p3 - list_first - 3) / kUnitCols;
-                __syncwarp();
-                fold_pending(s, kept, G, lane, root, rg);
-                __syncwarp();
-                tau4 = *reinterpret_cast<const float4 *>(&s.tau[colq]);
-                p0 = list_first; p1 = list_first + 1; p2 = list_first + 2; p3 = list_first + 3;
+                for (int i = 0; i < kRowsPerQuad; ++i) {
+                    const bool valid = full_tile || (kQuads * i < rows_left);
+                    const uint32_t row = row_step + uint32_t(kQuads * i);
+                    if (valid && !(v[i].x <= tau4.x)) { sts_v2(p0, __float_as_uint(v[i].x), row); p0 += kSlotBytes; }
+                    if (valid && !(v[i].y <= tau4.y)) { sts_v2(p1, __float_as_uint(v[i].y), row); p1 += kSlotBytes; }
+                    if (valid && !(v[i].z <= tau4.z)) { sts_v2(p2, __float_as_uint(v[i].z), row); p2 += kSlotBytes; }
+                    if (valid && !(v[i].w <= tau4.w)) { sts_v2(p3, __float_as_uint(v[i].w), row); p3 += kSlotBytes; }
+                }
+                const bool want = (p0 > list_limit) | (p1 > list_limit + 8) | (p2 > list_limit + 16) | (p3 > list_limit + 24);
+                if (__any_sync(0xffffffffu, want))
+                    publish_and_fold<GROUP>(s, kept, lane, q, colq, list_first, p0, p1, p2, p3, tau4);
             }
         }
     }
-    s.pcnt[q][colq + 0] = static_cast<int>(p0 - list_first) / kUnitCols;
-    s.pcnt[q][colq + 1] = static_cast<int>(p1 - list_first - 1) / kUnitCols;
-    s.pcnt[q][colq + 2] = static_cast<int>(p2 - list_first - 2) / kUnitCols;
-    s.pcnt[q][colq + 3] = static_cast<int>(p3 - list_first - 3) / kUnitCols;
-    __syncwarp();
-    fold_pending(s, kept, G, lane, root, rg);
+    publish_and_fold<GROUP>(s, kept, lane, q, colq, list_first, p0, p1, p2, p3, tau4);
     if (lane < ncols) {
         unsigned long long *dst = cand + (int64_t(split) * k) * K + c0 + lane;
-        for (int i = 0; i < k; ++i) dst[int64_t(i) * K] = kept[i * kUnitCols + lane];
+        for (int i = 0; i < k; ++i) dst[int64_t(i) * K] = pack_key(kept_hi[i * kUnitCols], kept_lo[i * kUnitCols]);
     }
 }
 
@@ -334,7 +434,7 @@ struct TopkPlan {
 };
 
 static bool make_plan(int64_t N, int64_t K, int64_t k64, TopkPlan *p) {
-    if (k64 < 1 || k64 > 2048) return false;
+    if (k64 < 1 || k64 > 512) return false;     // kept-set groups: 8 x 64 entries at most
     const int k = static_cast<int>(k64);
     const int64_t sms = num_sms();
     // ring depth: enough scan warps per SM (the scan is latency-bound per warp) with a few tiles in flight each
@@ -378,7 +478,7 @@ static bool make_plan(int64_t N, int64_t K, int64_t k64, TopkPlan *p) {
     while (mpad < p->splits * k) mpad <<= 1;
     p->mpad = mpad;
     p->cand_bytes = (size_t(p->splits) * size_t(k) * size_t(K) * 8 + 255) / 256 * 256;
-    p->kept_bytes = size_t(ncb) * p->splits * size_t(kept_slots(k)) * kUnitCols * 8;
+    p->kept_bytes = size_t(ncb) * p->splits * size_t(kept_slots(k)) * kUnitCols * 8;   // (key, ~row) u32 pairs
     return true;
 }
 
@@ -411,6 +511,16 @@ static bool make_tile_map(CUtensorMap *map, const float *A, int64_t lda, int64_t
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+template <int GROUP>
+static int launch_scan(dim3 grid, const TopkPlan &p, const CUtensorMap &map, const float *A, int64_t lda, int64_t N,
+                       int64_t K, int k, unsigned long long *cand, uint32_t *kept, int feed, cudaStream_t st) {
+    auto kern = topk_scan_kernel<GROUP>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(p.smem)) != cudaSuccess)
+        return MCD_ERR_CUDA;
+    kern<<<grid, kScanThreads, p.smem, st>>>(map, A, lda, N, K, k, p.nstage, p.rows_per_split, cand, kept, feed);
+    return check_launch();
+}
+
 }  // namespace mcd
 
 extern "C" size_t mcd_topk_cols_workspace_bytes(int64_t N, int64_t K, int64_t k) {
@@ -430,7 +540,7 @@ extern "C" int mcd_topk_cols_f32(const float *A, int64_t lda, int64_t N, int64_t
     if (reinterpret_cast<uintptr_t>(workspace) % 8 != 0) return MCD_ERR_INVALID_ARGUMENT;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     auto *cand = static_cast<unsigned long long *>(workspace);
-    auto *kept = reinterpret_cast<unsigned long long *>(static_cast<char *>(workspace) + p.cand_bytes);
+    auto *kept = reinterpret_cast<uint32_t *>(static_cast<char *>(workspace) + p.cand_bytes);
 
     // feed: TMA tensor tiles need a 16-byte aligned base and row pitch; anything else takes element copies
     const bool aligned = (lda % 4 == 0) && (reinterpret_cast<uintptr_t>(A) % 16 == 0);
@@ -440,12 +550,13 @@ extern "C" int mcd_topk_cols_f32(const float *A, int64_t lda, int64_t N, int64_t
     memset(&map, 0, sizeof(map));
     if (feed == kFeedTensorTile && !make_tile_map(&map, A, lda, N, K, kUnitCols, kTileRows)) feed = kFeedElements;
 
-    if (cudaFuncSetAttribute(topk_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(p.smem)) != cudaSuccess)
-        return MCD_ERR_CUDA;
     dim3 grid(static_cast<unsigned>(ceil_div<int64_t>(K, kUnitCols)), static_cast<unsigned>(p.splits));
-    topk_scan_kernel<<<grid, kScanThreads, p.smem, st>>>(map, A, lda, N, K, int(k), p.nstage, p.rows_per_split, cand,
-                                                         kept, feed);
-    int rc = check_launch();
+    int rc;
+    switch (kept_group_size(int(k))) {
+        case 16: rc = launch_scan<16>(grid, p, map, A, lda, N, K, int(k), cand, kept, feed, st); break;
+        case 32: rc = launch_scan<32>(grid, p, map, A, lda, N, K, int(k), cand, kept, feed, st); break;
+        default: rc = launch_scan<64>(grid, p, map, A, lda, N, K, int(k), cand, kept, feed, st); break;
+    }
     if (rc != MCD_OK) return rc;
 
     const size_t fsmem = size_t(kFinishWarps) * p.mpad * sizeof(unsigned long long);

@@ -140,7 +140,7 @@ def topk_cols(target_feats, k, device="cuda", want_values=False, want_int32=Fals
     vals = torch.empty((k, K), dtype=torch.float32, device=dev) if want_values else None
     need = lib.mcd_topk_cols_workspace_bytes(N, K, k)
     if need == 0:
-        raise RuntimeError("top_k=%d is outside the supported range of the column top-k kernel (<= 496)" % k)
+        raise RuntimeError("top_k=%d is outside the supported range of the column top-k kernel (<= 512)" % k)
     ws = _workspace(need, dev)
     with torch.cuda.device(dev):
         _lib.check(lib.mcd_topk_cols_f32(_ptr(A), _ld(A), N, K, k, _ptr(idx64), _ptr(idx32), _ptr(vals), _ptr(ws),
@@ -158,7 +158,7 @@ def _topk_int32(A, k, dev):
     idx32 = torch.empty((k, K), dtype=torch.int32, device=dev)
     need = lib.mcd_topk_cols_workspace_bytes(N, K, k)
     if need == 0:
-        raise RuntimeError("top_k=%d is outside the supported range of the column top-k kernel (<= 496)" % k)
+        raise RuntimeError("top_k=%d is outside the supported range of the column top-k kernel (<= 512)" % k)
     ws = _workspace(need, dev)
     _lib.check(lib.mcd_topk_cols_f32(_ptr(A), _ld(A), N, K, k, None, _ptr(idx32), None, _ptr(ws), ws.numel(),
                                      _stream(dev)), "mcd_topk_cols_f32")

@@ -52,7 +52,7 @@ def check_scores(out, L, ref_out, ref_L, f64_out=None, label=""):
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("N,K,k", [(2000, 256, 100), (777, 33, 28), (300, 7, 1), (130, 33, 130), (5000, 40, 10),
                                    (1024, 64, 48), (1500, 129, 112), (3000, 68, 200), (4000, 36, 300),
-                                   (2048, 12, 496), (64, 4, 64)])
+                                   (2048, 12, 496), (64, 4, 64), (1024, 70, 512), (700, 33, 129), (900, 40, 257)])
 def test_topk_tie_free(sim, N, K, k):
     A = torch.randn(N, K, generator=gen(N + K + k))
     vals, idx = sim.topk_cols(A, k, device=DEV, want_values=True)
