@@ -27,7 +27,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["soft_wpmi", "wpmi", "cos_similarity", "cos_similarity_cubed", "cos_similarity_cubed_single",
+__all__ = ["soft_wpmi", "wpmi", "cos_similarity", "cos_similarity_cubed", "cos_similarity_cubed_single", "rank_reorder",
            "topk_cols", "concept_probabilities", "pmi_scores"]
 
 _S_ALIGN = 32  # leading dimension of the probability matrix: rows start on 128-byte boundaries
@@ -287,3 +287,12 @@ def cos_similarity_cubed_single(clip_feats, target_feats, device='cuda', min_nor
     if tuple(clip_feats.shape) != tuple(target_feats.shape):
         raise RuntimeError("cos_similarity_cubed_single needs equally shaped inputs")
     return torch.diagonal(_cos(clip_feats, target_feats, device, True, min_norm)).clone()
+
+
+def rank_reorder(clip_feats, target_feats, device="cuda", p=3, top_fraction=0.05, scale_p=0.5, top_k=None):
+    """Reference similarity.py:99-132.  NOT on the CUDA path yet (the last of the
+    "next" rows): it needs a large-k (5 % of the probe set) selection, per-concept rank-of-rank and a host
+    replay of the reference's global-RNG torch.randperm stream.  There is deliberately no CPU fallback."""
+    raise NotImplementedError(
+        "rank_reorder is not implemented on the B200 path yet (scope row f4); soft_wpmi, wpmi, cos_similarity and "
+        "cos_similarity_cubed are")

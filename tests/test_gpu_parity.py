@@ -344,3 +344,66 @@ def test_properties_at_scale(sim):
     d = raw - out
     assert (d - d[0:1]).abs().max().item() <= 1e-3
     assert bool(torch.isfinite(out).all())
+
+
+# ------------------------------------------------------------------------------------------------
+# the drivers' call sequence (describe_clip_neurons.py:41-66, CLIP_og_utils.py:60-75,153-175) end to end
+# ------------------------------------------------------------------------------------------------
+def test_driver_call_sequence(sim, tmp_path):
+    import mammo_clip_dissect_b200.similarity as similarity      # noqa: F401  (the name the driver's eval() uses)
+    from mammo_clip_dissect_b200 import features
+    from mammo_clip_dissect_b200.hooks import get_activation      # noqa: F401  (used inside the eval below)
+
+    class Target(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.layer1 = torch.nn.Conv2d(3, 24, 3, padding=1)
+            self.layer2 = torch.nn.Conv2d(24, 40, 3, stride=2)
+            self.fc = torch.nn.Linear(40 * 7 * 7, 12)
+
+        def forward(self, x):
+            return self.fc(torch.relu(self.layer2(torch.relu(self.layer1(x)))).flatten(1))
+
+    torch.manual_seed(0)
+    target_model = Target().to(DEV).eval()
+    images = torch.randn(300, 3, 16, 16)
+    img_feats, txt_feats = torch.randn(300, 64) * 2, torch.randn(29, 64)
+    # hooks are registered exactly like the reference does it: through eval() on a layer string
+    all_features = {name: [] for name in ("layer1", "layer2", "fc")}
+    hooks = {}
+    for target_layer in all_features:
+        command = "target_model.{}.register_forward_hook(get_activation(all_features[target_layer], 'avg'))".format(target_layer)
+        hooks[target_layer] = eval(command)
+    with torch.no_grad():
+        for i in range(0, 300, 100):
+            target_model(images[i:i + 100].to(DEV))
+    torch.save(img_feats, tmp_path / "img.pt")
+    torch.save(txt_feats, tmp_path / "txt.pt")
+    cpu_model = Target().eval()
+    cpu_model.load_state_dict({k: v.cpu() for k, v in target_model.state_dict().items()})
+    acts = {}
+    with torch.no_grad():
+        x1 = cpu_model.layer1(images)
+        x2 = cpu_model.layer2(torch.relu(x1))
+        acts["layer1"], acts["layer2"] = x1.mean(dim=[2, 3]), x2.mean(dim=[2, 3])
+        acts["fc"] = cpu_model.fc(torch.relu(x2).flatten(1))
+    similarity_fn = eval("similarity.{}".format("soft_wpmi"))
+    P_ref = orc.similarity_matrix(img_feats, txt_feats)
+    for layer in all_features:
+        pooled = torch.cat(all_features[layer])
+        hooks[layer].remove()
+        assert pooled.is_cuda and pooled.shape == acts[layer].shape
+        assert torch.allclose(pooled.cpu(), acts[layer], rtol=1e-4, atol=1e-5)       # cuDNN vs CPU conv noise
+        torch.save(pooled.cpu(), tmp_path / ("%s.pt" % layer))
+        sims, target_feats = features.get_similarity_from_activations(
+            str(tmp_path / ("%s.pt" % layer)), str(tmp_path / "img.pt"), str(tmp_path / "txt.pt"), similarity_fn,
+            return_target_feats=True, device=DEV)
+        vals, ids = torch.max(sims, dim=1)
+        _, top_ids = torch.topk(target_feats, k=5, dim=0)
+        ref, refL, _ = orc.soft_wpmi_fast(P_ref, pooled.cpu(), return_parts=True)
+        assert sims.shape == ref.shape and sims.is_cuda
+        assert (sims.cpu() - ref).abs().max().item() <= 1e-5 * refL.abs().max().item()
+        assert (ids.cpu() == ref.argmax(1)).float().mean().item() >= 0.99
+        assert top_ids.shape == (5, pooled.shape[1])
+    with pytest.raises(NotImplementedError):
+        similarity.rank_reorder(P_ref, acts["fc"], device=DEV)
