@@ -7,7 +7,7 @@
 // neurons are sharded it is computed in fixed blocks of MCD_LSE_BLOCK = 256 neurons:
 //   partial[b] = ( m_b[c] = max_j L[j,c],  s_b[c] = sum_j exp(L[j,c] - m_b[c]) )   (fp32, j in block order)
 // and the partials of ALL blocks are combined in global block order in fp64:
-//   lse[c] = M + log( sum_b s_b * exp(m_b - M) ),  M = max_b m_b.
+//   lse[c] = M + log( sum_b s_b * exp(m_b - M) ),  M = max_b m_b   (fp64 sum, fp32 block weights).
 #include "common.cuh"
 
 namespace mcd {
@@ -36,13 +36,14 @@ lse_combine_kernel(const float *__restrict__ partials, int64_t n_blocks, int C, 
                    float *__restrict__ prob_d) {
     const int c = blockIdx.x * kLseThreads + threadIdx.x;
     if (c >= C) return;
-    double big = -INFINITY;
-    for (int64_t b = 0; b < n_blocks; ++b) big = fmax(big, double(partials[(b * 2) * C + c]));
-    const double bs = isinf(big) ? 0.0 : big;
+    float big = -INFINITY;
+    for (int64_t b = 0; b < n_blocks; ++b) big = fmaxf(big, partials[(b * 2) * C + c]);
+    const float bs = isinf(big) ? 0.f : big;
+    // block weights exp(m_b - M) in fp32 (the fp64 exp dominated this kernel), accumulation in fp64, block order
     double total = 0.0;
     for (int64_t b = 0; b < n_blocks; ++b)
-        total += double(partials[(b * 2 + 1) * C + c]) * exp(double(partials[(b * 2) * C + c]) - bs);
-    prob_d[c] = static_cast<float>(bs + log(total) - log_count);
+        total += double(partials[(b * 2 + 1) * C + c]) * double(expf(partials[(b * 2) * C + c] - bs));
+    prob_d[c] = static_cast<float>(double(bs) + log(total) - log_count);
 }
 
 __global__ void __launch_bounds__(256)

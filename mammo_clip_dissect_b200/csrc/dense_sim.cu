@@ -195,10 +195,19 @@ int sim_matrix_fp32(const float *I, int64_t ldi, const float *T, int64_t ldt, in
 }
 }  // namespace mcd
 
+namespace mcd {
+size_t sim_matrix_tc_workspace(int64_t N, int64_t C, int64_t D);                       // gemm_tf32x3.cu
+int sim_matrix_tc(const float *I, int64_t ldi, const float *T, int64_t ldt, int64_t N, int64_t C, int64_t D,
+                  int normalize_rows, float *P, int64_t ldp, void *ws, size_t ws_bytes, cudaStream_t st);
+static size_t gemm_base_workspace(int64_t N, int64_t C) {
+    const size_t ldp = size_t(ceil_div<int64_t>(C, 4) * 4);
+    return ((size_t(N) + size_t(C)) * sizeof(float) + 255) / 256 * 256 + size_t(N) * ldp * sizeof(float) + 256;
+}
+}  // namespace mcd
+
 extern "C" size_t mcd_gemm_nt_softmax_workspace_bytes(int64_t N, int64_t C, int64_t D) {
     if (N < 1 || C < 1 || D < 1) return 0;
-    const size_t ldp = size_t(mcd::ceil_div<int64_t>(C, 4) * 4);
-    return (size_t(N) + size_t(C)) * sizeof(float) + size_t(N) * ldp * sizeof(float) + 256;
+    return mcd::gemm_base_workspace(N, C) + mcd::sim_matrix_tc_workspace(N, C, D);
 }
 
 extern "C" int mcd_gemm_nt_softmax_f32(const float *I, int64_t ldi, const float *T, int64_t ldt, int64_t N, int64_t C,
@@ -217,7 +226,13 @@ extern "C" int mcd_gemm_nt_softmax_f32(const float *I, int64_t ldi, const float 
         P = reinterpret_cast<float *>(static_cast<char *>(workspace) + off);
         ld = ceil_div<int64_t>(C, 4) * 4;
     }
-    int rc = sim_matrix_fp32(I, ldi, T, ldt, N, C, D, normalize_rows, P, ld, norms, st);
+    // tensor-core path (tcgen05 kind::tf32, 3-term split); tunable gemm_variant = 1 forces the fp32 CUDA-core kernel
+    int rc = MCD_ERR_UNSUPPORTED;
+    if (tunable(kGemmVariant) != 1) {
+        char *tc_ws = static_cast<char *>(workspace) + gemm_base_workspace(N, C);
+        rc = sim_matrix_tc(I, ldi, T, ldt, N, C, D, normalize_rows, P, ld, tc_ws, workspace_bytes - gemm_base_workspace(N, C), st);
+    }
+    if (rc == MCD_ERR_UNSUPPORTED) rc = sim_matrix_fp32(I, ldi, T, ldt, N, C, D, normalize_rows, P, ld, norms, st);
     if (rc != MCD_OK || !S_out) return rc;
     return mcd_softmax_rows_f32(P, ld, S_out, lds, N, C, a, stream);
 }

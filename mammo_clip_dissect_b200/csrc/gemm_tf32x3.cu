@@ -1,0 +1,280 @@
+// K1 on the 5th-generation tensor cores: P = normalise(I) * normalise(T)^T   (reference concept_vit/utils.py:577-594)
+//
+// The reference multiplies in true fp32 (torch's allow_tf32 is off) and soft_wpmi then scales the logits by a = 10,
+// so a single-pass TF32 product (6.5e-4 relative error on the softmax) is not acceptable.  The product
+// is therefore evaluated as a 3-term split on tcgen05 kind::tf32 with fp32 accumulation in TMEM:
+//        x = hi + lo,  hi = x with the low 13 mantissa bits cleared (exactly representable in TF32),  lo = x - hi
+//        I T^T  ~=  Ihi Thi^T + Ihi Tlo^T + Ilo Thi^T                                  (the lo*lo term is < 2^-20)
+// which reproduces fp32-grade results (1.4e-6 on the softmax in the survey's emulation; measured in the tests).
+//
+//   prepare_rows_kernel   one warp per row: ||x||, x/||x|| with the reference's per-element division, hi / lo split,
+//                         written as two row-padded fp32 matrices (rows to a multiple of the tile, D to 32)
+//   gemm_tf32x3_kernel    CTA = one 128 x 128 output tile.  warp 0: TMA producer (4 operand tiles per 32-wide
+//                         k-block, 128-byte swizzle, 3-stage mbarrier ring); warp 1: one thread issues 12
+//                         tcgen05.mma (M128 N128 K8) per k-block and commits to the stage's `empty` barrier;
+//                         warps 2-5: epilogue, tcgen05.ld 32 lanes x 32 columns at a time -> global stores.
+//                         The N-tile index is the fastest grid dimension so the CTAs sharing an I tile hit L2.
+// The tensor core's fp32 accumulation truncates, so its error grows linearly with the length of the k loop
+// (measured 5.4e-6 of max|P| at D = 512 with one accumulator vs 1e-6 for the fp32 FFMA kernel).  The k-blocks are
+// therefore dealt round-robin onto 4 independent TMEM accumulators (4 x 128 columns = the whole TMEM) that the
+// epilogue adds with round-to-nearest fp32 adds.
+#include <cuda.h>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace mcd {
+
+constexpr int kBM = 128, kBN = 128, kBK = 32;            // CTA tile; kBK fp32 = one 128-byte swizzle row
+constexpr int kGemmStages = 3;
+constexpr int kAccSegs = 4;                              // independent TMEM accumulators (k-blocks round-robin)
+constexpr int kTmemCols = kAccSegs * kBN;                // 512 = all of TMEM
+constexpr int kTcThreads = 192;                          // producer warp, MMA warp, 4 epilogue warps
+constexpr uint32_t kATileBytes = kBM * kBK * 4;          // 16 KB
+constexpr uint32_t kBTileBytes = kBN * kBK * 4;          // 16 KB
+constexpr uint32_t kStageBytes = 2 * kATileBytes + 2 * kBTileBytes;   // hi + lo of both operands: 64 KB
+constexpr size_t kTcSmemBytes = size_t(kGemmStages) * kStageBytes + 1024 /*alignment slack*/ + 256 /*barriers*/;
+
+__global__ void __launch_bounds__(256)
+prepare_rows_kernel(const float *__restrict__ X, int64_t ldx, int64_t R, int64_t D, int normalize,
+                    float *__restrict__ Xhi, float *__restrict__ Xlo, int64_t Rpad, int64_t Dpad) {
+    const int lane = threadIdx.x & 31;
+    const int64_t r = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    if (r >= Rpad) return;
+    float *hi = Xhi + r * Dpad, *lo = Xlo + r * Dpad;
+    if (r >= R) {
+        for (int64_t d = lane; d < Dpad; d += 32) hi[d] = lo[d] = 0.f;
+        return;
+    }
+    const float *x = X + r * ldx;
+    float nrm = 1.f;
+    if (normalize) {
+        float s = 0.f;
+        for (int64_t d = lane; d < D; d += 32) {
+            const float v = x[d];
+            s = fmaf(v, v, s);
+        }
+        nrm = sqrtf(warp_sum(s));
+    }
+    for (int64_t d = lane; d < Dpad; d += 32) {
+        float v = 0.f;
+        if (d < D) v = normalize ? __fdiv_rn(x[d], nrm) : x[d];
+        const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        hi[d] = h;
+        lo[d] = __fsub_rn(v, h);          // exact
+    }
+}
+
+// ---- tcgen05 / TMA plumbing -------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
+    // a mis-programmed pipeline must fail loudly, never hang the GPU
+    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
+        if (spin > (1u << 28)) __trap();
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap *tmap, int x, int y, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_dst), "l"(tmap), "r"(x), "r"(y), "r"(smem_u32(bar))
+                 : "memory");
+}
+// K-major operand tile, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO); version 1 (sm_100)
+__device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
+    return uint64_t((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+}
+// kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 128
+constexpr uint32_t kIdescTf32 = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(kBN >> 3) << 17) | (uint32_t(kBM >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(kIdescTf32), "r"(uint32_t(accumulate))
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float *v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
+                   const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
+                   int64_t M, int64_t Nn, int num_kb, float *__restrict__ P, int64_t ldp) {
+    extern __shared__ unsigned char smem_dyn[];
+    // 128-byte swizzle needs 1024-byte aligned tiles
+    const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    unsigned char *aligned = smem_dyn + (base - smem_u32(smem_dyn));
+    uint64_t *full = reinterpret_cast<uint64_t *>(aligned + size_t(kGemmStages) * kStageBytes);
+    uint64_t *empty = full + kGemmStages;
+    uint64_t *tmem_full = empty + kGemmStages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kGemmStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(tmem_full, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) {     // TMEM: 4 x 128 fp32 accumulator columns x 128 lanes
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % kGemmStages, use = kb / kGemmStages;
+                if (use > 0) mbar_wait_bounded(&empty[s], (use - 1) & 1);
+                mbar_arrive_expect_tx(&full[s], kStageBytes);
+                const uint32_t st = base + s * kStageBytes;
+                const int kx = kb * kBK;
+                tma_load_2d(st, &mapAhi, kx, m_tile * kBM, &full[s]);
+                tma_load_2d(st + kATileBytes, &mapAlo, kx, m_tile * kBM, &full[s]);
+                tma_load_2d(st + 2 * kATileBytes, &mapBhi, kx, n_tile * kBN, &full[s]);
+                tma_load_2d(st + 2 * kATileBytes + kBTileBytes, &mapBlo, kx, n_tile * kBN, &full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % kGemmStages, use = kb / kGemmStages;
+                mbar_wait_bounded(&full[s], use & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = base + s * kStageBytes;
+                const uint64_t ahi = umma_desc_k128(st), alo = umma_desc_k128(st + kATileBytes);
+                const uint64_t bhi = umma_desc_k128(st + 2 * kATileBytes), blo = umma_desc_k128(st + 2 * kATileBytes + kBTileBytes);
+#pragma unroll
+                const uint32_t acc = tmem_base + uint32_t(kb % kAccSegs) * kBN;     // this k-block's accumulator
+#pragma unroll
+                for (int kk = 0; kk < kBK / 8; ++kk) {          // K = 8 per tf32 MMA: 32 bytes inside the swizzle row
+                    const uint64_t adv = uint64_t((kk * 32) >> 4);
+                    umma_tf32(acc, ahi + adv, bhi + adv, kb >= kAccSegs || kk > 0);
+                    umma_tf32(acc, ahi + adv, blo + adv, true);
+                    umma_tf32(acc, alo + adv, bhi + adv, true);
+                }
+                umma_commit(&empty[s]);                          // smem stage reusable once these MMAs have read it
+            }
+            umma_commit(tmem_full);                              // accumulator complete
+        }
+    } else {
+        // epilogue warps 2..5: warp w may touch TMEM lanes 32*(w%4) .. +31 only
+        const int quarter = warp & 3;
+        mbar_wait_bounded(tmem_full, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int64_t row = int64_t(m_tile) * kBM + quarter * 32 + lane;
+        const int64_t col0 = int64_t(n_tile) * kBN;
+        const bool vec_ok = (ldp % 4 == 0) && (reinterpret_cast<uintptr_t>(P) % 16 == 0);
+#pragma unroll 1
+        const int nseg = num_kb < kAccSegs ? num_kb : kAccSegs;
+        for (int c = 0; c < kBN; c += 32) {
+            float v[32];
+            tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(c), v);
+            for (int sgm = 1; sgm < nseg; ++sgm) {
+                float w[32];
+                tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(sgm * kBN + c), w);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __fadd_rn(v[i], w[i]);
+            }
+            if (row < M) {
+                float *dst = P + row * ldp + col0 + c;
+                if (vec_ok && col0 + c + 32 <= Nn) {
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4 *>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (col0 + c + i < Nn) dst[i] = v[i];
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    }
+}
+
+// ---- host ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn2)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn2 encode_fn2() {
+    static EncodeTiledFn2 fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return reinterpret_cast<EncodeTiledFn2>(p);
+    }();
+    return fn;
+}
+
+static bool make_operand_map(CUtensorMap *map, const float *X, int64_t rows, int64_t cols, int box_rows) {
+    EncodeTiledFn2 enc = encode_fn2();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
+    cuuint64_t strides[1] = {cuuint64_t(cols) * sizeof(float)};
+    cuuint32_t box[2] = {cuuint32_t(kBK), cuuint32_t(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(X), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+size_t sim_matrix_tc_workspace(int64_t N, int64_t C, int64_t D) {
+    const int64_t Np = ceil_div<int64_t>(N, kBM) * kBM, Cp = ceil_div<int64_t>(C, kBN) * kBN, Dp = ceil_div<int64_t>(D, kBK) * kBK;
+    return size_t(Np + Cp) * size_t(Dp) * 2 * sizeof(float) + 1024;
+}
+
+// returns MCD_ERR_UNSUPPORTED when the tensor-map encoder is unavailable (caller then uses the CUDA-core kernel)
+int sim_matrix_tc(const float *I, int64_t ldi, const float *T, int64_t ldt, int64_t N, int64_t C, int64_t D,
+                  int normalize_rows, float *P, int64_t ldp, void *ws, size_t ws_bytes, cudaStream_t st) {
+    const int64_t Np = ceil_div<int64_t>(N, kBM) * kBM, Cp = ceil_div<int64_t>(C, kBN) * kBN, Dp = ceil_div<int64_t>(D, kBK) * kBK;
+    if (ws_bytes < sim_matrix_tc_workspace(N, C, D)) return MCD_ERR_WORKSPACE;
+    if (Np / kBM > 65535) return MCD_ERR_UNSUPPORTED;
+    char *w = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
+    float *Ihi = reinterpret_cast<float *>(w);
+    float *Ilo = Ihi + Np * Dp;
+    float *Thi = Ilo + Np * Dp;
+    float *Tlo = Thi + Cp * Dp;
+    CUtensorMap mAhi, mAlo, mBhi, mBlo;
+    if (!make_operand_map(&mAhi, Ihi, Np, Dp, kBM) || !make_operand_map(&mAlo, Ilo, Np, Dp, kBM) ||
+        !make_operand_map(&mBhi, Thi, Cp, Dp, kBN) || !make_operand_map(&mBlo, Tlo, Cp, Dp, kBN))
+        return MCD_ERR_UNSUPPORTED;
+    prepare_rows_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(Np, 8)), 256, 0, st>>>(I, ldi, N, D, normalize_rows, Ihi, Ilo, Np, Dp);
+    prepare_rows_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(Cp, 8)), 256, 0, st>>>(T, ldt, C, D, normalize_rows, Thi, Tlo, Cp, Dp);
+    count_launch(2);
+    if (cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTcSmemBytes)) != cudaSuccess)
+        return MCD_ERR_CUDA;
+    dim3 grid(static_cast<unsigned>(Cp / kBN), static_cast<unsigned>(Np / kBM));
+    gemm_tf32x3_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(mAhi, mAlo, mBhi, mBlo, N, C, static_cast<int>(Dp / kBK), P, ldp);
+    return check_launch();
+}
+
+}  // namespace mcd

@@ -64,6 +64,19 @@ def main():
             print("accum tile=%d: %.3f ms  gather %.0f GB/s" % (t, ms, args.topk * K * 768 * 4 / 1e9 / ms * 1e3), flush=True)
         _lib.set_tunable("accum_tile", 0)
         print("softmax: %.3f ms" % timeit(lambda: sim.concept_probabilities(P, 10, dev)))
+    if args.what in ("gemm", "all"):
+        from mammo_clip_dissect_b200 import features
+        I = torch.randn(N, 512, generator=g, device=dev)
+        T = torch.randn(C, 512, generator=g, device=dev)
+        fl = 2.0 * N * C * 512
+        for var in (0, 1):
+            _lib.set_tunable("gemm_variant", var)
+            ms = timeit(lambda: features.similarity_matrix(I, T, device=dev))
+            print("K1 I.T^T variant=%d (%s): %.3f ms  %.1f TFLOP/s (algorithmic 2NCD)" % (var, "tcgen05 3xTF32" if var == 0 else "fp32 FFMA", ms, fl / ms / 1e9), flush=True)
+            ms = timeit(lambda: features.similarity_matrix(I, T, device=dev, softmax_scale=10))
+            print("   + softmax: %.3f ms" % ms, flush=True)
+        _lib.set_tunable("gemm_variant", 0)
+    if args.what in ("accum", "all"):
         L = out.clone()
         print("lse+finalize: %.3f ms" % timeit(lambda: sim.pmi_finalize(L, sim.lse_partials(L), K, 1.0)))
 
