@@ -20,7 +20,18 @@ namespace mcd {
 constexpr int kAccumThreads = 192;
 constexpr int kAccumMaxK = 512;
 
-template <bool SOFT>
+// lg2.approx without .ftz makes the compiler wrap every MUFU in a denormal rescue (compare, scale by 2^24,
+// subtract 24): three extra instructions per element in an issue-bound kernel.  With min_prob a normal number the
+// argument (>= min_prob for probabilities in [0,1] and weights <= 1) can never be subnormal, so the host selects FTZ.
+template <bool FTZ>
+__device__ __forceinline__ float lg2_fast(float x) {
+    float r;
+    if (FTZ) asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    else asm("lg2.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+template <bool SOFT, bool FTZ>
 __device__ __forceinline__ float term_lg2(float s, float w, float eps) {
     float v;
     if (SOFT) {
@@ -31,15 +42,18 @@ __device__ __forceinline__ float term_lg2(float s, float w, float eps) {
     } else {
         v = __fadd_rn(s, eps);
     }
-    return lg2_approx(v);
+    return lg2_fast<FTZ>(v);
 }
 
-template <int TPN, int U, bool SOFT, bool VEC>
+template <int TPN, int U, bool SOFT, bool VEC, bool FTZ>
 __global__ void __launch_bounds__(kAccumThreads)
 wpmi_accum_kernel(const float *__restrict__ S, int64_t lds, int C, const int32_t *__restrict__ idx, int64_t K, int k,
-                  const float *__restrict__ p, float eps, float *__restrict__ L, int64_t ldl, int n_groups) {
+                  const float *__restrict__ p, float eps, float *__restrict__ L, int64_t ldl, int n_groups, int hint) {
     constexpr int NPB = kAccumThreads / TPN;
-    __shared__ int32_t s_idx[NPB][kAccumMaxK];
+    // the gathered rows of S are re-read ~k*K/N (33 at c4) times: ask L2 to keep them (evict-last), measured
+    // 1.15 -> 0.80 ms at c4 (tunable accum_unroll = 2 switches the hint off)
+    const uint64_t keep = l2_policy_evict_last();
+    __shared__ uint32_t s_idx[NPB][kAccumMaxK];     // row offsets idx * lds (elements; the host checks N * lds < 2^32)
     __shared__ float s_p[kAccumMaxK];
 
     const int tile = blockIdx.x / n_groups;
@@ -50,7 +64,7 @@ wpmi_accum_kernel(const float *__restrict__ S, int64_t lds, int C, const int32_t
     for (int i = tid; i < NPB * k; i += kAccumThreads) {
         const int n = i / k, r = i - n * k;
         const int64_t j = j0 + n;
-        s_idx[n][r] = j < K ? idx[int64_t(r) * K + j] : 0;
+        s_idx[n][r] = j < K ? uint32_t(idx[int64_t(r) * K + j]) * uint32_t(lds) : 0u;
     }
     if (SOFT)
         for (int r = tid; r < k; r += kAccumThreads) s_p[r] = p[r];
@@ -65,7 +79,7 @@ wpmi_accum_kernel(const float *__restrict__ S, int64_t lds, int C, const int32_t
     // a vector load may run past C only inside the row's padding (c0 + 4 <= lds is guaranteed by
     // the host when VEC); the scalar path loads exactly the valid columns
     const float *base = S + c0;
-    const int32_t *my_idx = s_idx[n];
+    const uint32_t *my_idx = s_idx[n];
 
     float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
     int r = 0;
@@ -73,9 +87,9 @@ wpmi_accum_kernel(const float *__restrict__ S, int64_t lds, int C, const int32_t
         float4 s[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const float *row = base + int64_t(my_idx[r + u]) * lds;
+            const float *row = base + my_idx[r + u];
             if (VEC) {
-                s[u] = ldg_nc_v4(row);
+                s[u] = hint ? ldg_nc_v4_hint(row, keep) : ldg_nc_v4(row);
             } else {
                 s[u].x = __ldg(row);
                 s[u].y = nvalid > 1 ? __ldg(row + 1) : 0.f;
@@ -87,17 +101,17 @@ wpmi_accum_kernel(const float *__restrict__ S, int64_t lds, int C, const int32_t
         for (int u = 0; u < U; ++u) {
             const float w = SOFT ? s_p[r + u] : 0.f;
             float *acc = (u & 1) ? acc1 : acc0;
-            acc[0] += term_lg2<SOFT>(s[u].x, w, eps);
-            acc[1] += term_lg2<SOFT>(s[u].y, w, eps);
-            acc[2] += term_lg2<SOFT>(s[u].z, w, eps);
-            acc[3] += term_lg2<SOFT>(s[u].w, w, eps);
+            acc[0] += term_lg2<SOFT, FTZ>(s[u].x, w, eps);
+            acc[1] += term_lg2<SOFT, FTZ>(s[u].y, w, eps);
+            acc[2] += term_lg2<SOFT, FTZ>(s[u].z, w, eps);
+            acc[3] += term_lg2<SOFT, FTZ>(s[u].w, w, eps);
         }
     }
     for (; r < k; ++r) {
-        const float *row = base + int64_t(my_idx[r]) * lds;
+        const float *row = base + my_idx[r];
         float4 s;
         if (VEC) {
-            s = ldg_nc_v4(row);
+            s = hint ? ldg_nc_v4_hint(row, keep) : ldg_nc_v4(row);
         } else {
             s.x = __ldg(row);
             s.y = nvalid > 1 ? __ldg(row + 1) : 0.f;
@@ -105,10 +119,10 @@ wpmi_accum_kernel(const float *__restrict__ S, int64_t lds, int C, const int32_t
             s.w = nvalid > 3 ? __ldg(row + 3) : 0.f;
         }
         const float w = SOFT ? s_p[r] : 0.f;
-        acc0[0] += term_lg2<SOFT>(s.x, w, eps);
-        acc0[1] += term_lg2<SOFT>(s.y, w, eps);
-        acc0[2] += term_lg2<SOFT>(s.z, w, eps);
-        acc0[3] += term_lg2<SOFT>(s.w, w, eps);
+        acc0[0] += term_lg2<SOFT, FTZ>(s.x, w, eps);
+        acc0[1] += term_lg2<SOFT, FTZ>(s.y, w, eps);
+        acc0[2] += term_lg2<SOFT, FTZ>(s.z, w, eps);
+        acc0[3] += term_lg2<SOFT, FTZ>(s.w, w, eps);
     }
     constexpr float kLn2 = 0.693147180559945309417f;
     float *out = L + j * ldl + c0;
@@ -120,13 +134,18 @@ wpmi_accum_kernel(const float *__restrict__ S, int64_t lds, int C, const int32_t
 template <int TPN, bool SOFT, bool VEC>
 static int launch_accum(const float *S, int64_t lds, int C, const int32_t *idx, int64_t K, int k, const float *p,
                         float eps, float *L, int64_t ldl, cudaStream_t st) {
+    const bool ftz = eps >= 1.17549435e-38f;
     constexpr int NPB = kAccumThreads / TPN;
     const int n_tiles = ceil_div(C, TPN * 4);
     const int64_t n_groups = ceil_div<int64_t>(K, NPB);
     const int64_t blocks = n_groups * n_tiles;
     if (blocks > 0x7FFFFFFFll) return MCD_ERR_UNSUPPORTED;
-    wpmi_accum_kernel<TPN, 8, SOFT, VEC><<<static_cast<unsigned>(blocks), kAccumThreads, 0, st>>>(
-        S, lds, C, idx, K, k, p, eps, L, ldl, static_cast<int>(n_groups));
+    if (ftz)
+        wpmi_accum_kernel<TPN, 8, SOFT, VEC, true><<<static_cast<unsigned>(blocks), kAccumThreads, 0, st>>>(
+            S, lds, C, idx, K, k, p, eps, L, ldl, static_cast<int>(n_groups), tunable(kAccumUnroll) == 2 ? 0 : 1);
+    else
+        wpmi_accum_kernel<TPN, 8, SOFT, VEC, false><<<static_cast<unsigned>(blocks), kAccumThreads, 0, st>>>(
+            S, lds, C, idx, K, k, p, eps, L, ldl, static_cast<int>(n_groups), tunable(kAccumUnroll) == 2 ? 0 : 1);
     return check_launch();
 }
 
@@ -138,6 +157,7 @@ static int dispatch_tile(int tpn, const float *S, int64_t lds, int C, const int3
         case 96: return launch_accum<96, SOFT, VEC>(S, lds, C, idx, K, k, p, eps, L, ldl, st);
         case 64: return launch_accum<64, SOFT, VEC>(S, lds, C, idx, K, k, p, eps, L, ldl, st);
         case 48: return launch_accum<48, SOFT, VEC>(S, lds, C, idx, K, k, p, eps, L, ldl, st);
+        case 16: return launch_accum<16, SOFT, VEC>(S, lds, C, idx, K, k, p, eps, L, ldl, st);
         default: return launch_accum<32, SOFT, VEC>(S, lds, C, idx, K, k, p, eps, L, ldl, st);
     }
 }
@@ -149,7 +169,7 @@ extern "C" int mcd_wpmi_accum_f32(const float *S, int64_t lds, int64_t N, int64_
                                   mcd_stream_t stream) {
     using namespace mcd;
     if (!S || !idx || !L || N < 1 || C < 1 || K < 1 || k < 1 || lds < C || ldl < C) return MCD_ERR_INVALID_ARGUMENT;
-    if (k > kAccumMaxK || C > (1 << 24)) return MCD_ERR_UNSUPPORTED;
+    if (k > kAccumMaxK || C > (1 << 24) || N * lds >= (int64_t(1) << 32)) return MCD_ERR_UNSUPPORTED;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // 16-byte loads need aligned rows and must stay inside a row (padding included)
     const bool vec = (lds % 4 == 0) && (reinterpret_cast<uintptr_t>(S) % 16 == 0) && (ceil_div<int64_t>(C, 4) * 4 <= lds);
@@ -164,7 +184,8 @@ extern "C" int mcd_wpmi_accum_f32(const float *S, int64_t lds, int64_t N, int64_
     else if (want > 64) tpn = 96;
     else if (want > 48) tpn = 64;
     else if (want > 32) tpn = 48;
-    else tpn = 32;
+    else if (want > 16) tpn = 32;
+    else tpn = 16;
     const int Ci = static_cast<int>(C), ki = static_cast<int>(k);
     if (p) return vec ? dispatch_tile<true, true>(tpn, S, lds, Ci, idx, K, ki, p, min_prob, L, ldl, st)
                       : dispatch_tile<true, false>(tpn, S, lds, Ci, idx, K, ki, p, min_prob, L, ldl, st);

@@ -58,10 +58,13 @@ def main():
         idx = sim._topk_int32(A, args.topk, dev)
         w = sim._reference_ramp(args.topk, 0.998, 0.97).to(dev)
         out = torch.empty((K, C), device=dev)
-        for t in [int(x) for x in args.tiles.split(",")]:
-            _lib.set_tunable("accum_tile", t)
-            ms = timeit(lambda: sim.log_sums(S, idx, w, 1e-7, out=out))
-            print("accum tile=%d: %.3f ms  gather %.0f GB/s" % (t, ms, args.topk * K * 768 * 4 / 1e9 / ms * 1e3), flush=True)
+        for hint in (2, 0):
+            _lib.set_tunable("accum_unroll", hint)
+            for t in [int(x) for x in args.tiles.split(",")]:
+                _lib.set_tunable("accum_tile", t)
+                ms = timeit(lambda: sim.log_sums(S, idx, w, 1e-7, out=out))
+                print("accum tile=%d hint=%d: %.3f ms  gather %.0f GB/s" % (t, hint, ms, args.topk * K * 768 * 4 / 1e9 / ms * 1e3), flush=True)
+        _lib.set_tunable("accum_unroll", 0)
         _lib.set_tunable("accum_tile", 0)
         print("softmax: %.3f ms" % timeit(lambda: sim.concept_probabilities(P, 10, dev)))
     if args.what in ("gemm", "all"):
