@@ -165,9 +165,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
                 const uint32_t st = base + s * kStageBytes;
                 const uint64_t ahi = umma_desc_k128(st), alo = umma_desc_k128(st + kATileBytes);
                 const uint64_t bhi = umma_desc_k128(st + 2 * kATileBytes), blo = umma_desc_k128(st + 2 * kATileBytes + kBTileBytes);
-#pragma unroll
                 const uint32_t acc = tmem_base + uint32_t(kb % kAccSegs) * kBN;     // this k-block's accumulator
-#pragma unroll
                 for (int kk = 0; kk < kBK / 8; ++kk) {          // K = 8 per tf32 MMA: 32 bytes inside the swizzle row
                     const uint64_t adv = uint64_t((kk * 32) >> 4);
                     umma_tf32(acc, ahi + adv, bhi + adv, kb >= kAccSegs || kk > 0);

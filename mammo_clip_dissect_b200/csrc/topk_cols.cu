@@ -107,6 +107,7 @@ struct Kept {
     int *gms;
     uint32_t root_hi, root_lo;  // current overall minimum (the column's k-th best so far)
     int rg, rs;                 // its group and slot within the group
+    float floor_tau;            // threshold while the set still has empty slots (NaN = admit everything)
 
     __device__ __forceinline__ void init(uint32_t *hi_, uint32_t *lo_, ScanSmem &s, int lane, int G) {
         hi = hi_;
@@ -216,7 +217,7 @@ __device__ __forceinline__ void fold_pending(ScanSmem &s, Kept<GROUP> &kept, int
             if (key_gt(ch, cl, kept.root_hi, kept.root_lo)) kept.replace_min(ch, cl);
         }
     }
-    s.tau[lane] = key_to_threshold(kept.root_hi);
+    s.tau[lane] = kept.root_hi == 0u ? kept.floor_tau : key_to_threshold(kept.root_hi);
 }
 
 constexpr uint32_t kSlotBytes = kUnitCols * 8;       // one pending slot row
@@ -243,13 +244,16 @@ template <int GROUP>
 __global__ void __launch_bounds__(kScanThreads)
 topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ A, int64_t lda, int64_t N,
                  int64_t K, int k, int nstage, int64_t rows_per_split, unsigned long long *__restrict__ cand,
-                 uint32_t *__restrict__ kept_ws, int feed) {
+                 uint32_t *__restrict__ kept_ws, int feed, const float *__restrict__ tau0, float *__restrict__ tau_out,
+                 int *__restrict__ flags, int only_flagged) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // the ring is declared with kMaxStages but only nstage stages are allocated: everything behind it moves up
     ScanSmem &s = *reinterpret_cast<ScanSmem *>(smem_raw - size_t(kMaxStages - nstage) * kTileRows * kUnitCols * 4);
     float(*ring)[kTileRows][kUnitCols] = reinterpret_cast<float(*)[kTileRows][kUnitCols]>(smem_raw);
     constexpr uint32_t kTileBytes = kTileRows * kUnitCols * 4;
 
+    // second pass of the pre-threshold scheme: only column groups whose first pass came up short are redone
+    if (only_flagged && flags[blockIdx.x] == 0) return;
     const int lane = threadIdx.x;
     const int64_t c0 = int64_t(blockIdx.x) * kUnitCols;
     const int ncols = static_cast<int>(min(int64_t(kUnitCols), K - c0));
@@ -287,7 +291,11 @@ topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
     }
     Kept<GROUP> kept;
     kept.init(kept_hi, kept_lo, s, lane, G);
-    s.tau[lane] = lane < ncols ? __uint_as_float(0x7FC00000u) : INFINITY;   // columns past K never pass
+    // Start threshold: NaN admits everything; with a pre-threshold (a value known -- with overwhelming
+    // probability -- to have at least k elements of the column above it) the insert-heavy start of the scan
+    // disappears.  If fewer than k elements turn out to beat it, the group is flagged and redone without it.
+    kept.floor_tau = (tau0 != nullptr && !only_flagged && lane < ncols) ? tau0[c0 + lane] : __uint_as_float(0x7FC00000u);
+    s.tau[lane] = lane < ncols ? kept.floor_tau : INFINITY;                  // columns past K never pass
     __syncwarp();
 
     // A lane reads 4 adjacent columns of one row with one LDS.128; quarter-warp q takes rows q, q+4, q+8, q+12
@@ -379,7 +387,12 @@ topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
         }
     }
     publish_and_fold<GROUP>(s, kept, lane, q, colq, list_first, p0, p1, p2, p3, tau4);
-    if (lane < ncols) {
+    if (tau_out != nullptr && lane < ncols) tau_out[c0 + lane] = key_to_threshold(kept.root_hi);   // NaN if not full
+    if (flags != nullptr && tau0 != nullptr && !only_flagged) {
+        const bool short_of_k = lane < ncols && kept.root_hi == 0u;
+        if (__any_sync(0xffffffffu, short_of_k) && lane == 0) flags[blockIdx.x] = 1;
+    }
+    if (cand != nullptr && lane < ncols) {
         unsigned long long *dst = cand + (int64_t(split) * k) * K + c0 + lane;
         for (int i = 0; i < k; ++i) dst[int64_t(i) * K] = pack_key(kept_hi[i * kUnitCols], kept_lo[i * kUnitCols]);
     }
@@ -431,7 +444,13 @@ struct TopkPlan {
     int64_t rows_per_split;
     size_t smem;
     size_t cand_bytes, kept_bytes;      // workspace: candidates [splits*k][K], then one kept region per scan warp
+    // pre-threshold pass (single-split scans of long columns): every pre_stride-th row, k-th largest = pre_k
+    int pre_stride, pre_k;
+    int64_t pre_rows;
+    size_t pre_bytes;                   // tau [K] floats, flags [ncb] ints, kept regions of the pre-pass
 };
+
+constexpr int kPreStride = 32;
 
 static bool make_plan(int64_t N, int64_t K, int64_t k64, TopkPlan *p) {
     if (k64 < 1 || k64 > 512) return false;     // kept-set groups: 8 x 64 entries at most
@@ -479,6 +498,26 @@ static bool make_plan(int64_t N, int64_t K, int64_t k64, TopkPlan *p) {
     p->mpad = mpad;
     p->cand_bytes = (size_t(p->splits) * size_t(k) * size_t(K) * 8 + 255) / 256 * 256;
     p->kept_bytes = size_t(ncb) * p->splits * size_t(kept_slots(k)) * kUnitCols * 8;   // (key, ~row) u32 pairs
+    // Pre-threshold: the k-th largest of a column ranks ~ Poisson(k/stride) within a stride-sample of its rows,
+    // so the (lambda + 6 sqrt(lambda) + 4)-th largest sample value has >= k column elements above it except with
+    // probability ~1e-8 (and a column that does come up short is redone exactly).
+    p->pre_stride = 0;
+    p->pre_k = 0;
+    p->pre_rows = 0;
+    p->pre_bytes = 0;
+    if (tunable(kTopkPre) != 2 && p->splits == 1 && N >= 16384 && k <= 256) {
+        const double lam = double(k) / kPreStride;
+        int pk = static_cast<int>(lam + 6.0 * sqrt(lam) + 4.0 + 0.999);
+        if (pk < 8) pk = 8;
+        const int64_t pr = N / kPreStride;
+        if (pk <= 128 && pr >= 4 * pk) {
+            p->pre_stride = kPreStride;
+            p->pre_k = pk;
+            p->pre_rows = pr;
+            p->pre_bytes = (size_t(K) * 4 + 255) / 256 * 256 + (size_t(ncb) * 4 + 255) / 256 * 256 +
+                           size_t(ncb) * size_t(kept_slots(pk)) * kUnitCols * 8;
+        }
+    }
     return true;
 }
 
@@ -511,14 +550,34 @@ static bool make_tile_map(CUtensorMap *map, const float *A, int64_t lda, int64_t
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+struct ScanArgs {
+    const float *A;
+    int64_t lda, N, K, rows_per_split;
+    int k, feed;
+    unsigned long long *cand;
+    uint32_t *kept;
+    const float *tau0;
+    float *tau_out;
+    int *flags;
+    int only_flagged;
+};
+
 template <int GROUP>
-static int launch_scan(dim3 grid, const TopkPlan &p, const CUtensorMap &map, const float *A, int64_t lda, int64_t N,
-                       int64_t K, int k, unsigned long long *cand, uint32_t *kept, int feed, cudaStream_t st) {
+static int launch_scan_t(dim3 grid, const TopkPlan &p, const CUtensorMap &map, const ScanArgs &a, cudaStream_t st) {
     auto kern = topk_scan_kernel<GROUP>;
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(p.smem)) != cudaSuccess)
         return MCD_ERR_CUDA;
-    kern<<<grid, kScanThreads, p.smem, st>>>(map, A, lda, N, K, k, p.nstage, p.rows_per_split, cand, kept, feed);
+    kern<<<grid, kScanThreads, p.smem, st>>>(map, a.A, a.lda, a.N, a.K, a.k, p.nstage, a.rows_per_split, a.cand, a.kept,
+                                             a.feed, a.tau0, a.tau_out, a.flags, a.only_flagged);
     return check_launch();
+}
+
+static int launch_scan(dim3 grid, const TopkPlan &p, const CUtensorMap &map, const ScanArgs &a, cudaStream_t st) {
+    switch (kept_group_size(a.k)) {
+        case 16: return launch_scan_t<16>(grid, p, map, a, st);
+        case 32: return launch_scan_t<32>(grid, p, map, a, st);
+        default: return launch_scan_t<64>(grid, p, map, a, st);
+    }
 }
 
 }  // namespace mcd
@@ -526,7 +585,7 @@ static int launch_scan(dim3 grid, const TopkPlan &p, const CUtensorMap &map, con
 extern "C" size_t mcd_topk_cols_workspace_bytes(int64_t N, int64_t K, int64_t k) {
     mcd::TopkPlan p;
     if (N < 1 || K < 1 || k < 1 || k > N || !mcd::make_plan(N, K, k, &p)) return 0;
-    return p.cand_bytes + p.kept_bytes;
+    return p.cand_bytes + p.kept_bytes + p.pre_bytes;
 }
 
 extern "C" int mcd_topk_cols_f32(const float *A, int64_t lda, int64_t N, int64_t K, int64_t k, int64_t *idx64_out,
@@ -536,7 +595,7 @@ extern "C" int mcd_topk_cols_f32(const float *A, int64_t lda, int64_t N, int64_t
     if (!A || N < 1 || K < 1 || k < 1 || k > N || lda < K || N >= 0x7FFFFFFFll) return MCD_ERR_INVALID_ARGUMENT;
     TopkPlan p;
     if (!make_plan(N, K, k, &p)) return MCD_ERR_UNSUPPORTED;
-    if (!workspace || workspace_bytes < p.cand_bytes + p.kept_bytes) return MCD_ERR_WORKSPACE;
+    if (!workspace || workspace_bytes < p.cand_bytes + p.kept_bytes + p.pre_bytes) return MCD_ERR_WORKSPACE;
     if (reinterpret_cast<uintptr_t>(workspace) % 8 != 0) return MCD_ERR_INVALID_ARGUMENT;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     auto *cand = static_cast<unsigned long long *>(workspace);
@@ -551,12 +610,31 @@ extern "C" int mcd_topk_cols_f32(const float *A, int64_t lda, int64_t N, int64_t
     if (feed == kFeedTensorTile && !make_tile_map(&map, A, lda, N, K, kUnitCols, kTileRows)) feed = kFeedElements;
 
     dim3 grid(static_cast<unsigned>(ceil_div<int64_t>(K, kUnitCols)), static_cast<unsigned>(p.splits));
+    ScanArgs main_args{A, lda, N, K, p.rows_per_split, int(k), feed, cand, kept, nullptr, nullptr, nullptr, 0};
     int rc;
-    switch (kept_group_size(int(k))) {
-        case 16: rc = launch_scan<16>(grid, p, map, A, lda, N, K, int(k), cand, kept, feed, st); break;
-        case 32: rc = launch_scan<32>(grid, p, map, A, lda, N, K, int(k), cand, kept, feed, st); break;
-        default: rc = launch_scan<64>(grid, p, map, A, lda, N, K, int(k), cand, kept, feed, st); break;
+    if (p.pre_stride > 0 && feed == kFeedTensorTile) {
+        // pass 0: k'-th largest of every 32nd row -> start threshold per column; pass 1: the real scan starting
+        // from it; pass 2: exact redo (no start threshold) of the column groups that pass 1 flagged as short of k
+        char *pre = static_cast<char *>(workspace) + p.cand_bytes + p.kept_bytes;
+        float *tau = reinterpret_cast<float *>(pre);
+        int *flags = reinterpret_cast<int *>(pre + (size_t(K) * 4 + 255) / 256 * 256);
+        uint32_t *kept_pre = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(flags) + (size_t(grid.x) * 4 + 255) / 256 * 256);
+        CUtensorMap map_pre;
+        memset(&map_pre, 0, sizeof(map_pre));
+        if (make_tile_map(&map_pre, A, lda * p.pre_stride, p.pre_rows, K, kUnitCols, kTileRows)) {
+            if (cudaMemsetAsync(flags, 0, size_t(grid.x) * 4, st) != cudaSuccess) return MCD_ERR_CUDA;
+            ScanArgs pre_args{A, lda * p.pre_stride, p.pre_rows, K, ceil_div<int64_t>(p.pre_rows, kTileRows) * kTileRows,
+                              p.pre_k, feed, nullptr, kept_pre, nullptr, tau, nullptr, 0};
+            rc = launch_scan(dim3(grid.x, 1), p, map_pre, pre_args, st);
+            if (rc != MCD_OK) return rc;
+            main_args.tau0 = tau;
+            main_args.flags = flags;
+            rc = launch_scan(grid, p, map, main_args, st);
+            if (rc != MCD_OK) return rc;
+            main_args.only_flagged = 1;
+        }
     }
+    rc = launch_scan(grid, p, map, main_args, st);
     if (rc != MCD_OK) return rc;
 
     const size_t fsmem = size_t(kFinishWarps) * p.mpad * sizeof(unsigned long long);

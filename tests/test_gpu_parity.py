@@ -111,6 +111,40 @@ def test_topk_strided_unaligned_and_forced_splits(sim):
         _lib.set_tunable("topk_cols", 0)
 
 
+@pytest.mark.parametrize("kind", ["randn", "spikes_on_sampled_rows", "relu", "const", "nan_cols", "sorted_up"])
+def test_topk_pre_threshold_and_exact_redo(sim, kind):
+    """Long single-split scans start from a sampled threshold (k'-th largest of every 32nd row); column groups
+    where fewer than k elements beat it are redone exactly.  Results must not depend on whether the scheme is on."""
+    from mammo_clip_dissect_b200 import _lib
+    N, K, k = 20000, 200, 100
+    A = torch.randn(N, K, generator=gen(77))
+    if kind == "spikes_on_sampled_rows":
+        A[::32] += 50.0                      # the sample only sees the spikes: threshold far too high -> redo
+    elif kind == "relu":
+        A = torch.relu(A - 2.5)              # 99.4 % exact zeros
+    elif kind == "const":
+        A = torch.full((N, K), -3.0)
+    elif kind == "nan_cols":
+        A[:, ::3] = float("nan")
+        A[::5, 1] = float("inf")
+    elif kind == "sorted_up":
+        A = torch.sort(A, dim=0).values
+    ref = orc.topk_cols(A, k)[1]
+    try:
+        _lib.set_tunable("topk_splits", 1)
+        n0 = _lib.launch_count()
+        got = sim.topk_cols(A, k, device=DEV)
+        assert _lib.launch_count() - n0 == 4            # sample pass, scan, redo pass, finish
+        assert torch.equal(got.cpu(), ref), kind
+        _lib.set_tunable("topk_pre", 2)                  # scheme off
+        n0 = _lib.launch_count()
+        assert torch.equal(sim.topk_cols(A, k, device=DEV).cpu(), ref)
+        assert _lib.launch_count() - n0 == 2
+    finally:
+        _lib.set_tunable("topk_splits", 0)
+        _lib.set_tunable("topk_pre", 0)
+
+
 def test_topk_errors(sim):
     A = torch.randn(50, 4)
     with pytest.raises(RuntimeError):

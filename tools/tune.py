@@ -45,6 +45,11 @@ def main():
     P = torch.randn(N, C, generator=g, device=dev) * 0.044
     gb = 4.0 * N * K / 1e9
     if args.what in ("topk", "all"):
+        for pre in (0, 2):
+            _lib.set_tunable("topk_pre", pre)
+            ms = timeit(lambda: sim._topk_int32(A, args.topk, dev))
+            print("topk pre-threshold %s: %.3f ms  %.0f GB/s" % ("on" if pre == 0 else "off", ms, gb / ms * 1e3), flush=True)
+        _lib.set_tunable("topk_pre", 0)
         for var in [int(x) for x in args.variants.split(",")]:
             _lib.set_tunable("topk_cols", var)
             for s in [int(x) for x in args.splits.split(",")]:
