@@ -31,19 +31,38 @@ col_lse_partials_kernel(const float *__restrict__ L, int64_t ldl, int64_t K, int
     partials[(b * 2 + 1) * C + c] = s;
 }
 
-__global__ void __launch_bounds__(kLseThreads)
+// 32 columns x 8 block-slices per CTA: slice s reduces blocks s, s+8, ... (independent loads in flight instead of
+// one long dependent chain), then thread (c, 0) folds the 8 slice results in slice order -- a fixed order, so the
+// result is still independent of how the neurons were sharded.
+__global__ void __launch_bounds__(256)
 lse_combine_kernel(const float *__restrict__ partials, int64_t n_blocks, int C, double log_count,
                    float *__restrict__ prob_d) {
-    const int c = blockIdx.x * kLseThreads + threadIdx.x;
-    if (c >= C) return;
+    __shared__ float s_max[8][33];
+    __shared__ double s_sum[8][33];
+    const int cx = threadIdx.x & 31, sl = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cx;
     float big = -INFINITY;
-    for (int64_t b = 0; b < n_blocks; ++b) big = fmaxf(big, partials[(b * 2) * C + c]);
-    const float bs = isinf(big) ? 0.f : big;
-    // block weights exp(m_b - M) in fp32 (the fp64 exp dominated this kernel), accumulation in fp64, block order
+    if (c < C)
+        for (int64_t b = sl; b < n_blocks; b += 8) big = fmaxf(big, partials[(b * 2) * C + c]);
+    s_max[sl][cx] = big;
+    __syncthreads();
+    float all = s_max[0][cx];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) all = fmaxf(all, s_max[q][cx]);
+    const float bs = isinf(all) ? 0.f : all;
+    // block weights exp(m_b - M) in fp32 (an fp64 exp dominated this kernel), accumulation in fp64
     double total = 0.0;
-    for (int64_t b = 0; b < n_blocks; ++b)
-        total += double(partials[(b * 2 + 1) * C + c]) * double(expf(partials[(b * 2) * C + c] - bs));
-    prob_d[c] = static_cast<float>(double(bs) + log(total) - log_count);
+    if (c < C)
+        for (int64_t b = sl; b < n_blocks; b += 8)
+            total += double(partials[(b * 2 + 1) * C + c]) * double(expf(partials[(b * 2) * C + c] - bs));
+    s_sum[sl][cx] = total;
+    __syncthreads();
+    if (sl == 0 && c < C) {
+        double t = s_sum[0][cx];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) t += s_sum[q][cx];
+        prob_d[c] = static_cast<float>(double(bs) + log(t) - log_count);
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -78,7 +97,7 @@ extern "C" int mcd_pmi_finalize_f32(const float *L, int64_t ldl, int64_t K, int6
         K_total < 1 || C > (1 << 24))
         return MCD_ERR_INVALID_ARGUMENT;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    lse_combine_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(C, kLseThreads)), kLseThreads, 0, st>>>(
+    lse_combine_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(C, 32)), 256, 0, st>>>(
         partials_all, n_blocks_total, int(C), log(double(K_total)), prob_d_out);
     int rc = check_launch();
     if (rc != MCD_OK) return rc;

@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(kScanThreads)
 topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ A, int64_t lda, int64_t N,
                  int64_t K, int k, int nstage, int64_t rows_per_split, unsigned long long *__restrict__ cand,
                  uint32_t *__restrict__ kept_ws, int feed, const float *__restrict__ tau0, float *__restrict__ tau_out,
-                 int *__restrict__ flags, int only_flagged) {
+                 int *__restrict__ flags, int only_flagged, int tile_row_stride) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // the ring is declared with kMaxStages but only nstage stages are allocated: everything behind it moves up
     ScanSmem &s = *reinterpret_cast<ScanSmem *>(smem_raw - size_t(kMaxStages - nstage) * kTileRows * kUnitCols * 4);
@@ -276,7 +276,7 @@ topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
     if (feed == kFeedTensorTile && lane == 0) {
         for (int t = 0; t < nstage && t < ntiles; ++t) {
             mbar_arrive_expect_tx(&s.full[t], kTileBytes);
-            tma_tile_g2s(ring_addr + t * kTileBytes, &tmap, tx, ty0 + t * kTileRows, full_addr + t * 8, policy);
+            tma_tile_g2s(ring_addr + t * kTileBytes, &tmap, tx, ty0 + t * tile_row_stride, full_addr + t * 8, policy);
         }
     }
     // kept sets start as k empty-slot sentinels (0, 0) that sort below every real entry; the NaN threshold
@@ -348,7 +348,7 @@ topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
         if (feed == kFeedTensorTile && lane == 0 && t + nstage < ntiles) {
             fence_proxy_async();                         // generic-proxy reads before the async-proxy refill
             mbar_arrive_expect_tx(&s.full[stage], kTileBytes);
-            tma_tile_g2s(tile_addr, &tmap, tx, ty0 + (t + nstage) * kTileRows, full_addr + stage * 8, policy);
+            tma_tile_g2s(tile_addr, &tmap, tx, ty0 + (t + nstage) * tile_row_stride, full_addr + stage * 8, policy);
         }
         if (++stage == nstage) {
             stage = 0;
@@ -509,7 +509,7 @@ static bool make_plan(int64_t N, int64_t K, int64_t k64, TopkPlan *p) {
         const double lam = double(k) / kPreStride;
         int pk = static_cast<int>(lam + 6.0 * sqrt(lam) + 4.0 + 0.999);
         if (pk < 8) pk = 8;
-        const int64_t pr = N / kPreStride;
+        const int64_t pr = N / (int64_t(kTileRows) * kPreStride) * kTileRows;     // whole tiles only
         if (pk <= 128 && pr >= 4 * pk) {
             p->pre_stride = kPreStride;
             p->pre_k = pk;
@@ -560,6 +560,7 @@ struct ScanArgs {
     float *tau_out;
     int *flags;
     int only_flagged;
+    int tile_row_stride;      // kTileRows for a real scan; larger for the sample pass (tile t starts at row t * stride)
 };
 
 template <int GROUP>
@@ -568,7 +569,7 @@ static int launch_scan_t(dim3 grid, const TopkPlan &p, const CUtensorMap &map, c
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(p.smem)) != cudaSuccess)
         return MCD_ERR_CUDA;
     kern<<<grid, kScanThreads, p.smem, st>>>(map, a.A, a.lda, a.N, a.K, a.k, p.nstage, a.rows_per_split, a.cand, a.kept,
-                                             a.feed, a.tau0, a.tau_out, a.flags, a.only_flagged);
+                                             a.feed, a.tau0, a.tau_out, a.flags, a.only_flagged, a.tile_row_stride);
     return check_launch();
 }
 
@@ -610,22 +611,22 @@ extern "C" int mcd_topk_cols_f32(const float *A, int64_t lda, int64_t N, int64_t
     if (feed == kFeedTensorTile && !make_tile_map(&map, A, lda, N, K, kUnitCols, kTileRows)) feed = kFeedElements;
 
     dim3 grid(static_cast<unsigned>(ceil_div<int64_t>(K, kUnitCols)), static_cast<unsigned>(p.splits));
-    ScanArgs main_args{A, lda, N, K, p.rows_per_split, int(k), feed, cand, kept, nullptr, nullptr, nullptr, 0};
+    ScanArgs main_args{A, lda, N, K, p.rows_per_split, int(k), feed, cand, kept, nullptr, nullptr, nullptr, 0, kTileRows};
     int rc;
     if (p.pre_stride > 0 && feed == kFeedTensorTile) {
-        // pass 0: k'-th largest of every 32nd row -> start threshold per column; pass 1: the real scan starting
+        // pass 0: k'-th largest of a 1/32 row sample -> start threshold per column; pass 1: the real scan starting
         // from it; pass 2: exact redo (no start threshold) of the column groups that pass 1 flagged as short of k
         char *pre = static_cast<char *>(workspace) + p.cand_bytes + p.kept_bytes;
         float *tau = reinterpret_cast<float *>(pre);
         int *flags = reinterpret_cast<int *>(pre + (size_t(K) * 4 + 255) / 256 * 256);
         uint32_t *kept_pre = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(flags) + (size_t(grid.x) * 4 + 255) / 256 * 256);
-        CUtensorMap map_pre;
-        memset(&map_pre, 0, sizeof(map_pre));
-        if (make_tile_map(&map_pre, A, lda * p.pre_stride, p.pre_rows, K, kUnitCols, kTileRows)) {
+        {
+            // the sample is one 32-row tile out of every pre_stride tiles (contiguous rows: efficient TMA tiles);
+            // the kernel sees it as a scan of pre_rows rows whose tile t starts at row t * 32 * pre_stride
             if (cudaMemsetAsync(flags, 0, size_t(grid.x) * 4, st) != cudaSuccess) return MCD_ERR_CUDA;
-            ScanArgs pre_args{A, lda * p.pre_stride, p.pre_rows, K, ceil_div<int64_t>(p.pre_rows, kTileRows) * kTileRows,
-                              p.pre_k, feed, nullptr, kept_pre, nullptr, tau, nullptr, 0};
-            rc = launch_scan(dim3(grid.x, 1), p, map_pre, pre_args, st);
+            ScanArgs pre_args{A, lda, p.pre_rows, K, p.pre_rows, p.pre_k, feed, nullptr, kept_pre, nullptr, tau, nullptr, 0,
+                              kTileRows * p.pre_stride};
+            rc = launch_scan(dim3(grid.x, 1), p, map, pre_args, st);
             if (rc != MCD_OK) return rc;
             main_args.tau0 = tau;
             main_args.flags = flags;
