@@ -112,6 +112,13 @@ int mcd_cos_matmul_f32(const float *A, int64_t lda, const float *meanA, const fl
                        int64_t N, int64_t K, int64_t C, int cubed,
                        float *out, int64_t ldo, mcd_stream_t stream);
 
+/* ---- rank_reorder (similarity.py:99-132).  idx / vals [top_n, K] from mcd_topk_cols_f32 (top_n = int(0.05 N) <= 512),
+ *      perms [K, 5, top_n] int32: the reference's torch.randperm stream replayed on the host, baseline_ws [K] scratch.
+ *      out[j,c] = -(mean_r |t_r - asc[rank_rc]|^p / baseline_j) / (mean_r P[idx_r, c])^scale_p */
+int mcd_rank_reorder_f32(const float *P, int64_t ldp, int64_t N, int64_t C, const int32_t *idx, const float *vals,
+                         int64_t K, int64_t top_n, const int32_t *perms, float p, float scale_p,
+                         float *baseline_ws, float *out, int64_t ldo, mcd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

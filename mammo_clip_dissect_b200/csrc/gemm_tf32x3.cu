@@ -184,8 +184,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
         const int64_t row = int64_t(m_tile) * kBM + quarter * 32 + lane;
         const int64_t col0 = int64_t(n_tile) * kBN;
         const bool vec_ok = (ldp % 4 == 0) && (reinterpret_cast<uintptr_t>(P) % 16 == 0);
-#pragma unroll 1
         const int nseg = num_kb < kAccSegs ? num_kb : kAccSegs;
+#pragma unroll 1
         for (int c = 0; c < kBN; c += 32) {
             float v[32];
             tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(c), v);

@@ -290,9 +290,32 @@ def cos_similarity_cubed_single(clip_feats, target_feats, device='cuda', min_nor
 
 
 def rank_reorder(clip_feats, target_feats, device="cuda", p=3, top_fraction=0.05, scale_p=0.5, top_k=None):
-    """Reference similarity.py:99-132.  NOT on the CUDA path yet (the last of the
-    "next" rows): it needs a large-k (5 % of the probe set) selection, per-concept rank-of-rank and a host
-    replay of the reference's global-RNG torch.randperm stream.  There is deliberately no CPU fallback."""
-    raise NotImplementedError(
-        "rank_reorder is not implemented on the B200 path yet (scope row f4); soft_wpmi, wpmi, cos_similarity and "
-        "cos_similarity_cubed are")
+    """Reference similarity.py:99-132 on the GPU.  The reference draws 5 x torch.randperm(top_n) per neuron from
+    the GLOBAL CPU generator (in neuron order); the same stream is drawn here on the host and shipped to the
+    kernel, so under the same torch.manual_seed the two implementations see identical permutations.
+    Limits: top_n = int(N * top_fraction) <= 512 (N <= 10240 at the default 5 %) and K <= 65535."""
+    dev = _cuda_device(device)
+    lib = _lib.lib()
+    with torch.no_grad(), torch.cuda.device(dev):
+        P = _as_f32_matrix(clip_feats, dev, "clip_feats")
+        A = _as_f32_matrix(target_feats, dev, "target_feats")
+        if P.shape[0] != A.shape[0]:
+            raise RuntimeError("clip_feats and target_feats must share the probe-image axis")
+        N, C = P.shape
+        K = A.shape[1]
+        top_n = int(N * top_fraction)
+        if top_n < 1:
+            raise RuntimeError("rank_reorder: top_fraction selects no probe image")
+        if top_n > 512 or K > 65535:
+            raise NotImplementedError("rank_reorder on the B200 path supports top_n <= 512 and K <= 65535 "
+                                      "(got top_n=%d, K=%d)" % (top_n, K))
+        (vals, _), idx32 = topk_cols(A, top_n, dev, want_values=True, want_int32=True)
+        # the reference's RNG stream: for every neuron, five permutations of range(top_n)
+        perms = torch.stack([torch.stack([torch.randperm(top_n) for _ in range(5)]) for _ in range(K)]).to(torch.int32)
+        perms = perms.to(dev)
+        base = torch.empty((K,), dtype=torch.float32, device=dev)
+        out = torch.empty((K, C), dtype=torch.float32, device=dev)
+        _lib.check(lib.mcd_rank_reorder_f32(_ptr(P), _ld(P), N, C, _ptr(idx32), _ptr(vals), K, top_n, _ptr(perms), float(p),
+                                            float(scale_p), _ptr(base), _ptr(out), _ld(out), _stream(dev)),
+                   "mcd_rank_reorder_f32")
+    return out

@@ -230,7 +230,9 @@ def rank_reorder(clip_feats, target_feats, p=3, top_fraction=0.05, scale_p=0.5,
         for j in range(target_feats.shape[1]):
             picked = clip_feats.index_select(0, inds[:, j])            # [top_n, C] raw P
             avg = picked.mean(dim=0, keepdim=True)
-            ranks = torch.argsort(torch.argsort(picked, dim=0), dim=0)  # rank 0 = smallest
+            # rank 0 = smallest.  The reference's torch.argsort is not stable, so ties among the gathered cosines
+            # are ordered arbitrarily there; the stated rule (here and in the CUDA path) is: ties by row position.
+            ranks = torch.argsort(torch.argsort(picked, dim=0, stable=True), dim=0, stable=True)
             tgt = vals[:, j:j + 1]                                      # descending
             asc = torch.flip(tgt, dims=[0])
             if perms is None:

@@ -475,5 +475,37 @@ def test_driver_call_sequence(sim, tmp_path):
         assert (sims.cpu() - ref).abs().max().item() <= 1e-5 * refL.abs().max().item()
         assert (ids.cpu() == ref.argmax(1)).float().mean().item() >= 0.99
         assert top_ids.shape == (5, pooled.shape[1])
+    torch.manual_seed(5)
+    rr = similarity.rank_reorder(P_ref, acts["fc"], device=DEV)
+    assert rr.shape == (12, 29) and rr.is_cuda
+
+
+# ------------------------------------------------------------------------------------------------
+# rank_reorder (scope row f4): RNG stream replayed on the host, NaN where the mean cosine is negative
+# ------------------------------------------------------------------------------------------------
+def _same_with_nan(a, b, rtol):
+    assert torch.equal(torch.isnan(a), torch.isnan(b))
+    m = ~torch.isnan(a)
+    return bool(((a[m] - b[m]).abs() <= rtol * b[m].abs() + 1e-7).all())
+
+
+def test_rank_reorder_golden(sim, golden):
+    g = golden("rank_reorder_200x21x6.npz")
+    torch.manual_seed(int(g["seed"]))
+    got = sim.rank_reorder(g["clip_feats"], g["target_feats"], device=DEV).cpu()
+    assert _same_with_nan(got, g["rank_reorder"], 2e-5)
+
+
+@pytest.mark.parametrize("N,C,K,kw", [(2000, 763, 40, {}), (5000, 100, 24, {}), (1000, 37, 9, dict(p=2, top_fraction=0.1, scale_p=1.0)),
+                                       (3000, 64, 16, dict(p=2.5, scale_p=0.25))])
+def test_rank_reorder_vs_oracle(sim, N, C, K, kw):
+    P = torch.randn(N, C, generator=gen(N)) * 0.05 + 0.04          # mixed-sign means: some concepts give NaN
+    A = torch.randn(N, K, generator=gen(K))
+    torch.manual_seed(123)
+    got = sim.rank_reorder(P, A, device=DEV, **kw).cpu()
+    torch.manual_seed(123)
+    ref = orc.rank_reorder(P, A, **kw)
+    assert got.shape == ref.shape == (K, C)
+    assert _same_with_nan(got, ref, 5e-5)
     with pytest.raises(NotImplementedError):
-        similarity.rank_reorder(P_ref, acts["fc"], device=DEV)
+        sim.rank_reorder(torch.randn(20000, 8), torch.randn(20000, 4), device=DEV)      # top_n = 1000 > 512
