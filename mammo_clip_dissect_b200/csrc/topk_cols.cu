@@ -354,7 +354,7 @@ topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
             stage = 0;
             ++use;
         }
-        // the two steps share one copy of the append / fold code (instruction-cache footprint)
+        // the two 16-row steps of the tile share one copy of the append / fold code (unrolling them measured slower)
 #pragma unroll 1
         for (int half = 0; half < 2; ++half, row_step += kSubRows) {
             float4 v[kRowsPerQuad];

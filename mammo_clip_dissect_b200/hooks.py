@@ -18,6 +18,18 @@ from . import _lib
 _DTYPES = {torch.float32: _lib.F32, torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
 
 
+_WS = {}   # grow-only partials buffer per (device, stream): the hook fires once per layer per batch
+
+
+def _workspace(device, nbytes):
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, device=device)
+        _WS[key] = buf
+    return buf
+
+
 def pool_nchw(x: torch.Tensor, mode: str) -> torch.Tensor:
     """[B,C,H,W] CUDA tensor -> [B,C] spatial mean ('avg') or max ('max'), same dtype."""
     if x.dim() != 4:
@@ -34,13 +46,16 @@ def pool_nchw(x: torch.Tensor, mode: str) -> torch.Tensor:
         x = x.contiguous()          # channels_last / sliced activations: one repack, then the NCHW kernel
     lib = _lib.lib()
     out = torch.empty((B, C), dtype=x.dtype, device=x.device)
-    need = lib.mcd_pool_nchw_workspace_bytes(B, C, H, W)
-    ws = torch.empty(max(int(need), 16), dtype=torch.uint8, device=x.device)
-    with torch.cuda.device(x.device):
-        stream = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
-        code = lib.mcd_pool_nchw(ctypes.c_void_p(x.data_ptr()), _DTYPES[x.dtype], B, C, H, W,
-                                 _lib.POOL_MEAN if mode == "avg" else _lib.POOL_MAX,
-                                 ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(ws.data_ptr()), ws.numel(), stream)
+    need = int(lib.mcd_pool_nchw_workspace_bytes(B, C, H, W))
+    ws = _workspace(x.device, need) if need else None      # only planes split across CTAs need partials
+    args = (ctypes.c_void_p(x.data_ptr()), _DTYPES[x.dtype], B, C, H, W,
+            _lib.POOL_MEAN if mode == "avg" else _lib.POOL_MAX, ctypes.c_void_p(out.data_ptr()),
+            ctypes.c_void_p(ws.data_ptr() if ws is not None else 0), need)
+    if x.device.index == torch.cuda.current_device():
+        code = lib.mcd_pool_nchw(*args, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    else:
+        with torch.cuda.device(x.device):
+            code = lib.mcd_pool_nchw(*args, ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
     _lib.check(code, "mcd_pool_nchw")
     return out
 

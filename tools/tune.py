@@ -37,6 +37,8 @@ def main():
     dev = torch.device("cuda:0")
     N, K, C = args.n, args.k, 763
     g = torch.Generator(device=dev).manual_seed(0)
+    if args.what == "pool":
+        N, K = 8, 8
     A = torch.randn(N, K, generator=g, device=dev)
     if args.data == "zeros":
         A.zero_()
@@ -72,6 +74,23 @@ def main():
         _lib.set_tunable("accum_unroll", 0)
         _lib.set_tunable("accum_tile", 0)
         print("softmax: %.3f ms" % timeit(lambda: sim.concept_probabilities(P, 10, dev)))
+    if args.what in ("pool",):
+        from mammo_clip_dissect_b200.hooks import pool_nchw
+        # EfficientNet-B5 @1520x912 hooked block shapes, batch 4 (reference loader) and 32
+        for B in (4, 32):
+            tot_ms = tot_b = 0.0
+            for (Cc, H, W, reps) in ((24, 760, 456, 3), (40, 380, 228, 5), (64, 190, 114, 5), (128, 95, 57, 7),
+                                     (176, 95, 57, 7), (304, 48, 29, 9), (512, 48, 29, 3)):
+                x = torch.randn(B, Cc, H, W, device=dev)
+                ms = timeit(lambda: pool_nchw(x, "avg"), iters=10)
+                ref = timeit(lambda: x.mean(dim=[2, 3]), iters=10)
+                gbytes = x.numel() * 4 / 1e9
+                print("pool B=%d C=%d %dx%d: %.4f ms  %.0f GB/s   (torch mean: %.4f ms)" % (B, Cc, H, W, ms, gbytes / ms * 1e3, ref), flush=True)
+                tot_ms += ms * reps
+                tot_b += gbytes * reps
+                del x
+            print("pool all 39 blocks, B=%d: %.3f ms for %.2f GB -> %.0f GB/s" % (B, tot_ms, tot_b, tot_b / tot_ms * 1e3), flush=True)
+        return
     if args.what in ("gemm", "all"):
         from mammo_clip_dissect_b200 import features
         I = torch.randn(N, 512, generator=g, device=dev)
