@@ -48,10 +48,10 @@ __device__ __forceinline__ float term_lg2(float s, float w, float eps) {
 template <int TPN, int U, bool SOFT, bool VEC, bool FTZ>
 __global__ void __launch_bounds__(kAccumThreads)
 wpmi_accum_kernel(const float *__restrict__ S, int64_t lds, int C, const int32_t *__restrict__ idx, int64_t K, int k,
-                  const float *__restrict__ p, float eps, float *__restrict__ L, int64_t ldl, int n_groups, int hint) {
+                  const float *__restrict__ p, float eps, float *__restrict__ L, int64_t ldl, int n_groups) {
     constexpr int NPB = kAccumThreads / TPN;
     // the gathered rows of S are re-read ~k*K/N (33 at c4) times: ask L2 to keep them (evict-last), measured
-    // 1.15 -> 0.80 ms at c4 (tunable accum_unroll = 2 switches the hint off)
+    // 1.15 -> 0.80 ms at c4
     const uint64_t keep = l2_policy_evict_last();
     __shared__ uint32_t s_idx[NPB][kAccumMaxK];     // row offsets idx * lds (elements; the host checks N * lds < 2^32)
     __shared__ float s_p[kAccumMaxK];
@@ -89,7 +89,7 @@ wpmi_accum_kernel(const float *__restrict__ S, int64_t lds, int C, const int32_t
         for (int u = 0; u < U; ++u) {
             const float *row = base + my_idx[r + u];
             if (VEC) {
-                s[u] = hint ? ldg_nc_v4_hint(row, keep) : ldg_nc_v4(row);
+                s[u] = ldg_nc_v4_hint(row, keep);
             } else {
                 s[u].x = __ldg(row);
                 s[u].y = nvalid > 1 ? __ldg(row + 1) : 0.f;
@@ -111,7 +111,7 @@ wpmi_accum_kernel(const float *__restrict__ S, int64_t lds, int C, const int32_t
         const float *row = base + my_idx[r];
         float4 s;
         if (VEC) {
-            s = hint ? ldg_nc_v4_hint(row, keep) : ldg_nc_v4(row);
+            s = ldg_nc_v4_hint(row, keep);
         } else {
             s.x = __ldg(row);
             s.y = nvalid > 1 ? __ldg(row + 1) : 0.f;
@@ -142,10 +142,10 @@ static int launch_accum(const float *S, int64_t lds, int C, const int32_t *idx, 
     if (blocks > 0x7FFFFFFFll) return MCD_ERR_UNSUPPORTED;
     if (ftz)
         wpmi_accum_kernel<TPN, 8, SOFT, VEC, true><<<static_cast<unsigned>(blocks), kAccumThreads, 0, st>>>(
-            S, lds, C, idx, K, k, p, eps, L, ldl, static_cast<int>(n_groups), tunable(kAccumUnroll) == 2 ? 0 : 1);
+            S, lds, C, idx, K, k, p, eps, L, ldl, static_cast<int>(n_groups));
     else
         wpmi_accum_kernel<TPN, 8, SOFT, VEC, false><<<static_cast<unsigned>(blocks), kAccumThreads, 0, st>>>(
-            S, lds, C, idx, K, k, p, eps, L, ldl, static_cast<int>(n_groups), tunable(kAccumUnroll) == 2 ? 0 : 1);
+            S, lds, C, idx, K, k, p, eps, L, ldl, static_cast<int>(n_groups));
     return check_launch();
 }
 

@@ -65,8 +65,7 @@ def main():
         idx = sim._topk_int32(A, args.topk, dev)
         w = sim._reference_ramp(args.topk, 0.998, 0.97).to(dev)
         out = torch.empty((K, C), device=dev)
-        for hint in (2, 0):
-            _lib.set_tunable("accum_unroll", hint)
+        for hint in (0,):
             for t in [int(x) for x in args.tiles.split(",")]:
                 _lib.set_tunable("accum_tile", t)
                 ms = timeit(lambda: sim.log_sums(S, idx, w, 1e-7, out=out))
