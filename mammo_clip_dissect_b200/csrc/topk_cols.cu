@@ -403,6 +403,72 @@ topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
     }
 }
 
+// ---- start threshold from a row sample ---------------------------------------------------------------------------
+// sample_tilemax_kernel: per column the maximum (as an ordered key, so NaN counts as the largest value) of each
+// sampled 32-row tile -- one tile out of every `stride` (32 at c4: 1/32 of A).  Pure streaming, 16-byte loads.
+// sample_select_kernel : thread per column, the j-th largest of those tile maxima (small unsorted buffer in shared
+// memory).  It is <= the j-th largest element of the sample, so the Poisson bound of make_plan() applies to it.
+constexpr int kSampleCols = 128, kSampleThreads = 256, kSelectThreads = 128, kSelectMaxJ = 64;
+
+__global__ void __launch_bounds__(kSampleThreads)
+sample_tilemax_kernel(const float *__restrict__ A, int64_t lda, int64_t K, int64_t tile_row_stride, int vec_ok,
+                      uint32_t *__restrict__ tilemax /*[ntiles][K]*/) {
+    __shared__ uint32_t red[kSampleThreads / 32][kSampleCols];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t c = int64_t(blockIdx.x) * kSampleCols + lane * 4;
+    const int64_t r0 = int64_t(blockIdx.y) * tile_row_stride;
+    uint32_t m[4] = {0u, 0u, 0u, 0u};
+    for (int r = warp; r < kTileRows; r += kSampleThreads / 32) {
+        const float *src = A + (r0 + r) * lda + c;
+        float v[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        if (vec_ok && c + 3 < K) {
+            const float4 q = ldg_nc_v4(src);
+            v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (c + e < K) v[e] = __ldg(src + e);
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) m[e] = max(m[e], ordered_key(v[e]));
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) red[warp][lane * 4 + e] = m[e];
+    __syncthreads();
+    if (threadIdx.x < kSampleCols) {
+        uint32_t best = red[0][threadIdx.x];
+#pragma unroll
+        for (int w = 1; w < kSampleThreads / 32; ++w) best = max(best, red[w][threadIdx.x]);
+        const int64_t col = int64_t(blockIdx.x) * kSampleCols + threadIdx.x;
+        if (col < K) tilemax[int64_t(blockIdx.y) * K + col] = best;
+    }
+}
+
+__global__ void __launch_bounds__(kSelectThreads)
+sample_select_kernel(const uint32_t *__restrict__ tilemax, int ntiles, int64_t K, int j, float *__restrict__ tau) {
+    __shared__ uint32_t top[kSelectMaxJ][kSelectThreads];      // the j largest keys seen so far, unsorted
+    const int64_t col = int64_t(blockIdx.x) * kSelectThreads + threadIdx.x;
+    if (col >= K) return;
+    for (int i = 0; i < j; ++i) top[i][threadIdx.x] = 0u;
+    uint32_t low = 0u;
+    int low_at = 0;
+    for (int t = 0; t < ntiles; ++t) {
+        const uint32_t v = tilemax[int64_t(t) * K + col];
+        if (v > low) {
+            top[low_at][threadIdx.x] = v;
+            low = 0xFFFFFFFFu;
+            for (int i = 0; i < j; ++i) {
+                const uint32_t x = top[i][threadIdx.x];
+                if (x < low) {
+                    low = x;
+                    low_at = i;
+                }
+            }
+        }
+    }
+    tau[col] = key_to_threshold(low);      // NaN (admit everything) if fewer than j tiles or the j-th largest is NaN
+}
+
 // One warp per column: sort the splits*k candidates (descending 64-bit words) and emit the top k.
 constexpr int kFinishWarps = 4;
 
@@ -455,7 +521,6 @@ struct TopkPlan {
     size_t pre_bytes;                   // tau [K] floats, flags [ncb] ints, kept regions of the pre-pass
 };
 
-constexpr int kPreStride = 32;
 
 static bool make_plan(int64_t N, int64_t K, int64_t k64, TopkPlan *p) {
     if (k64 < 1 || k64 > 512) return false;     // kept-set groups: 8 x 64 entries at most
@@ -503,24 +568,29 @@ static bool make_plan(int64_t N, int64_t K, int64_t k64, TopkPlan *p) {
     p->mpad = mpad;
     p->cand_bytes = (size_t(p->splits) * size_t(k) * size_t(K) * 8 + 255) / 256 * 256;
     p->kept_bytes = size_t(ncb) * p->splits * size_t(kept_slots(k)) * kUnitCols * 8;   // (key, ~row) u32 pairs
-    // Pre-threshold: the k-th largest of a column ranks ~ Poisson(k/stride) within a stride-sample of its rows,
-    // so the (lambda + 6 sqrt(lambda) + 4)-th largest sample value has >= k column elements above it except with
-    // probability ~1e-8 (and a column that does come up short is redone exactly).
+    // Pre-threshold: the number of a column's top-k elements that fall into a 1/stride row sample is
+    // ~ Poisson(k/stride), so the j = (lambda + 6 sqrt(lambda) + 4)-th largest sample value -- and a fortiori the j-th
+    // largest of the sample's per-tile maxima, which is what is computed -- has >= k column elements above it
+    // except with probability ~1e-8 (and a column that does come up short is redone exactly).
     p->pre_stride = 0;
     p->pre_k = 0;
     p->pre_rows = 0;
     p->pre_bytes = 0;
     if (tunable(kTopkPre) != 2 && p->splits == 1 && N >= 16384 && k <= 256) {
-        const double lam = double(k) / kPreStride;
-        int pk = static_cast<int>(lam + 6.0 * sqrt(lam) + 4.0 + 0.999);
-        if (pk < 8) pk = 8;
-        const int64_t pr = N / (int64_t(kTileRows) * kPreStride) * kTileRows;     // whole tiles only
-        if (pk <= 128 && pr >= 4 * pk) {
-            p->pre_stride = kPreStride;
-            p->pre_k = pk;
-            p->pre_rows = pr;
-            p->pre_bytes = (size_t(K) * 4 + 255) / 256 * 256 + (size_t(ncb) * 4 + 255) / 256 * 256 +
-                           size_t(ncb) * size_t(kept_slots(pk)) * kUnitCols * 8;
+        static const int kStrides[] = {32, 16, 8};                  // sample one 32-row tile out of every `stride`
+        for (int stride : kStrides) {
+            const double lam = double(k) / stride;
+            int pk = static_cast<int>(lam + 6.0 * sqrt(lam) + 4.0 + 0.999);
+            if (pk < 8) pk = 8;
+            const int64_t ntile = N / (int64_t(kTileRows) * stride);
+            if (pk <= kSelectMaxJ && ntile >= 2 * pk) {
+                p->pre_stride = stride;
+                p->pre_k = pk;
+                p->pre_rows = ntile * kTileRows;
+                p->pre_bytes = (size_t(K) * 4 + 255) / 256 * 256 + (size_t(ncb) * 4 + 255) / 256 * 256 +
+                               size_t(ntile) * size_t(K) * 4;          // tau, flags, tile maxima
+                break;
+            }
         }
     }
     return true;
@@ -624,14 +694,18 @@ extern "C" int mcd_topk_cols_f32(const float *A, int64_t lda, int64_t N, int64_t
         char *pre = static_cast<char *>(workspace) + p.cand_bytes + p.kept_bytes;
         float *tau = reinterpret_cast<float *>(pre);
         int *flags = reinterpret_cast<int *>(pre + (size_t(K) * 4 + 255) / 256 * 256);
-        uint32_t *kept_pre = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(flags) + (size_t(grid.x) * 4 + 255) / 256 * 256);
+        uint32_t *tilemax = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(flags) + (size_t(grid.x) * 4 + 255) / 256 * 256);
         {
-            // the sample is one 32-row tile out of every pre_stride tiles (contiguous rows: efficient TMA tiles);
-            // the kernel sees it as a scan of pre_rows rows whose tile t starts at row t * 32 * pre_stride
+            // the sample is one 32-row tile out of every pre_stride tiles
             if (cudaMemsetAsync(flags, 0, size_t(grid.x) * 4, st) != cudaSuccess) return MCD_ERR_CUDA;
-            ScanArgs pre_args{A, lda, p.pre_rows, K, p.pre_rows, p.pre_k, feed, nullptr, kept_pre, nullptr, tau, nullptr, 0,
-                              kTileRows * p.pre_stride};
-            rc = launch_scan(dim3(grid.x, 1), p, map, pre_args, st);
+            const int nsample = static_cast<int>(p.pre_rows / kTileRows);
+            dim3 sgrid(static_cast<unsigned>(ceil_div<int64_t>(K, kSampleCols)), static_cast<unsigned>(nsample));
+            sample_tilemax_kernel<<<sgrid, kSampleThreads, 0, st>>>(A, lda, K, int64_t(kTileRows) * p.pre_stride, 1, tilemax);
+            rc = check_launch();
+            if (rc != MCD_OK) return rc;
+            sample_select_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(K, kSelectThreads)), kSelectThreads, 0, st>>>(
+                tilemax, nsample, K, p.pre_k, tau);
+            rc = check_launch();
             if (rc != MCD_OK) return rc;
             main_args.tau0 = tau;
             main_args.flags = flags;

@@ -134,7 +134,7 @@ def test_topk_pre_threshold_and_exact_redo(sim, kind):
         _lib.set_tunable("topk_splits", 1)
         n0 = _lib.launch_count()
         got = sim.topk_cols(A, k, device=DEV)
-        assert _lib.launch_count() - n0 == 4            # sample pass, scan, redo pass, finish
+        assert _lib.launch_count() - n0 == 5            # sample tile maxima, select, scan, redo pass, finish
         assert torch.equal(got.cpu(), ref), kind
         _lib.set_tunable("topk_pre", 2)                  # scheme off
         n0 = _lib.launch_count()
