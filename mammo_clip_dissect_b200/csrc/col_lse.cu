@@ -14,6 +14,8 @@ namespace mcd {
 
 constexpr int kLseThreads = 128;
 
+// thread per concept, one pass over the block's 256 rows with an online (max, sum) pair: the running sum is
+// rescaled whenever the maximum rises (the rescale factor is exactly 1 otherwise), loads 4 rows ahead
 __global__ void __launch_bounds__(kLseThreads)
 col_lse_partials_kernel(const float *__restrict__ L, int64_t ldl, int64_t K, int C, float *__restrict__ partials) {
     const int c = blockIdx.x * kLseThreads + threadIdx.x;
@@ -22,11 +24,29 @@ col_lse_partials_kernel(const float *__restrict__ L, int64_t ldl, int64_t K, int
     const int64_t j0 = b * MCD_LSE_BLOCK;
     const int64_t j1 = min(K, j0 + MCD_LSE_BLOCK);
     const float *col = L + c;
-    float m = -INFINITY;
-    for (int64_t j = j0; j < j1; ++j) m = fmaxf(m, col[j * ldl]);
-    const float ms = (m == -INFINITY) ? 0.f : m;
-    float s = 0.f;
-    for (int64_t j = j0; j < j1; ++j) s += expf(col[j * ldl] - ms);
+    float m = -INFINITY, s = 0.f;
+    int64_t j = j0;
+    for (; j + 4 <= j1; j += 4) {
+        const float x0 = col[j * ldl], x1 = col[(j + 1) * ldl], x2 = col[(j + 2) * ldl], x3 = col[(j + 3) * ldl];
+        const float mx = fmaxf(fmaxf(x0, x1), fmaxf(x2, x3));
+        if (mx > m) {
+            s *= (m == -INFINITY) ? 0.f : expf(m - mx);
+            m = mx;
+        }
+        const float ms = (m == -INFINITY) ? 0.f : m;
+        s += expf(x0 - ms);
+        s += expf(x1 - ms);
+        s += expf(x2 - ms);
+        s += expf(x3 - ms);
+    }
+    for (; j < j1; ++j) {
+        const float x = col[j * ldl];
+        if (x > m) {
+            s *= (m == -INFINITY) ? 0.f : expf(m - x);
+            m = x;
+        }
+        s += expf(x - ((m == -INFINITY) ? 0.f : m));
+    }
     partials[(b * 2 + 0) * C + c] = m;
     partials[(b * 2 + 1) * C + c] = s;
 }
@@ -65,15 +85,14 @@ lse_combine_kernel(const float *__restrict__ partials, int64_t n_blocks, int C, 
     }
 }
 
+// thread per concept, rows strided over blockIdx.y: no integer division, coalesced along the concept axis
 __global__ void __launch_bounds__(256)
 pmi_finalize_kernel(const float *__restrict__ L, int64_t ldl, int64_t K, int C, const float *__restrict__ prob_d,
                     float lam, float *__restrict__ out, int64_t ldo) {
-    const int64_t total = K * int64_t(C);
-    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += int64_t(gridDim.x) * blockDim.x) {
-        const int64_t j = i / C;
-        const int c = static_cast<int>(i - j * C);
-        out[j * ldo + c] = __fsub_rn(L[j * ldl + c], __fmul_rn(lam, prob_d[c]));
-    }
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= C) return;
+    const float shift = __fmul_rn(lam, prob_d[c]);
+    for (int64_t j = blockIdx.y; j < K; j += gridDim.y) out[j * ldo + c] = __fsub_rn(L[j * ldl + c], shift);
 }
 
 }  // namespace mcd
@@ -101,11 +120,11 @@ extern "C" int mcd_pmi_finalize_f32(const float *L, int64_t ldl, int64_t K, int6
         partials_all, n_blocks_total, int(C), log(double(K_total)), prob_d_out);
     int rc = check_launch();
     if (rc != MCD_OK) return rc;
-    const int64_t total = K * C;
-    int64_t blocks = ceil_div<int64_t>(total, 256 * 4);
-    const int64_t cap = int64_t(num_sms()) * 16;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    pmi_finalize_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(L, ldl, K, int(C), prob_d_out, lam, out, ldo);
+    int64_t rows = int64_t(num_sms()) * 16 / ceil_div<int64_t>(C, 256);
+    if (rows > K) rows = K;
+    if (rows > 65535) rows = 65535;
+    if (rows < 1) rows = 1;
+    dim3 grid(static_cast<unsigned>(ceil_div<int64_t>(C, 256)), static_cast<unsigned>(rows));
+    pmi_finalize_kernel<<<grid, 256, 0, st>>>(L, ldl, K, int(C), prob_d_out, lam, out, ldo);
     return check_launch();
 }
