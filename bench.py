@@ -261,7 +261,8 @@ def run_ours(args):
         e2e = {"value": round(K_NEURONS * world / (ms_e2e / 1e3), 1), "unit": UNIT,
                "h2d_bytes_per_step": int(P_h.numel() * 4 + A_h.numel() * 4), "d2h_bytes_per_step": int(res_h.numel() * 4),
                "ms_per_step": round(ms_e2e, 3), "steps": e2e_steps,
-               "api": "similarity.soft_wpmi(P_host_pinned, A_host_pinned, device='cuda') -> scores copied to host"}
+               "api": ("similarity.soft_wpmi" if world == 1 else "distributed.soft_wpmi_sharded") +
+                      "(P_host_pinned, A_host_pinned, device='cuda') -> score matrix copied to pinned host memory"}
     except RuntimeError as exc:                      # e.g. the box cannot pin 13.4 GB
         e2e = {"value": None, "unit": UNIT, "error": str(exc)[:200]}
 

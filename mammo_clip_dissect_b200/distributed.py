@@ -60,10 +60,12 @@ class CudaBackend:
             return sim.log_sums(S, idx32, weights, min_prob)
 
     def lse_partials(self, L):
-        return self.sim.lse_partials(L)
+        with self.sim._Stage("lse_partials"):
+            return self.sim.lse_partials(L)
 
     def finalize(self, L, partials_all, K_total, lam):
-        return self.sim.pmi_finalize(L, partials_all, K_total, lam)[0]
+        with self.sim._Stage("lse_finalize"):
+            return self.sim.pmi_finalize(L, partials_all, K_total, lam)[0]
 
 
 def _all_gather_var(t: torch.Tensor, sizes: Sequence[int], group) -> torch.Tensor:
@@ -102,7 +104,11 @@ def pmi_scores_sharded(clip_feats, target_shard, shard_sizes: Sequence[int], top
     local = backend.finalize(L, part_all, K_total, lam)
     if not gather_scores or world == 1:
         return local
-    return _all_gather_var(local, list(shard_sizes), group)
+    stage = getattr(getattr(backend, "sim", None), "_Stage", None)
+    if stage is None:
+        return _all_gather_var(local, list(shard_sizes), group)
+    with stage("allgather_scores"):
+        return _all_gather_var(local, list(shard_sizes), group)
 
 
 def soft_wpmi_sharded(clip_feats, target_shard, shard_sizes, top_k=100, a=10, lam=1, device='cuda',
