@@ -36,7 +36,7 @@ def main():
     lines = ["# ncu summary of `%s`" % os.path.basename(rep), "",
              "Captured with `ncu --set full --clock-control none --import-source on` under gpurun on a B200; read with",
              "`ncu -i ... --page raw --csv` (tools/ncu_summary.py).  Per-launch values.", ""]
-    traffic = {}
+    traffic, seen = {}, {}
     tpath = os.path.join(os.path.dirname(out), "traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath))
@@ -55,7 +55,11 @@ def main():
             v, un = float(d[key]), u[key]
             return v * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "Tbyte": 1e12}[un]
         try:
-            traffic[short.split("<")[0]] = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
+            key = short.split("<")[0]
+            val = to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum")
+            # a kernel launched more than once per call (the scan and its redo pass): keep the dominant launch
+            seen[key] = max(seen.get(key, 0.0), val)
+            traffic[key] = seen[key]
         except (KeyError, ValueError):
             pass
     with open(out + ".md", "w") as f:
