@@ -76,7 +76,9 @@ int mcd_topk_cols_f32(const float *A, int64_t lda, int64_t N, int64_t K, int64_t
 
 /* ---- K3: L[j,c] = sum_r log(1 + p[r] (S[idx[r,j],c] - 1) + min_prob)   (soft-WPMI body,
  *      similarity.py:59-65); p == NULL gives sum_r log(S[idx[r,j],c] + min_prob) (WPMI body,
- *      similarity.py:85-89).  S [N,C] (lds), idx [k,K] int32 (ld = K), p [k], L [K,C] (ldl). */
+ *      similarity.py:85-89).  S [N,C] (lds), idx [k,K] int32 (ld = K), p [k], L [K,C] (ldl).
+ *      S is a probability matrix (what mcd_softmax_rows_f32 / mcd_gemm_nt_softmax_f32 write):
+ *      finite entries must lie in [0, 1]; NaN propagates.  Limits: k <= 512, N * lds < 2^30. */
 int mcd_wpmi_accum_f32(const float *S, int64_t lds, int64_t N, int64_t C,
                        const int32_t *idx, int64_t K, int64_t k, const float *p, float min_prob,
                        float *L, int64_t ldl, mcd_stream_t stream);

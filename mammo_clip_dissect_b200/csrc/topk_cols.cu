@@ -408,7 +408,7 @@ topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
 // sampled 32-row tile -- one tile out of every `stride` (32 at c4: 1/32 of A).  Pure streaming, 16-byte loads.
 // sample_select_kernel : thread per column, the j-th largest of those tile maxima (small unsorted buffer in shared
 // memory).  It is <= the j-th largest element of the sample, so the Poisson bound of make_plan() applies to it.
-constexpr int kSampleCols = 128, kSampleThreads = 256, kSelectThreads = 128, kSelectMaxJ = 64;
+constexpr int kSampleCols = 128, kSampleThreads = 256, kSelectThreads = 64, kSelectMaxJ = 64;
 
 __global__ void __launch_bounds__(kSampleThreads)
 sample_tilemax_kernel(const float *__restrict__ A, int64_t lda, int64_t K, int64_t tile_row_stride, int vec_ok,
@@ -452,8 +452,7 @@ sample_select_kernel(const uint32_t *__restrict__ tilemax, int ntiles, int64_t K
     for (int i = 0; i < j; ++i) top[i][threadIdx.x] = 0u;
     uint32_t low = 0u;
     int low_at = 0;
-    for (int t = 0; t < ntiles; ++t) {
-        const uint32_t v = tilemax[int64_t(t) * K + col];
+    auto offer = [&](uint32_t v) {
         if (v > low) {
             top[low_at][threadIdx.x] = v;
             low = 0xFFFFFFFFu;
@@ -465,7 +464,18 @@ sample_select_kernel(const uint32_t *__restrict__ tilemax, int ntiles, int64_t K
                 }
             }
         }
+    };
+    // the loads of a batch are independent (the scan of the small buffer is not): 8 L2 round trips overlap
+    constexpr int kBatch = 8;
+    int t = 0;
+    for (; t + kBatch <= ntiles; t += kBatch) {
+        uint32_t v[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) v[u] = tilemax[int64_t(t + u) * K + col];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) offer(v[u]);
     }
+    for (; t < ntiles; ++t) offer(tilemax[int64_t(t) * K + col]);
     tau[col] = key_to_threshold(low);      // NaN (admit everything) if fewer than j tiles or the j-th largest is NaN
 }
 
@@ -504,6 +514,69 @@ topk_finish_kernel(const unsigned long long *__restrict__ cand, int M, int Mpad,
         if (idx64) idx64[o] = static_cast<int64_t>(row);
         if (idx32) idx32[o] = static_cast<int32_t>(row);
         if (vals) vals[o] = A[int64_t(row) * lda + col];
+    }
+}
+
+// The common case (splits * k <= 128, e.g. the default k = 100 of soft_wpmi): the same bitonic network with the
+// 128 words in registers, word i = 4 * lane + slot.  Strides 1 and 2 exchange inside a lane, strides 4..64 with
+// shfl.xor; no shared memory, no loops left after unrolling -- about a third of the instructions of the generic
+// kernel.  A CTA is 8 warps = 8 adjacent columns, so its index stores fill whole 32-byte sectors.
+constexpr int kFinishRegWarps = 8;
+
+__device__ __forceinline__ void cmpx(unsigned long long &a, unsigned long long &b, bool a_keeps_max) {
+    const unsigned long long hi = a > b ? a : b, lo = a > b ? b : a;
+    a = a_keeps_max ? hi : lo;
+    b = a_keeps_max ? lo : hi;
+}
+
+__global__ void __launch_bounds__(kFinishRegWarps * 32)
+topk_finish128_kernel(const unsigned long long *__restrict__ cand, int M, int k, int64_t K,
+                      const float *__restrict__ A, int64_t lda, int64_t *__restrict__ idx64,
+                      int32_t *__restrict__ idx32, float *__restrict__ vals) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t col = int64_t(blockIdx.x) * kFinishRegWarps + warp;
+    if (col >= K) return;
+    unsigned long long v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int i = lane * 4 + e;
+        v[e] = i < M ? cand[int64_t(i) * K + col] : 0ull;
+    }
+#pragma unroll
+    for (int size = 2; size <= 128; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= 4) {
+                // descending block <=> (i & size) == 0; the lower index of a pair keeps the maximum there
+                const bool desc = size >= 128 || ((lane * 4) & size) == 0;
+                const bool upper = (lane & (stride >> 2)) != 0;
+                const bool keep_max = desc != upper;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const unsigned long long o = __shfl_xor_sync(0xffffffffu, v[e], stride >> 2);
+                    const unsigned long long hi = v[e] > o ? v[e] : o, lo = v[e] > o ? o : v[e];
+                    v[e] = keep_max ? hi : lo;
+                }
+            } else if (stride == 2) {
+                const bool d0 = ((lane * 4 + 0) & size) == 0;       // same block for all four words when size >= 4
+                cmpx(v[0], v[2], d0);
+                cmpx(v[1], v[3], d0);
+            } else {
+                cmpx(v[0], v[1], ((lane * 4 + 0) & size) == 0);
+                cmpx(v[2], v[3], ((lane * 4 + 2) & size) == 0);
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int r = lane * 4 + e;
+        if (r < k) {
+            const uint32_t row = ~static_cast<uint32_t>(v[e]);
+            const int64_t o = int64_t(r) * K + col;
+            if (idx64) idx64[o] = static_cast<int64_t>(row);
+            if (idx32) idx32[o] = static_cast<int32_t>(row);
+            if (vals) vals[o] = A[int64_t(row) * lda + col];
+        }
     }
 }
 
@@ -717,6 +790,12 @@ extern "C" int mcd_topk_cols_f32(const float *A, int64_t lda, int64_t N, int64_t
     rc = launch_scan(grid, p, map, main_args, st);
     if (rc != MCD_OK) return rc;
 
+    if (p.mpad <= 128 && tunable(kTopkVariant) != 2) {
+        const unsigned fgrid = static_cast<unsigned>(ceil_div<int64_t>(K, kFinishRegWarps));
+        topk_finish128_kernel<<<fgrid, kFinishRegWarps * 32, 0, st>>>(cand, p.splits * int(k), int(k), K, A, lda,
+                                                                      idx64_out, idx32_out, vals_out);
+        return check_launch();
+    }
     const size_t fsmem = size_t(kFinishWarps) * p.mpad * sizeof(unsigned long long);
     if (cudaFuncSetAttribute(topk_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fsmem)) != cudaSuccess)
         return MCD_ERR_CUDA;

@@ -31,44 +31,67 @@ __device__ __forceinline__ float lg2_fast(float x) {
     return r;
 }
 
-template <bool SOFT, bool FTZ>
-__device__ __forceinline__ float term_lg2(float s, float w, float eps) {
-    float v;
+// value inside the log: the reference's unfused sequence (sub, mul, add, add)
+template <bool SOFT>
+__device__ __forceinline__ float term(float s, float w, float eps) {
     if (SOFT) {
-        v = __fsub_rn(s, 1.0f);
+        float v = __fsub_rn(s, 1.0f);
         v = __fmul_rn(w, v);
         v = __fadd_rn(1.0f, v);
-        v = __fadd_rn(v, eps);
-    } else {
-        v = __fadd_rn(s, eps);
+        return __fadd_rn(v, eps);
     }
-    return lg2_fast<FTZ>(v);
+    return __fadd_rn(s, eps);
 }
 
-template <int TPN, int U, bool SOFT, bool VEC, bool FTZ>
+template <bool VEC>
+__device__ __forceinline__ float4 load_row(const char *base, uint32_t off, int nvalid, uint64_t keep) {
+    const float *row = reinterpret_cast<const float *>(base + off);
+    if (VEC) return ldg_nc_v4_hint(row, keep);
+    float4 s;
+    s.x = __ldg(row);
+    s.y = nvalid > 1 ? __ldg(row + 1) : 0.f;
+    s.z = nvalid > 2 ? __ldg(row + 2) : 0.f;
+    s.w = nvalid > 3 ? __ldg(row + 3) : 0.f;
+    return s;
+}
+
+// The MUFU pipe (16 lg2 / clk / SM) is the binding unit of this kernel when every term gets its own lg2
+// (k*K*C = 2.5e9 logs at c4 = 0.54 ms).  With GROUPED the terms of 4 consecutive ranks are multiplied first:
+// log(t0 t1 t2 t3), one lg2 per 4 terms.  Valid when every term lies in [eps, 1 + eps] with eps >= 1e-9 (no
+// underflow: the product is >= 1e-36; no sign cancellation), i.e. for probabilities S in [0,1] and weights p in
+// [0,1]; the host checks eps, the CTA checks p, S in [0,1] is the documented domain of this entry point.  The extra
+// rounding (3 products, 6e-8 relative each = 1.8e-7 absolute in the log) is below lg2.approx's own error.
+template <int TPN, int U, bool SOFT, bool VEC, bool FTZ, bool GROUPED>
 __global__ void __launch_bounds__(kAccumThreads)
 wpmi_accum_kernel(const float *__restrict__ S, int64_t lds, int C, const int32_t *__restrict__ idx, int64_t K, int k,
                   const float *__restrict__ p, float eps, float *__restrict__ L, int64_t ldl, int n_groups) {
+    static_assert(U == 8, "two groups of four ranks per iteration");
     constexpr int NPB = kAccumThreads / TPN;
     // the gathered rows of S are re-read ~k*K/N (33 at c4) times: ask L2 to keep them (evict-last), measured
     // 1.15 -> 0.80 ms at c4
     const uint64_t keep = l2_policy_evict_last();
-    __shared__ uint32_t s_idx[NPB][kAccumMaxK];     // row offsets idx * lds (elements; the host checks N * lds < 2^32)
-    __shared__ float s_p[kAccumMaxK];
+    __shared__ __align__(16) uint32_t s_off[NPB][kAccumMaxK];   // BYTE offsets idx * lds * 4 (host: N * lds < 2^30)
+    __shared__ __align__(16) float s_p[kAccumMaxK];
 
     const int tile = blockIdx.x / n_groups;
     const int group = blockIdx.x - tile * n_groups;
     const int64_t j0 = int64_t(group) * NPB;
     const int tid = threadIdx.x;
 
-    for (int i = tid; i < NPB * k; i += kAccumThreads) {
-        const int n = i / k, r = i - n * k;
+    for (int n = 0; n < NPB; ++n) {
         const int64_t j = j0 + n;
-        s_idx[n][r] = j < K ? uint32_t(idx[int64_t(r) * K + j]) * uint32_t(lds) : 0u;
+        for (int r = tid; r < k; r += kAccumThreads)
+            s_off[n][r] = j < K ? uint32_t(idx[int64_t(r) * K + j]) * uint32_t(lds) * 4u : 0u;
     }
+    bool p_ok = true;
     if (SOFT)
-        for (int r = tid; r < k; r += kAccumThreads) s_p[r] = p[r];
-    __syncthreads();
+        for (int r = tid; r < k; r += kAccumThreads) {
+            const float w = p[r];
+            s_p[r] = w;
+            p_ok = p_ok && (w >= 0.f) && (w <= 1.f);
+        }
+    const bool grouped = GROUPED && (__syncthreads_and(p_ok) != 0);
+    if (!GROUPED) __syncthreads();
 
     const int n = tid / TPN;
     const int tl = tid - n * TPN;
@@ -78,51 +101,73 @@ wpmi_accum_kernel(const float *__restrict__ S, int64_t lds, int C, const int32_t
     const int nvalid = min(4, C - c0);
     // a vector load may run past C only inside the row's padding (c0 + 4 <= lds is guaranteed by
     // the host when VEC); the scalar path loads exactly the valid columns
-    const float *base = S + c0;
-    const uint32_t *my_idx = s_idx[n];
+    const char *base = reinterpret_cast<const char *>(S + c0);
+    const uint32_t *my_off = s_off[n];
 
     float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
     int r = 0;
-    for (; r + U <= k; r += U) {
-        float4 s[U];
+    if (grouped) {
+        for (; r + U <= k; r += U) {
+            float4 s[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const float *row = base + my_idx[r + u];
-            if (VEC) {
-                s[u] = ldg_nc_v4_hint(row, keep);
-            } else {
-                s[u].x = __ldg(row);
-                s[u].y = nvalid > 1 ? __ldg(row + 1) : 0.f;
-                s[u].z = nvalid > 2 ? __ldg(row + 2) : 0.f;
-                s[u].w = nvalid > 3 ? __ldg(row + 3) : 0.f;
+            for (int u = 0; u < U; ++u) s[u] = load_row<VEC>(base, my_off[r + u], nvalid, keep);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float *acc = h ? acc1 : acc0;
+                float w[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) w[u] = SOFT ? s_p[r + 4 * h + u] : 0.f;
+                const float4 *q = s + 4 * h;
+                acc[0] += lg2_fast<FTZ>((term<SOFT>(q[0].x, w[0], eps) * term<SOFT>(q[1].x, w[1], eps)) *
+                                        (term<SOFT>(q[2].x, w[2], eps) * term<SOFT>(q[3].x, w[3], eps)));
+                acc[1] += lg2_fast<FTZ>((term<SOFT>(q[0].y, w[0], eps) * term<SOFT>(q[1].y, w[1], eps)) *
+                                        (term<SOFT>(q[2].y, w[2], eps) * term<SOFT>(q[3].y, w[3], eps)));
+                acc[2] += lg2_fast<FTZ>((term<SOFT>(q[0].z, w[0], eps) * term<SOFT>(q[1].z, w[1], eps)) *
+                                        (term<SOFT>(q[2].z, w[2], eps) * term<SOFT>(q[3].z, w[3], eps)));
+                acc[3] += lg2_fast<FTZ>((term<SOFT>(q[0].w, w[0], eps) * term<SOFT>(q[1].w, w[1], eps)) *
+                                        (term<SOFT>(q[2].w, w[2], eps) * term<SOFT>(q[3].w, w[3], eps)));
             }
         }
+        for (; r + 4 <= k; r += 4) {
+            float4 q[4];
+            float w[4];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const float w = SOFT ? s_p[r + u] : 0.f;
-            float *acc = (u & 1) ? acc1 : acc0;
-            acc[0] += term_lg2<SOFT, FTZ>(s[u].x, w, eps);
-            acc[1] += term_lg2<SOFT, FTZ>(s[u].y, w, eps);
-            acc[2] += term_lg2<SOFT, FTZ>(s[u].z, w, eps);
-            acc[3] += term_lg2<SOFT, FTZ>(s[u].w, w, eps);
+            for (int u = 0; u < 4; ++u) {
+                q[u] = load_row<VEC>(base, my_off[r + u], nvalid, keep);
+                w[u] = SOFT ? s_p[r + u] : 0.f;
+            }
+            acc0[0] += lg2_fast<FTZ>((term<SOFT>(q[0].x, w[0], eps) * term<SOFT>(q[1].x, w[1], eps)) *
+                                     (term<SOFT>(q[2].x, w[2], eps) * term<SOFT>(q[3].x, w[3], eps)));
+            acc0[1] += lg2_fast<FTZ>((term<SOFT>(q[0].y, w[0], eps) * term<SOFT>(q[1].y, w[1], eps)) *
+                                     (term<SOFT>(q[2].y, w[2], eps) * term<SOFT>(q[3].y, w[3], eps)));
+            acc0[2] += lg2_fast<FTZ>((term<SOFT>(q[0].z, w[0], eps) * term<SOFT>(q[1].z, w[1], eps)) *
+                                     (term<SOFT>(q[2].z, w[2], eps) * term<SOFT>(q[3].z, w[3], eps)));
+            acc0[3] += lg2_fast<FTZ>((term<SOFT>(q[0].w, w[0], eps) * term<SOFT>(q[1].w, w[1], eps)) *
+                                     (term<SOFT>(q[2].w, w[2], eps) * term<SOFT>(q[3].w, w[3], eps)));
+        }
+    } else {
+        for (; r + U <= k; r += U) {
+            float4 s[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) s[u] = load_row<VEC>(base, my_off[r + u], nvalid, keep);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const float w = SOFT ? s_p[r + u] : 0.f;
+                float *acc = (u & 1) ? acc1 : acc0;
+                acc[0] += lg2_fast<FTZ>(term<SOFT>(s[u].x, w, eps));
+                acc[1] += lg2_fast<FTZ>(term<SOFT>(s[u].y, w, eps));
+                acc[2] += lg2_fast<FTZ>(term<SOFT>(s[u].z, w, eps));
+                acc[3] += lg2_fast<FTZ>(term<SOFT>(s[u].w, w, eps));
+            }
         }
     }
     for (; r < k; ++r) {
-        const float *row = base + my_idx[r];
-        float4 s;
-        if (VEC) {
-            s = ldg_nc_v4_hint(row, keep);
-        } else {
-            s.x = __ldg(row);
-            s.y = nvalid > 1 ? __ldg(row + 1) : 0.f;
-            s.z = nvalid > 2 ? __ldg(row + 2) : 0.f;
-            s.w = nvalid > 3 ? __ldg(row + 3) : 0.f;
-        }
+        const float4 s = load_row<VEC>(base, my_off[r], nvalid, keep);
         const float w = SOFT ? s_p[r] : 0.f;
-        acc0[0] += term_lg2<SOFT, FTZ>(s.x, w, eps);
-        acc0[1] += term_lg2<SOFT, FTZ>(s.y, w, eps);
-        acc0[2] += term_lg2<SOFT, FTZ>(s.z, w, eps);
-        acc0[3] += term_lg2<SOFT, FTZ>(s.w, w, eps);
+        acc0[0] += lg2_fast<FTZ>(term<SOFT>(s.x, w, eps));
+        acc0[1] += lg2_fast<FTZ>(term<SOFT>(s.y, w, eps));
+        acc0[2] += lg2_fast<FTZ>(term<SOFT>(s.z, w, eps));
+        acc0[3] += lg2_fast<FTZ>(term<SOFT>(s.w, w, eps));
     }
     constexpr float kLn2 = 0.693147180559945309417f;
     float *out = L + j * ldl + c0;
@@ -140,11 +185,16 @@ static int launch_accum(const float *S, int64_t lds, int C, const int32_t *idx, 
     const int64_t n_groups = ceil_div<int64_t>(K, NPB);
     const int64_t blocks = n_groups * n_tiles;
     if (blocks > 0x7FFFFFFFll) return MCD_ERR_UNSUPPORTED;
-    if (ftz)
-        wpmi_accum_kernel<TPN, 8, SOFT, VEC, true><<<static_cast<unsigned>(blocks), kAccumThreads, 0, st>>>(
+    // grouped logs need eps >= 1e-9 (see the kernel); tunable accum_unroll = 1 forces one lg2 per term
+    const bool grouped = eps >= 1e-9f && eps <= 1.0f && tunable(kAccumUnroll) != 1;
+    if (grouped)
+        wpmi_accum_kernel<TPN, 8, SOFT, VEC, true, true><<<static_cast<unsigned>(blocks), kAccumThreads, 0, st>>>(
+            S, lds, C, idx, K, k, p, eps, L, ldl, static_cast<int>(n_groups));
+    else if (ftz)
+        wpmi_accum_kernel<TPN, 8, SOFT, VEC, true, false><<<static_cast<unsigned>(blocks), kAccumThreads, 0, st>>>(
             S, lds, C, idx, K, k, p, eps, L, ldl, static_cast<int>(n_groups));
     else
-        wpmi_accum_kernel<TPN, 8, SOFT, VEC, false><<<static_cast<unsigned>(blocks), kAccumThreads, 0, st>>>(
+        wpmi_accum_kernel<TPN, 8, SOFT, VEC, false, false><<<static_cast<unsigned>(blocks), kAccumThreads, 0, st>>>(
             S, lds, C, idx, K, k, p, eps, L, ldl, static_cast<int>(n_groups));
     return check_launch();
 }
@@ -169,7 +219,7 @@ extern "C" int mcd_wpmi_accum_f32(const float *S, int64_t lds, int64_t N, int64_
                                   mcd_stream_t stream) {
     using namespace mcd;
     if (!S || !idx || !L || N < 1 || C < 1 || K < 1 || k < 1 || lds < C || ldl < C) return MCD_ERR_INVALID_ARGUMENT;
-    if (k > kAccumMaxK || C > (1 << 24) || N * lds >= (int64_t(1) << 32)) return MCD_ERR_UNSUPPORTED;
+    if (k > kAccumMaxK || C > (1 << 24) || N * lds >= (int64_t(1) << 30)) return MCD_ERR_UNSUPPORTED;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // 16-byte loads need aligned rows and must stay inside a row (padding included)
     const bool vec = (lds % 4 == 0) && (reinterpret_cast<uintptr_t>(S) % 16 == 0) && (ceil_div<int64_t>(C, 4) * 4 <= lds);

@@ -111,6 +111,23 @@ def test_topk_strided_unaligned_and_forced_splits(sim):
         _lib.set_tunable("topk_cols", 0)
 
 
+@pytest.mark.parametrize("k", [1, 5, 31, 64, 100, 128])
+def test_topk_finish_register_and_generic_sorters_agree(sim, k):
+    """splits * k <= 128 takes the register-resident bitonic network; topk_variant = 2 forces the shared-memory one."""
+    from mammo_clip_dissect_b200 import _lib
+    A = torch.randn(1500, 77, generator=gen(12)).round(decimals=1)         # heavy ties: the index order matters
+    A[5, 3] = float("nan")
+    ref_v, ref_i = orc.topk_cols(A, k)
+    got = sim.topk_cols(A, k, device=DEV, want_values=True)
+    try:
+        _lib.set_tunable("topk_variant", 2)
+        gen_i = sim.topk_cols(A, k, device=DEV).cpu()
+    finally:
+        _lib.set_tunable("topk_variant", 0)
+    assert torch.equal(got[1].cpu(), ref_i) and torch.equal(gen_i, ref_i)
+    assert torch.equal(got[0].cpu().nan_to_num(7.0), ref_v.nan_to_num(7.0))
+
+
 @pytest.mark.parametrize("kind", ["randn", "spikes_on_sampled_rows", "relu", "const", "nan_cols", "sorted_up"])
 def test_topk_pre_threshold_and_exact_redo(sim, kind):
     """Long single-split scans start from a sampled threshold (k'-th largest of every 32nd row); column groups
@@ -256,6 +273,30 @@ def test_accumulate_concept_tiles(sim, tile):
     finally:
         _lib.set_tunable("accum_tile", 0)
     assert (out - ref).abs().max().item() <= 1e-5 * refL.abs().max().item()
+
+
+@pytest.mark.parametrize("k", [1, 3, 4, 7, 8, 12, 50, 101])
+@pytest.mark.parametrize("case", ["soft", "hard", "tiny_eps", "weights_above_one", "per_term"])
+def test_accumulate_grouped_logs_and_fallbacks(sim, k, case):
+    """K3 multiplies the terms of 4 ranks before one lg2 when eps >= 1e-9 and every weight is in [0,1]; otherwise
+    (and with the tunable) it takes one lg2 per term.  All paths against the oracle, incl. NaN where the reference
+    takes the log of a negative number."""
+    from mammo_clip_dissect_b200 import _lib
+    S = torch.softmax(10 * torch.randn(400, 131, generator=gen(31)) * 0.3, dim=1)
+    idx = torch.stack([torch.randperm(400, generator=gen(32 + j))[:k] for j in range(45)], dim=1)   # [k, 45]
+    eps = 1e-12 if case == "tiny_eps" else 1e-7
+    w = None if case == "hard" else orc.p_ramp(k, 1.3 if case == "weights_above_one" else 0.998, 0.97)
+    ref = orc.log_sums_chunked(S, idx, w, eps)
+    try:
+        _lib.set_tunable("accum_unroll", 1 if case == "per_term" else 0)
+        out = sim.log_sums(S.to(DEV), idx.to(DEV).int(), None if w is None else w.to(DEV), eps).cpu()
+    finally:
+        _lib.set_tunable("accum_unroll", 0)
+    if case == "weights_above_one":
+        assert ref.isnan().any() or k < 3                      # the case is meant to reach log(negative)
+        assert torch.equal(out.isnan(), ref.isnan())
+    fin = ~ref.isnan()
+    assert ((out[fin] - ref[fin]).abs() <= 1e-5 * ref[fin].abs() + 1e-6).all()
 
 
 def test_tied_activations_use_the_stated_rule(sim):
