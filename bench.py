@@ -164,6 +164,10 @@ def workload_config(n_gpus):
     return {"workload": "c4: soft_wpmi, clip_feats 100000x763, target_feats 100000x32768 per GPU, top_k=100, a=10, lam=1",
             "N_img": N_IMG, "K_per_gpu": K_NEURONS, "K_total": K_NEURONS * n_gpus, "C": C_CONCEPTS, "top_k": TOP_K,
             "parallelism": "neuron-sharded x%d" % n_gpus,
+            "score_exchange": ("none (one GPU)" if n_gpus == 1 else
+                               {"copy": "DMA pushes into peer-mapped [K_total,C] buffers, overlapped with the next call's scan",
+                                "fused": "finalize kernel stores into all peers' [K_total,C] buffers",
+                                "nccl": "NCCL all_gather"}.get(os.environ.get("MCD_EXCHANGE", "copy"), "?")),
             "l2_policy": "inputs (13.4 GB per GPU) exceed the 126 MB L2; no flush needed"}
 
 
@@ -194,11 +198,27 @@ def run_ours(args):
     A = torch.randn(N_IMG, K_NEURONS, generator=g, device=dev)
     shard_sizes = [K_NEURONS] * world
     backend = mdist.CudaBackend(dev) if world > 1 else None
+    # N > 1: the [K_total, C] scores are exchanged through symmetric (peer-mapped) memory.  "copy": DMA pushes on side
+    # streams, the exchange of call i runs behind the column scan of call i+1 (double-buffered, at most one exchange in
+    # flight, the last one is waited for inside the timed region); "fused": the finalize kernel stores into all peers;
+    # "nccl": torch.distributed all_gather.
+    xmode = os.environ.get("MCD_EXCHANGE", "copy")
+    exchange = mdist.PeerScoreExchange(shard_sizes, C_CONCEPTS, dev, mode=xmode) if world > 1 and xmode != "nccl" else None
+    in_flight = []
 
-    def step(P_in, A_in):
+    def step(P_in, A_in, overlap=False):
         if world == 1:
             return similarity.soft_wpmi(P_in, A_in, top_k=TOP_K, device=dev)
-        return mdist.soft_wpmi_sharded(P_in, A_in, shard_sizes, top_k=TOP_K, device=dev, backend=backend)
+        h = mdist.soft_wpmi_sharded(P_in, A_in, shard_sizes, top_k=TOP_K, device=dev, backend=backend,
+                                    exchange=exchange, wait=not (overlap and exchange is not None))
+        if overlap and exchange is not None:
+            drain()
+            in_flight.append(h)
+        return h
+
+    def drain():
+        while in_flight:
+            in_flight.pop().wait()
 
     def barrier():
         if world > 1:
@@ -215,7 +235,8 @@ def run_ours(args):
         return float(t.item())
 
     for _ in range(max(args.warmup, 3)):
-        out = step(P, A)
+        out = step(P, A, overlap=True)
+    drain()
     barrier()
 
     # ---- device-resident timing: K steps between two events ----------------------------------
@@ -229,7 +250,8 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        out = step(P, A)
+        out = step(P, A, overlap=True)
+    drain()
     e1.record()
     barrier()
     launches = _lib.launch_count() - n0

@@ -95,6 +95,19 @@ int mcd_pmi_finalize_f32(const float *L, int64_t ldl, int64_t K, int64_t C,
                          float lam, float *prob_d_out /* [C] scratch+result */,
                          float *out, int64_t ldo, mcd_stream_t stream);
 
+/* ---- K3b fused with the all-gather of the scores (neuron-sharded multi-GPU call):
+ *      same arithmetic as mcd_pmi_finalize_f32 on this rank's contiguous [K, C] log-sums, but the
+ *      finalized slice is stored into rows [row_offset, row_offset + K) of EVERY destination
+ *      matrix dest_bases[0..n_dest) (contiguous [K_total, C] fp32, 16-byte aligned slices; peer
+ *      GPUs' memory mapped into this process plus the rank's own copy).  dest_bases is a HOST
+ *      array of device pointers.  The caller orders the exchange (a barrier across the ranks
+ *      before and after, on the same stream). */
+#define MCD_MAX_PEERS 16
+int mcd_pmi_finalize_bcast_f32(const float *L, int64_t K, int64_t C, const float *partials_all,
+                               int64_t n_blocks_total, int64_t K_total, float lam,
+                               float *prob_d_out, float *const *dest_bases, int n_dest,
+                               int64_t row_offset, mcd_stream_t stream);
+
 /* ---- K4: spatial pooling of a hooked NCHW activation   replaces utils.py:38 / :47 -------
  *      x [B,C,H,W] contiguous, dtype f32/f16/bf16; out [B,C] same dtype (fp32 accumulation).
  *      workspace: mcd_pool_nchw_workspace_bytes (partials for planes split across CTAs). */

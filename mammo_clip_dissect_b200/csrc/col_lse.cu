@@ -95,6 +95,44 @@ pmi_finalize_kernel(const float *__restrict__ L, int64_t ldl, int64_t K, int C, 
     for (int64_t j = blockIdx.y; j < K; j += gridDim.y) out[j * ldo + c] = __fsub_rn(L[j * ldl + c], shift);
 }
 
+// K3b fused with the score all-gather: the finalized slice is stored straight into the [K_total, C] score matrix
+// of every GPU of the node (peer memory over NVLink / NVSwitch; the rank's own copy is one of the destinations).
+// The slice is treated as a flat array so that every warp store is one aligned 512-byte run per destination, whatever
+// C is; the concept index of a thread advances by a constant modulo C (no division in the loop).
+constexpr int kMaxPeers = MCD_MAX_PEERS;
+struct PeerDests {
+    float *ptr[kMaxPeers];      // already offset to the first row of this rank's slice
+};
+
+__global__ void __launch_bounds__(256)
+pmi_finalize_bcast_kernel(const float *__restrict__ L, int64_t total, int C, const float *__restrict__ prob_d, float lam,
+                          PeerDests dst, int n_dst) {
+    const int64_t nvec = total / 4;
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    int c = static_cast<int>((4 * e) % C);
+    const int step_c = static_cast<int>((4 * stride) % C);
+    for (; e < nvec; e += stride) {
+        float4 v = __ldg(reinterpret_cast<const float4 *>(L) + e);
+        int c1 = c + 1 == C ? 0 : c + 1;
+        int c2 = c1 + 1 == C ? 0 : c1 + 1;
+        int c3 = c2 + 1 == C ? 0 : c2 + 1;
+        v.x = __fsub_rn(v.x, __fmul_rn(lam, __ldg(prob_d + c)));
+        v.y = __fsub_rn(v.y, __fmul_rn(lam, __ldg(prob_d + c1)));
+        v.z = __fsub_rn(v.z, __fmul_rn(lam, __ldg(prob_d + c2)));
+        v.w = __fsub_rn(v.w, __fmul_rn(lam, __ldg(prob_d + c3)));
+        for (int p = 0; p < n_dst; ++p) reinterpret_cast<float4 *>(dst.ptr[p])[e] = v;
+        c += step_c;
+        if (c >= C) c -= C;
+    }
+    // the last total % 4 elements
+    if (blockIdx.x == 0 && threadIdx.x < total - nvec * 4) {
+        const int64_t i = nvec * 4 + threadIdx.x;
+        const float v = __fsub_rn(L[i], __fmul_rn(lam, prob_d[i % C]));
+        for (int p = 0; p < n_dst; ++p) dst.ptr[p][i] = v;
+    }
+}
+
 }  // namespace mcd
 
 extern "C" int mcd_col_lse_partials_f32(const float *L, int64_t ldl, int64_t K, int64_t C, float *partials,
@@ -126,5 +164,36 @@ extern "C" int mcd_pmi_finalize_f32(const float *L, int64_t ldl, int64_t K, int6
     if (rows < 1) rows = 1;
     dim3 grid(static_cast<unsigned>(ceil_div<int64_t>(C, 256)), static_cast<unsigned>(rows));
     pmi_finalize_kernel<<<grid, 256, 0, st>>>(L, ldl, K, int(C), prob_d_out, lam, out, ldo);
+    return check_launch();
+}
+
+extern "C" int mcd_pmi_finalize_bcast_f32(const float *L, int64_t K, int64_t C, const float *partials_all,
+                                          int64_t n_blocks_total, int64_t K_total, float lam, float *prob_d_out,
+                                          float *const *dest_bases, int n_dest, int64_t row_offset,
+                                          mcd_stream_t stream) {
+    using namespace mcd;
+    if (!L || !partials_all || !prob_d_out || !dest_bases || K < 1 || C < 1 || n_blocks_total < 1 || K_total < 1 ||
+        C > (1 << 24) || n_dest < 1 || row_offset < 0 || row_offset + K > K_total)
+        return MCD_ERR_INVALID_ARGUMENT;
+    if (n_dest > kMaxPeers) return MCD_ERR_UNSUPPORTED;
+    PeerDests dst;
+    for (int p = 0; p < kMaxPeers; ++p) dst.ptr[p] = nullptr;
+    for (int p = 0; p < n_dest; ++p) {
+        if (!dest_bases[p]) return MCD_ERR_INVALID_ARGUMENT;
+        dst.ptr[p] = dest_bases[p] + row_offset * C;
+        if (reinterpret_cast<uintptr_t>(dst.ptr[p]) % 16 != 0) return MCD_ERR_UNSUPPORTED;   // 16-byte stores
+    }
+    if (reinterpret_cast<uintptr_t>(L) % 16 != 0) return MCD_ERR_UNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    lse_combine_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(C, 32)), 256, 0, st>>>(
+        partials_all, n_blocks_total, int(C), log(double(K_total)), prob_d_out);
+    int rc = check_launch();
+    if (rc != MCD_OK) return rc;
+    const int64_t total = K * C;
+    int64_t blocks = ceil_div<int64_t>(total / 4 + 1, 256);
+    const int64_t cap = int64_t(num_sms()) * 8;
+    if (blocks > cap) blocks = cap;
+    pmi_finalize_bcast_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(L, total, int(C), prob_d_out, lam, dst,
+                                                                             n_dest);
     return check_launch();
 }

@@ -37,12 +37,11 @@ namespace mcd {
 
 constexpr int kUnitCols = 32;                        // columns per scan warp (= per CTA)
 constexpr int kTileRows = 32;                        // rows per TMA tile
-constexpr int kSubRows = 16;                         // rows per scan step (4 quarter-warps x 4 rows)
 constexpr int kScanThreads = 32;
-constexpr int kQuads = 4;                            // quarter-warps: quarter q takes rows q, q+4, q+8, q+12 of a step
-constexpr int kListCap = 8;                          // pending slots per (quarter, column) list
+constexpr int kQuads = 4;                            // quarter-warps: quarter q takes rows q, q+4, ..., q+28 of a tile
+constexpr int kListCap = 12;                         // pending slots per (quarter, column) list
 constexpr int kPendCap = kQuads * kListCap;          // pending slots per column
-constexpr int kRowsPerQuad = kSubRows / kQuads;      // a step adds at most this many entries to a list
+constexpr int kRowsPerQuad = kTileRows / kQuads;     // a tile adds at most this many entries to a list
 constexpr int kMaxStages = 8;
 constexpr int kMaxGroups = 8;                        // kept set: at most 8 groups (their minima live in registers)
 enum FeedMode { kFeedElements = 0, kFeedTensorTile = 2 };
@@ -80,7 +79,7 @@ struct ScanSmem {
     float tau[kUnitCols];
     int pcnt[kQuads][kUnitCols];
     uint32_t gmh[kMaxGroups][kUnitCols], gml[kMaxGroups][kUnitCols];   // per group: its minimum entry (key, ~row)
-    int gms[kMaxGroups][kUnitCols];                                     // ... and the slot holding it
+    uint8_t gms[kMaxGroups][kUnitCols];                                 // ... and the slot holding it
     uint64_t full[kMaxStages];
 };
 __host__ __device__ inline size_t scan_smem_bytes(int nstage) {
@@ -104,7 +103,7 @@ template <int GROUP>
 struct Kept {
     uint32_t *hi, *lo;          // this lane's column: element [slot] is hi[slot * 32]
     uint32_t *gmh, *gml;        // shared memory: group g's minimum is gmh[g * 32], gml[g * 32], slot gms[g * 32]
-    int *gms;
+    uint8_t *gms;
     uint32_t root_hi, root_lo;  // current overall minimum (the column's k-th best so far)
     int rg, rs;                 // its group and slot within the group
     float floor_tau;            // threshold while the set still has empty slots (NaN = admit everything)
@@ -165,7 +164,7 @@ struct Kept {
         }
         gmh[rg * kUnitCols] = mh;
         gml[rg * kUnitCols] = ml;
-        gms[rg * kUnitCols] = ms;
+        gms[rg * kUnitCols] = static_cast<uint8_t>(ms);
         // overall minimum over the group minima (the changed group's values are taken from registers)
         uint32_t bh = 0xFFFFFFFFu, bl = 0xFFFFFFFFu;
         int bg = 0;
@@ -298,22 +297,21 @@ topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
     s.tau[lane] = lane < ncols ? kept.floor_tau : INFINITY;                  // columns past K never pass
     __syncwarp();
 
-    // A lane reads 4 adjacent columns of one row with one LDS.128; quarter-warp q takes rows q, q+4, q+8, q+12
-    // of a 16-row step.  Elements that beat their column's threshold are appended, without atomics or divergent
+    // A lane reads 4 adjacent columns of one row with one LDS.128; quarter-warp q takes rows q, q+4, ..., q+28
+    // of a tile.  Elements that beat their column's threshold are appended, without atomics or divergent
     // branches, to the pending list PRIVATE to (quarter q, column): one predicated store + add each.
     const int q = lane >> 3;
     const int colq = (lane & 7) * 4;                 // first of this lane's 4 columns
     float4 tau4 = *reinterpret_cast<const float4 *>(&s.tau[colq]);
     const uint32_t list_first = smem_u32(&s.pend[q * kListCap][colq]);
-    const uint32_t list_limit = list_first + (kListCap - kRowsPerQuad) * kSlotBytes;   // beyond: a step may overflow
+    const uint32_t list_limit = list_first + (kListCap - kRowsPerQuad) * kSlotBytes;   // beyond: a tile may overflow
     uint32_t p0 = list_first, p1 = list_first + 8, p2 = list_first + 16, p3 = list_first + 24;
     const uint32_t lane_off = uint32_t(q * kUnitCols + colq) * 4u;   // this lane's first element inside a tile
 
     int stage = 0, use = 0;
-    uint32_t row_step = static_cast<uint32_t>(row0) + q;       // row index of this lane's first row in the next step
-    static_assert(kTileRows == 2 * kSubRows, "a tile is scanned as two 16-row steps");
+    uint32_t row_tile = static_cast<uint32_t>(row0) + q;       // row index of this lane's first row in the next tile
 #pragma unroll 1
-    for (int t = 0; t < ntiles; ++t) {
+    for (int t = 0; t < ntiles; ++t, row_tile += kTileRows) {
         const uint32_t tile_addr = ring_addr + stage * kTileBytes;
         if (feed == kFeedTensorTile) {
             mbar_wait(&s.full[stage], use & 1);
@@ -325,25 +323,10 @@ topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
             __syncwarp();
         }
         const bool full_tile = (t + 1) * kTileRows <= nrows;
-        const int rows_left_tile = nrows - t * kTileRows - q;      // > r  <=>  this lane's row r of the tile exists
-        float4 va[kRowsPerQuad], vb[kRowsPerQuad];                 // rows of the first / second 16-row step
-        if (full_tile) {
+        const int rows_left = nrows - t * kTileRows - q;           // > r  <=>  this lane's row r of the tile exists
+        float4 v[kRowsPerQuad];                                    // this lane's 8 rows x 4 columns of the tile
 #pragma unroll
-            for (int i = 0; i < kRowsPerQuad; ++i) {
-                va[i] = lds_v4(tile_addr + lane_off + uint32_t(kQuads * i) * (kUnitCols * 4));
-                vb[i] = lds_v4(tile_addr + lane_off + uint32_t(kSubRows + kQuads * i) * (kUnitCols * 4));
-            }
-        } else {
-            // last, partial tile: rows past the end read as -inf (and are masked by `valid` below, because
-            // -inf still passes an unfilled NaN threshold)
-#pragma unroll
-            for (int i = 0; i < kRowsPerQuad; ++i) {
-                va[i] = vb[i] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-                if (kQuads * i < rows_left_tile) va[i] = lds_v4(tile_addr + lane_off + uint32_t(kQuads * i) * (kUnitCols * 4));
-                if (kSubRows + kQuads * i < rows_left_tile)
-                    vb[i] = lds_v4(tile_addr + lane_off + uint32_t(kSubRows + kQuads * i) * (kUnitCols * 4));
-            }
-        }
+        for (int i = 0; i < kRowsPerQuad; ++i) v[i] = lds_v4(tile_addr + lane_off + uint32_t(kQuads * i) * (kUnitCols * 4));
         __syncwarp();                                    // every lane has the tile's rows in registers
         if (feed == kFeedTensorTile && lane == 0 && t + nstage < ntiles) {
             fence_proxy_async();                         // generic-proxy reads before the async-proxy refill
@@ -354,42 +337,27 @@ topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
             stage = 0;
             ++use;
         }
-        // the two 16-row steps of the tile share one copy of the append / fold code (unrolling them measured slower)
-#pragma unroll 1
-        for (int half = 0; half < 2; ++half, row_step += kSubRows) {
-            float4 v[kRowsPerQuad];
+        // ~0.35 of the 128 elements of a row group pass on average: one vote per row group, and (warp-uniformly)
+        // nothing else for the groups nobody appends from.  Rows past the end of the last, partial tile (stale ring
+        // contents) are masked inside the branch only.
 #pragma unroll
-            for (int i = 0; i < kRowsPerQuad; ++i) {
-                v[i].x = half ? vb[i].x : va[i].x;
-                v[i].y = half ? vb[i].y : va[i].y;
-                v[i].z = half ? vb[i].z : va[i].z;
-                v[i].w = half ? vb[i].w : va[i].w;
-            }
-            bool any = false;
-#pragma unroll
-            for (int i = 0; i < kRowsPerQuad; ++i)
-                any |= !(v[i].x <= tau4.x) | !(v[i].y <= tau4.y) | !(v[i].z <= tau4.z) | !(v[i].w <= tau4.w);
-            if (__any_sync(0xffffffffu, any)) {
-                const int rows_left = rows_left_tile - half * kSubRows;
-                // ~1.4 of the 512 elements pass on average: skip (warp-uniformly) the rows nobody appends from
-#pragma unroll
-                for (int i = 0; i < kRowsPerQuad; ++i) {
-                    const bool valid = full_tile || (kQuads * i < rows_left);
-                    const bool px = valid && !(v[i].x <= tau4.x), py = valid && !(v[i].y <= tau4.y);
-                    const bool pz = valid && !(v[i].z <= tau4.z), pw = valid && !(v[i].w <= tau4.w);
-                    if (__any_sync(0xffffffffu, px | py | pz | pw)) {
-                        const uint32_t row = row_step + uint32_t(kQuads * i);
-                        if (px) { sts_v2(p0, __float_as_uint(v[i].x), row); p0 += kSlotBytes; }
-                        if (py) { sts_v2(p1, __float_as_uint(v[i].y), row); p1 += kSlotBytes; }
-                        if (pz) { sts_v2(p2, __float_as_uint(v[i].z), row); p2 += kSlotBytes; }
-                        if (pw) { sts_v2(p3, __float_as_uint(v[i].w), row); p3 += kSlotBytes; }
-                    }
+        for (int i = 0; i < kRowsPerQuad; ++i) {
+            bool px = !(v[i].x <= tau4.x), py = !(v[i].y <= tau4.y), pz = !(v[i].z <= tau4.z), pw = !(v[i].w <= tau4.w);
+            if (__any_sync(0xffffffffu, px | py | pz | pw)) {
+                if (!full_tile) {
+                    const bool valid = kQuads * i < rows_left;
+                    px &= valid; py &= valid; pz &= valid; pw &= valid;
                 }
-                const bool want = (p0 > list_limit) | (p1 > list_limit + 8) | (p2 > list_limit + 16) | (p3 > list_limit + 24);
-                if (__any_sync(0xffffffffu, want))
-                    publish_and_fold<GROUP>(s, kept, lane, q, colq, list_first, p0, p1, p2, p3, tau4);
+                const uint32_t row = row_tile + uint32_t(kQuads * i);
+                if (px) { sts_v2(p0, __float_as_uint(v[i].x), row); p0 += kSlotBytes; }
+                if (py) { sts_v2(p1, __float_as_uint(v[i].y), row); p1 += kSlotBytes; }
+                if (pz) { sts_v2(p2, __float_as_uint(v[i].z), row); p2 += kSlotBytes; }
+                if (pw) { sts_v2(p3, __float_as_uint(v[i].w), row); p3 += kSlotBytes; }
             }
         }
+        const bool want = (p0 > list_limit) | (p1 > list_limit + 8) | (p2 > list_limit + 16) | (p3 > list_limit + 24);
+        if (__any_sync(0xffffffffu, want))
+            publish_and_fold<GROUP>(s, kept, lane, q, colq, list_first, p0, p1, p2, p3, tau4);
     }
     publish_and_fold<GROUP>(s, kept, lane, q, colq, list_first, p0, p1, p2, p3, tau4);
     if (tau_out != nullptr && lane < ncols) tau_out[c0 + lane] = key_to_threshold(kept.root_hi);   // NaN if not full

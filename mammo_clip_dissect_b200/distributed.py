@@ -11,7 +11,14 @@ coupling is log p(d)[c] = logsumexp_j L[j,c] - log K over ALL neurons of the cal
   rather than receiving a 305 MB broadcast),
   exchange 1: all_gather of the per-256-neuron-block (max, sum-exp) partials  [nb_g, 2, C]   (tiny)
   local     : combine ALL partials in global block order (fp64)  -> bit-identical for any G
-  exchange 2: all_gather of the [K_g, C] score shards into the full [K, C] matrix (optional)
+  exchange 2: all_gather of the [K_g, C] score shards into the full [K, C] matrix (optional).  Three ways:
+              * NCCL all_gather (default; a fresh tensor per call);
+              * PeerScoreExchange(mode="fused"): K3b's finalize kernel stores its slice straight into every GPU's
+                [K, C] buffer through peer-mapped (symmetric) memory -- one kernel, no separate collective;
+              * PeerScoreExchange(mode="copy"): the slice is pushed to the peers by the copy engines on side
+                streams, so the exchange of one call can overlap the column scan of the next call (the scan is a
+                single wave of persistent warps that fills every SM: any SM-based collective running beside it
+                would delay it by its own duration; DMA pushes do not).
 
 Compute is injected through a small backend object so that the exchange logic can be tested on
 CPU with gloo (tests/test_dist_gloo.py drives it with the oracle); the product backend below
@@ -68,6 +75,92 @@ class CudaBackend:
             return self.sim.pmi_finalize(L, partials_all, K_total, lam)[0]
 
 
+class GatheredScores:
+    """Result of an asynchronous score exchange: `.wait()` makes the current stream wait for the exchange and
+    returns the [K_total, C] matrix (a view of a double-buffered symmetric buffer: it is overwritten by the
+    exchange `depth` calls later)."""
+
+    def __init__(self, tensor, event, keep=None):
+        self.tensor, self.event, self._keep = tensor, event, keep
+
+    def wait(self):
+        if self.event is not None:
+            torch.cuda.current_stream(self.tensor.device).wait_event(self.event)
+            self.event = None
+            self._keep = None
+        return self.tensor
+
+
+class PeerScoreExchange:
+    """[K_total, C] score buffers in symmetric memory (torch.distributed._symmetric_memory: every rank's buffer is
+    mapped into every process of the node), `depth` of them used round-robin.
+
+    mode "fused": mcd_pmi_finalize_bcast_f32 writes the finalized slice into all ranks' buffers (NVLink stores);
+    mode "copy" : mcd_pmi_finalize_f32 in place, then one DMA push per peer on side streams.
+    Both are ordered by the symmetric-memory barrier (signal pads, a few microseconds): one before the first remote
+    write (every rank has finished the calls that could still be reading this buffer) and one after the last."""
+
+    def __init__(self, shard_sizes: Sequence[int], C: int, device, group=None, mode: str = "copy", depth: int = 2):
+        import torch.distributed._symmetric_memory as symm_mem
+        if mode not in ("copy", "fused"):
+            raise ValueError("mode must be 'copy' or 'fused'")
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.mode, self.depth, self.C = mode, int(depth), int(C)
+        self.sizes = [int(x) for x in shard_sizes]
+        self.K_total = sum(self.sizes)
+        self.row0 = sum(self.sizes[: self.rank])
+        self.device = torch.device(device)
+        self.bufs, self.hdls, self.views = [], [], []
+        for _ in range(self.depth):
+            t = symm_mem.empty((self.K_total, self.C), dtype=torch.float32, device=self.device)
+            h = symm_mem.rendezvous(t, self.group)
+            self.bufs.append(t)
+            self.hdls.append(h)
+            self.views.append([h.get_buffer(p, (self.K_total, self.C), torch.float32) for p in range(self.world)])
+        self.comm = torch.cuda.Stream(device=self.device)
+        self.push_streams = [torch.cuda.Stream(device=self.device) for _ in range(self.world)]
+        self.turn = 0
+
+    def exchange(self, L, partials_all, lam, sim, wait: bool = True):
+        """L: this rank's [K_g, C] log-sums (finalized in place in mode "copy").  Returns the gathered matrix
+        (wait=True) or a GatheredScores handle (wait=False; only mode "copy" really runs behind the caller)."""
+        b = self.turn
+        self.turn = (self.turn + 1) % self.depth
+        hdl, buf, views = self.hdls[b], self.bufs[b], self.views[b]
+        main = torch.cuda.current_stream(self.device)
+        rows = slice(self.row0, self.row0 + self.sizes[self.rank])
+        if self.mode == "fused":
+            hdl.barrier(channel=0)
+            with sim._Stage("finalize_bcast"):
+                sim.pmi_finalize_bcast(L, partials_all, self.K_total, lam, list(hdl.buffer_ptrs), self.row0)
+            hdl.barrier(channel=1)
+            return buf if wait else GatheredScores(buf, None)
+        with sim._Stage("lse_finalize"):
+            local = sim.pmi_finalize(L, partials_all, self.K_total, lam)[0]
+        ready = torch.cuda.Event()
+        ready.record(main)
+        self.comm.wait_event(ready)
+        with torch.cuda.stream(self.comm):
+            hdl.barrier(channel=0)
+            start = torch.cuda.Event()
+            start.record(self.comm)
+            for i in range(self.world):
+                p = (self.rank + i) % self.world            # own copy first, then the peers in ring order
+                st = self.push_streams[i]
+                st.wait_event(start)
+                with torch.cuda.stream(st):
+                    views[p][rows].copy_(local, non_blocking=True)
+                self.comm.wait_stream(st)
+            hdl.barrier(channel=1)
+            done = torch.cuda.Event()
+            done.record(self.comm)
+        for st in self.push_streams + [self.comm]:
+            local.record_stream(st)
+        out = GatheredScores(buf, done, keep=local)
+        return out.wait() if wait else out
+
+
 def _all_gather_var(t: torch.Tensor, sizes: Sequence[int], group) -> torch.Tensor:
     """all_gather of tensors whose leading dimension differs per rank (sizes known to all ranks)."""
     world = dist.get_world_size(group)
@@ -84,11 +177,13 @@ def _all_gather_var(t: torch.Tensor, sizes: Sequence[int], group) -> torch.Tenso
 
 
 def pmi_scores_sharded(clip_feats, target_shard, shard_sizes: Sequence[int], top_k, a, lam, min_prob, ramp,
-                       backend, group=None, gather_scores: bool = True):
+                       backend, group=None, gather_scores: bool = True, exchange=None, wait: bool = True):
     """Scores for this rank's neurons (and, with gather_scores, for all neurons [K, C]).
 
     target_shard : [N, K_g] activations of this rank's neurons
     shard_sizes  : K_g of every rank, in rank order (interior boundaries multiples of 256)
+    exchange     : a PeerScoreExchange for the score all-gather (default: NCCL all_gather); with wait=False the
+                   result is a GatheredScores handle
     """
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
@@ -101,6 +196,10 @@ def pmi_scores_sharded(clip_feats, target_shard, shard_sizes: Sequence[int], top
     part = backend.lse_partials(L)
     nblocks = [(s + LSE_BLOCK - 1) // LSE_BLOCK for s in shard_sizes]
     part_all = _all_gather_var(part, nblocks, group) if world > 1 else part
+    if exchange is not None and gather_scores and world > 1:
+        if list(exchange.sizes) != [int(x) for x in shard_sizes] or exchange.C != L.shape[1]:
+            raise RuntimeError("PeerScoreExchange was built for other shard sizes")
+        return exchange.exchange(L, part_all, lam, backend.sim, wait=wait)
     local = backend.finalize(L, part_all, K_total, lam)
     if not gather_scores or world == 1:
         return local
@@ -112,16 +211,18 @@ def pmi_scores_sharded(clip_feats, target_shard, shard_sizes: Sequence[int], top
 
 
 def soft_wpmi_sharded(clip_feats, target_shard, shard_sizes, top_k=100, a=10, lam=1, device='cuda',
-                      min_prob=1e-7, p_start=0.998, p_end=0.97, group=None, gather_scores=True, backend=None):
+                      min_prob=1e-7, p_start=0.998, p_end=0.97, group=None, gather_scores=True, backend=None,
+                      exchange=None, wait=True):
     """Neuron-sharded soft_wpmi (reference similarity.py:49-73 semantics over the union of shards)."""
     from .similarity import _reference_ramp
     backend = backend or CudaBackend(device)
     return pmi_scores_sharded(clip_feats, target_shard, shard_sizes, top_k, a, lam, min_prob,
-                              _reference_ramp(int(top_k), p_start, p_end), backend, group, gather_scores)
+                              _reference_ramp(int(top_k), p_start, p_end), backend, group, gather_scores,
+                              exchange, wait)
 
 
 def wpmi_sharded(clip_feats, target_shard, shard_sizes, top_k=28, a=2, lam=0.6, device='cuda', min_prob=1e-7,
-                 group=None, gather_scores=True, backend=None):
+                 group=None, gather_scores=True, backend=None, exchange=None, wait=True):
     backend = backend or CudaBackend(device)
     return pmi_scores_sharded(clip_feats, target_shard, shard_sizes, top_k, a, lam, min_prob, None, backend, group,
-                              gather_scores)
+                              gather_scores, exchange, wait)

@@ -206,6 +206,22 @@ def pmi_finalize(L, partials_all, K_total, lam, out=None):
     return out, prob_d
 
 
+def pmi_finalize_bcast(L, partials_all, K_total, lam, dest_ptrs, row_offset):
+    """K3b fused with the score all-gather: finalize this rank's contiguous [K, C] log-sums and store the slice into
+    rows [row_offset, row_offset + K) of every [K_total, C] matrix in dest_ptrs (device pointers: the peers' symmetric
+    buffers and this rank's own).  Returns log p(d) [C]."""
+    import ctypes
+    K, C = L.shape
+    if not L.is_contiguous():
+        raise RuntimeError("pmi_finalize_bcast needs contiguous log-sums")
+    prob_d = torch.empty((C,), dtype=torch.float32, device=L.device)
+    arr = (ctypes.c_void_p * len(dest_ptrs))(*[int(p) for p in dest_ptrs])
+    _lib.check(_lib.lib().mcd_pmi_finalize_bcast_f32(_ptr(L), K, C, _ptr(partials_all), partials_all.shape[0],
+                                                     int(K_total), float(lam), _ptr(prob_d), arr, len(dest_ptrs),
+                                                     int(row_offset), _stream(L.device)), "mcd_pmi_finalize_bcast_f32")
+    return prob_d
+
+
 def pmi_scores(clip_feats, target_feats, top_k, a, lam, device, min_prob, ramp, return_parts=False):
     """Shared body of soft_wpmi / wpmi on one device."""
     dev = _cuda_device(device)

@@ -21,7 +21,17 @@ single = similarity.soft_wpmi(P, A, device=dev)
 same = torch.equal(full, single)
 w = mdist.wpmi_sharded(P, A[:, b[rank]:b[rank + 1]].contiguous(), sizes, device=dev)
 same_w = torch.equal(w, similarity.wpmi(P, A, device=dev))
-flag = torch.tensor([int(same and same_w)], device=dev)
+same_x = True
+for mode in ("copy", "fused"):
+    ex = mdist.PeerScoreExchange(sizes, C, dev, mode=mode)
+    for it in range(3):                      # more calls than buffers: the round-robin reuse is exercised
+        got = mdist.soft_wpmi_sharded(P, A[:, b[rank]:b[rank + 1]].contiguous(), sizes, device=dev, exchange=ex)
+        same_x = same_x and torch.equal(got, single)
+    h = mdist.soft_wpmi_sharded(P, A[:, b[rank]:b[rank + 1]].contiguous(), sizes, device=dev, exchange=ex, wait=False)
+    same_x = same_x and torch.equal(h.wait(), single)
+    if rank == 0:
+        print("exchange mode %s: %s" % (mode, "bit-identical" if same_x else "MISMATCH"), flush=True)
+flag = torch.tensor([int(same and same_w and same_x)], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
     print("multi-gpu parity (world=%d): %s" % (world, "bit-identical" if flag.item() else "MISMATCH"), flush=True)
