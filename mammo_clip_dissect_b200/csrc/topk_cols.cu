@@ -71,7 +71,7 @@ __device__ __forceinline__ void sts_v2(uint32_t addr, uint32_t a, uint32_t b) {
 //   tau    current threshold per column;  pcnt  entries per (quarter, column) list, published before a fold
 // Global memory (workspace, one region per warp; touched only by the folds, it stays in L2 because A is
 // streamed with evict-first):
-//   kept   per column the kept set as two [slot][32] u32 arrays (ordered key, ~row): G = ceil(k/GROUP) groups
+//   kept   per column the kept set as a [slot][32] array of (ordered key, ~row) u32 pairs: G = ceil(k/GROUP) groups
 //          of GROUP entries, UNSORTED; slots >= k of the last group hold all-ones and are never the minimum
 struct ScanSmem {
     float ring[kMaxStages][kTileRows][kUnitCols];
@@ -96,21 +96,25 @@ __device__ __forceinline__ bool key_gt(uint32_t ah, uint32_t al, uint32_t bh, ui
 }
 
 // The kept set of one column (owned by one lane) is a two-level min structure instead of a heap: G groups of
-// GROUP unsorted entries in global memory, and per group the minimum entry (key, ~row, slot) in registers.
-// Replacing the overall minimum costs one pass over one group (GROUP independent 4-byte loads, one L2 round
-// trip) plus a register-only pass over the <= 8 group minima.
+// GROUP unsorted (key, ~row) entries in global memory (L2-resident), per group its minimum entry in shared memory,
+// and a REGISTER copy of the group that holds the overall minimum (the column's k-th best so far).  Replacing the
+// minimum then needs no load at all: the entry is overwritten in the register copy (and stored to global, fire and
+// forget), the group's new minimum comes from registers, the new overall minimum from the <= 8 group minima; only
+// if it lies in another group are that group's GROUP entries loaded (independent 8-byte loads, one L2 round trip,
+// first needed at the next replacement).
 template <int GROUP>
 struct Kept {
-    uint32_t *hi, *lo;          // this lane's column: element [slot] is hi[slot * 32]
+    uint2 *ent;                 // this lane's column: entry [slot] is ent[slot * 32]  (x = ordered key, y = ~row)
     uint32_t *gmh, *gml;        // shared memory: group g's minimum is gmh[g * 32], gml[g * 32], slot gms[g * 32]
     uint8_t *gms;
     uint32_t root_hi, root_lo;  // current overall minimum (the column's k-th best so far)
     int rg, rs;                 // its group and slot within the group
     float floor_tau;            // threshold while the set still has empty slots (NaN = admit everything)
+    uint32_t ch[GROUP], cl[GROUP];   // register copy of group rg (statically indexed only)
 
-    __device__ __forceinline__ void init(uint32_t *hi_, uint32_t *lo_, ScanSmem &s, int lane, int G) {
-        hi = hi_;
-        lo = lo_;
+    // the caller has filled ent[] with k empty-slot sentinels (0, 0) followed by all-ones padding
+    __device__ __forceinline__ void init(uint2 *ent_, ScanSmem &s, int lane, int G, int k) {
+        ent = ent_;
         gmh = &s.gmh[0][lane];
         gml = &s.gml[0][lane];
         gms = &s.gms[0][lane];
@@ -120,47 +124,29 @@ struct Kept {
             gmh[g * kUnitCols] = gml[g * kUnitCols] = g < G ? 0u : 0xFFFFFFFFu;
             gms[g * kUnitCols] = 0;
         }
+#pragma unroll
+        for (int i = 0; i < GROUP; ++i) ch[i] = cl[i] = i < k ? 0u : 0xFFFFFFFFu;
     }
 
     // precondition: (eh, el) > root.  Overwrites the root entry with (eh, el) and re-establishes the minima.
     __device__ __forceinline__ void replace_min(uint32_t eh, uint32_t el) {
-        uint32_t *gh = hi + rg * (GROUP * kUnitCols);
-        uint32_t *gl = lo + rg * (GROUP * kUnitCols);
-        gh[rs * kUnitCols] = eh;
-        gl[rs * kUnitCols] = el;
-        uint32_t h[GROUP];
+        uint2 *g = ent + rg * (GROUP * kUnitCols);
+        g[rs * kUnitCols] = make_uint2(eh, el);
 #pragma unroll
-        for (int i = 0; i < GROUP; ++i) h[i] = gh[i * kUnitCols];
+        for (int i = 0; i < GROUP; ++i) {
+            ch[i] = (i == rs) ? eh : ch[i];
+            cl[i] = (i == rs) ? el : cl[i];
+        }
+        // minimum (key, ~row) of the group; a strictly smaller entry replaces, so among equal entries (the (0, 0)
+        // empty-slot sentinels) the first slot wins
+        uint32_t mh = ch[0], ml = cl[0];
+        int ms = 0;
 #pragma unroll
-        for (int i = 0; i < GROUP; ++i) h[i] = (i == rs) ? eh : h[i];       // do not depend on the store above
-        uint32_t mh = h[0];
-#pragma unroll
-        for (int i = 1; i < GROUP; ++i) mh = min(mh, h[i]);
-        int ms = -1, nmatch = 0;
-#pragma unroll
-        for (int i = GROUP - 1; i >= 0; --i)
-            if (h[i] == mh) {
-                ms = i;
-                ++nmatch;
-            }
-        uint32_t ml;
-        if (nmatch == 1 || mh == 0u) {
-            ml = (ms == rs) ? el : gl[ms * kUnitCols];     // empty-slot sentinels are all (0, 0): take the first
-        } else {
-            // equal keys inside the group (tied activation values): the minimum has the smallest ~row.
-            // Rare path: re-read the keys from memory (indexing h[] dynamically would put it on the stack).
-            ml = 0xFFFFFFFFu;
-            ms = -1;
-            for (int i = 0; i < GROUP; ++i) {
-                const uint32_t hv = (i == rs) ? eh : gh[i * kUnitCols];
-                if (hv == mh) {
-                    const uint32_t l = (i == rs) ? el : gl[i * kUnitCols];
-                    if (ms < 0 || l < ml) {
-                        ml = l;
-                        ms = i;
-                    }
-                }
-            }
+        for (int i = 1; i < GROUP; ++i) {
+            const bool less = key_gt(mh, ml, ch[i], cl[i]);
+            mh = less ? ch[i] : mh;
+            ml = less ? cl[i] : ml;
+            ms = less ? i : ms;
         }
         gmh[rg * kUnitCols] = mh;
         gml[rg * kUnitCols] = ml;
@@ -170,20 +156,29 @@ struct Kept {
         int bg = 0;
         uint32_t xh[kMaxGroups], xl[kMaxGroups];
 #pragma unroll
-        for (int g = 0; g < kMaxGroups; ++g) {
-            xh[g] = gmh[g * kUnitCols];
-            xl[g] = gml[g * kUnitCols];
+        for (int gg = 0; gg < kMaxGroups; ++gg) {
+            xh[gg] = gmh[gg * kUnitCols];
+            xl[gg] = gml[gg * kUnitCols];
         }
 #pragma unroll
-        for (int g = kMaxGroups - 1; g >= 0; --g) {
-            const uint32_t ah = (g == rg) ? mh : xh[g], al = (g == rg) ? ml : xl[g];
+        for (int gg = kMaxGroups - 1; gg >= 0; --gg) {
+            const uint32_t ah = (gg == rg) ? mh : xh[gg], al = (gg == rg) ? ml : xl[gg];
             if (!key_gt(ah, al, bh, bl)) {       // <= : on equal (sentinel) minima the lowest group wins
                 bh = ah;
                 bl = al;
-                bg = g;
+                bg = gg;
             }
         }
         const int bs = (bg == rg) ? ms : gms[bg * kUnitCols];
+        if (bg != rg) {
+            const uint2 *ng = ent + bg * (GROUP * kUnitCols);
+#pragma unroll
+            for (int i = 0; i < GROUP; ++i) {
+                const uint2 t = ng[i * kUnitCols];
+                ch[i] = t.x;
+                cl[i] = t.y;
+            }
+        }
         root_hi = bh;
         root_lo = bl;
         rg = bg;
@@ -281,15 +276,14 @@ topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
     // kept sets start as k empty-slot sentinels (0, 0) that sort below every real entry; the NaN threshold
     // admits everything until a column has seen k elements
     const int nslots = G * GROUP;
-    uint32_t *kept_hi = kept_ws + (size_t(blockIdx.y) * gridDim.x + blockIdx.x) * size_t(2 * nslots) * kUnitCols + lane;
-    uint32_t *kept_lo = kept_hi + nslots * kUnitCols;
+    uint2 *kept_ent = reinterpret_cast<uint2 *>(kept_ws) +
+                      (size_t(blockIdx.y) * gridDim.x + blockIdx.x) * size_t(nslots) * kUnitCols + lane;
     for (int slot = 0; slot < nslots; ++slot) {
         const uint32_t fill = slot >= k ? 0xFFFFFFFFu : 0u;    // padding of the last group: never the minimum
-        kept_hi[slot * kUnitCols] = fill;
-        kept_lo[slot * kUnitCols] = fill;
+        kept_ent[slot * kUnitCols] = make_uint2(fill, fill);
     }
     Kept<GROUP> kept;
-    kept.init(kept_hi, kept_lo, s, lane, G);
+    kept.init(kept_ent, s, lane, G, k);
     // Start threshold: NaN admits everything; with a pre-threshold (a value known -- with overwhelming
     // probability -- to have at least k elements of the column above it) the insert-heavy start of the scan
     // disappears.  If fewer than k elements turn out to beat it, the group is flagged and redone without it.
@@ -367,7 +361,10 @@ topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
     }
     if (cand != nullptr && lane < ncols) {
         unsigned long long *dst = cand + (int64_t(split) * k) * K + c0 + lane;
-        for (int i = 0; i < k; ++i) dst[int64_t(i) * K] = pack_key(kept_hi[i * kUnitCols], kept_lo[i * kUnitCols]);
+        for (int i = 0; i < k; ++i) {
+            const uint2 e = kept_ent[i * kUnitCols];
+            dst[int64_t(i) * K] = pack_key(e.x, e.y);
+        }
     }
 }
 
