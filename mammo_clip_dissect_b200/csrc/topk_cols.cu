@@ -40,6 +40,10 @@ constexpr int kTileRows = 32;                        // rows per TMA tile
 constexpr int kScanThreads = 32;
 constexpr int kQuads = 4;                            // quarter-warps: quarter q takes rows q, q+4, ..., q+28 of a tile
 constexpr int kListCap = 12;                         // pending slots per (quarter, column) list
+constexpr int kStepGroups = 8;                       // row groups (of 4 rows) scanned between two fold checks
+// (measured at c4: short lists -- kListCap 4, a check every 2 row groups -- buy 14 resident warps per SM with the image
+// axis split in two, and lose: 2.89 ms against 2.73 ms.  With nothing to insert 7 warps per SM already stream at
+// 5.96 TB/s; what is left above that floor is insert work, and a split adds ~50 % of it.)
 constexpr int kPendCap = kQuads * kListCap;          // pending slots per column
 constexpr int kRowsPerQuad = kTileRows / kQuads;     // a tile adds at most this many entries to a list
 constexpr int kMaxStages = 8;
@@ -246,11 +250,12 @@ topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
     float(*ring)[kTileRows][kUnitCols] = reinterpret_cast<float(*)[kTileRows][kUnitCols]>(smem_raw);
     constexpr uint32_t kTileBytes = kTileRows * kUnitCols * 4;
 
-    // second pass of the pre-threshold scheme: only column groups whose first pass came up short are redone
-    if (only_flagged && flags[blockIdx.x] == 0) return;
     const int lane = threadIdx.x;
     const int64_t c0 = int64_t(blockIdx.x) * kUnitCols;
     const int ncols = static_cast<int>(min(int64_t(kUnitCols), K - c0));
+    // second pass of the pre-threshold scheme: only column groups with a column that collected fewer than k elements
+    // (over all splits) above its start threshold are redone, exactly, without one
+    if (only_flagged && !__any_sync(0xffffffffu, lane < ncols && flags[c0 + lane] < k)) return;
     const int split = blockIdx.y;
     const int64_t row0 = int64_t(split) * rows_per_split;
     const int nrows = static_cast<int>(min(N, row0 + rows_per_split) - row0);
@@ -298,7 +303,7 @@ topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
     const int colq = (lane & 7) * 4;                 // first of this lane's 4 columns
     float4 tau4 = *reinterpret_cast<const float4 *>(&s.tau[colq]);
     const uint32_t list_first = smem_u32(&s.pend[q * kListCap][colq]);
-    const uint32_t list_limit = list_first + (kListCap - kRowsPerQuad) * kSlotBytes;   // beyond: a tile may overflow
+    const uint32_t list_limit = list_first + (kListCap - kStepGroups) * kSlotBytes;   // beyond: a step may overflow
     uint32_t p0 = list_first, p1 = list_first + 8, p2 = list_first + 16, p3 = list_first + 24;
     const uint32_t lane_off = uint32_t(q * kUnitCols + colq) * 4u;   // this lane's first element inside a tile
 
@@ -334,10 +339,16 @@ topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
         // ~0.35 of the 128 elements of a row group pass on average: one vote per row group, and (warp-uniformly)
         // nothing else for the groups nobody appends from.  Rows past the end of the last, partial tile (stale ring
         // contents) are masked inside the branch only.
+        // all votes first (independent chains: compare x4 -> vote), then the rarely taken append blocks
+        uint32_t hit[kRowsPerQuad];
+#pragma unroll
+        for (int i = 0; i < kRowsPerQuad; ++i)
+            hit[i] = __ballot_sync(0xffffffffu, !(v[i].x <= tau4.x) | !(v[i].y <= tau4.y) | !(v[i].z <= tau4.z) | !(v[i].w <= tau4.w));
 #pragma unroll
         for (int i = 0; i < kRowsPerQuad; ++i) {
-            bool px = !(v[i].x <= tau4.x), py = !(v[i].y <= tau4.y), pz = !(v[i].z <= tau4.z), pw = !(v[i].w <= tau4.w);
-            if (__any_sync(0xffffffffu, px | py | pz | pw)) {
+            if (hit[i] != 0u) {
+                // (a fold earlier in this tile may have raised tau4 since the vote: the test below uses the new one)
+                bool px = !(v[i].x <= tau4.x), py = !(v[i].y <= tau4.y), pz = !(v[i].z <= tau4.z), pw = !(v[i].w <= tau4.w);
                 if (!full_tile) {
                     const bool valid = kQuads * i < rows_left;
                     px &= valid; py &= valid; pz &= valid; pw &= valid;
@@ -348,16 +359,27 @@ topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
                 if (pz) { sts_v2(p2, __float_as_uint(v[i].z), row); p2 += kSlotBytes; }
                 if (pw) { sts_v2(p3, __float_as_uint(v[i].w), row); p3 += kSlotBytes; }
             }
+            if ((i + 1) % kStepGroups == 0) {
+                // fold as soon as the next step could overflow a list
+                const bool want = (p0 > list_limit) | (p1 > list_limit + 8) | (p2 > list_limit + 16) | (p3 > list_limit + 24);
+                if (__any_sync(0xffffffffu, want))
+                    publish_and_fold<GROUP>(s, kept, lane, q, colq, list_first, p0, p1, p2, p3, tau4);
+            }
         }
-        const bool want = (p0 > list_limit) | (p1 > list_limit + 8) | (p2 > list_limit + 16) | (p3 > list_limit + 24);
-        if (__any_sync(0xffffffffu, want))
-            publish_and_fold<GROUP>(s, kept, lane, q, colq, list_first, p0, p1, p2, p3, tau4);
     }
     publish_and_fold<GROUP>(s, kept, lane, q, colq, list_first, p0, p1, p2, p3, tau4);
     if (tau_out != nullptr && lane < ncols) tau_out[c0 + lane] = key_to_threshold(kept.root_hi);   // NaN if not full
-    if (flags != nullptr && tau0 != nullptr && !only_flagged) {
-        const bool short_of_k = lane < ncols && kept.root_hi == 0u;
-        if (__any_sync(0xffffffffu, short_of_k) && lane == 0) flags[blockIdx.x] = 1;
+    if (flags != nullptr && tau0 != nullptr && !only_flagged && lane < ncols) {
+        // how many real entries this (split, column) collected: k if the set filled up, else count them
+        int have = k;
+        if (kept.root_hi == 0u) {
+            have = 0;
+            for (int i = 0; i < k; ++i) {
+                const uint2 e = kept_ent[i * kUnitCols];
+                have += (e.x | e.y) != 0u;
+            }
+        }
+        atomicAdd(&flags[c0 + lane], have);
     }
     if (cand != nullptr && lane < ncols) {
         unsigned long long *dst = cand + (int64_t(split) * k) * K + c0 + lane;
@@ -482,59 +504,60 @@ topk_finish_kernel(const unsigned long long *__restrict__ cand, int M, int Mpad,
     }
 }
 
-// The common case (splits * k <= 128, e.g. the default k = 100 of soft_wpmi): the same bitonic network with the
-// 128 words in registers, word i = 4 * lane + slot.  Strides 1 and 2 exchange inside a lane, strides 4..64 with
-// shfl.xor; no shared memory, no loops left after unrolling -- about a third of the instructions of the generic
-// kernel.  A CTA is 8 warps = 8 adjacent columns, so its index stores fill whole 32-byte sectors.
+// The common cases (splits * k <= 256, e.g. the default k = 100 of soft_wpmi with one or two splits): the same
+// bitonic network with the words in registers, word i = PER * lane + slot (PER = 4 or 8).  Strides below PER exchange
+// inside a lane, the others with shfl.xor; no shared memory, no loops left after unrolling -- about a third of the
+// instructions of the generic kernel.  A CTA is 8 warps = 8 adjacent columns, so its index stores fill whole 32-byte
+// sectors.
 constexpr int kFinishRegWarps = 8;
 
-__device__ __forceinline__ void cmpx(unsigned long long &a, unsigned long long &b, bool a_keeps_max) {
-    const unsigned long long hi = a > b ? a : b, lo = a > b ? b : a;
-    a = a_keeps_max ? hi : lo;
-    b = a_keeps_max ? lo : hi;
-}
-
+template <int PER>
 __global__ void __launch_bounds__(kFinishRegWarps * 32)
-topk_finish128_kernel(const unsigned long long *__restrict__ cand, int M, int k, int64_t K,
-                      const float *__restrict__ A, int64_t lda, int64_t *__restrict__ idx64,
-                      int32_t *__restrict__ idx32, float *__restrict__ vals) {
+topk_finish_reg_kernel(const unsigned long long *__restrict__ cand, int M, int k, int64_t K,
+                       const float *__restrict__ A, int64_t lda, int64_t *__restrict__ idx64,
+                       int32_t *__restrict__ idx32, float *__restrict__ vals) {
+    constexpr int TOTAL = 32 * PER;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t col = int64_t(blockIdx.x) * kFinishRegWarps + warp;
     if (col >= K) return;
-    unsigned long long v[4];
+    unsigned long long v[PER];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const int i = lane * 4 + e;
+    for (int e = 0; e < PER; ++e) {
+        const int i = lane * PER + e;
         v[e] = i < M ? cand[int64_t(i) * K + col] : 0ull;
     }
 #pragma unroll
-    for (int size = 2; size <= 128; size <<= 1) {
+    for (int size = 2; size <= TOTAL; size <<= 1) {
 #pragma unroll
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            if (stride >= 4) {
+            if (stride >= PER) {
                 // descending block <=> (i & size) == 0; the lower index of a pair keeps the maximum there
-                const bool desc = size >= 128 || ((lane * 4) & size) == 0;
-                const bool upper = (lane & (stride >> 2)) != 0;
+                const bool desc = size >= TOTAL || ((lane * PER) & size) == 0;
+                const bool upper = (lane & (stride / PER)) != 0;
                 const bool keep_max = desc != upper;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const unsigned long long o = __shfl_xor_sync(0xffffffffu, v[e], stride >> 2);
+                for (int e = 0; e < PER; ++e) {
+                    const unsigned long long o = __shfl_xor_sync(0xffffffffu, v[e], stride / PER);
                     const unsigned long long hi = v[e] > o ? v[e] : o, lo = v[e] > o ? o : v[e];
                     v[e] = keep_max ? hi : lo;
                 }
-            } else if (stride == 2) {
-                const bool d0 = ((lane * 4 + 0) & size) == 0;       // same block for all four words when size >= 4
-                cmpx(v[0], v[2], d0);
-                cmpx(v[1], v[3], d0);
             } else {
-                cmpx(v[0], v[1], ((lane * 4 + 0) & size) == 0);
-                cmpx(v[2], v[3], ((lane * 4 + 2) & size) == 0);
+#pragma unroll
+                for (int e = 0; e < PER; ++e) {
+                    if ((e & stride) == 0) {
+                        const bool desc = size >= TOTAL || ((lane * PER + e) & size) == 0;
+                        const unsigned long long x = v[e], y = v[e + stride];
+                        const unsigned long long hi = x > y ? x : y, lo = x > y ? y : x;
+                        v[e] = desc ? hi : lo;
+                        v[e + stride] = desc ? lo : hi;
+                    }
+                }
             }
         }
     }
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const int r = lane * 4 + e;
+    for (int e = 0; e < PER; ++e) {
+        const int r = lane * PER + e;
         if (r < k) {
             const uint32_t row = ~static_cast<uint32_t>(v[e]);
             const int64_t o = int64_t(r) * K + col;
@@ -566,10 +589,13 @@ static bool make_plan(int64_t N, int64_t K, int64_t k64, TopkPlan *p) {
     const int64_t sms = num_sms();
     // ring depth: enough scan warps per SM (the scan is latency-bound per warp) with a few tiles in flight each
     int nstage = static_cast<int>(tunable(kTopkStages));
-    if (nstage < 2 || nstage > kMaxStages) nstage = 4;
+    if (nstage < 2 || nstage > kMaxStages) nstage = 4;      // measured: 2..5 stages are the same speed
     p->nstage = nstage;
     p->smem = scan_smem_bytes(nstage);
     int occ = static_cast<int>(kSmemPerSM / (p->smem + kSmemCtaReserve));
+    // registers: the kept set's root group lives in registers (topk_scan_kernel<16|32|64>: 112 / 154 / 235 per thread)
+    const int regs = k <= 128 ? 112 : (k <= 256 ? 160 : 240);
+    if (occ > 65536 / (32 * regs)) occ = 65536 / (32 * regs);
     if (occ > 16) occ = 16;
     if (occ < 1) occ = 1;
     p->occ = occ;
@@ -614,7 +640,7 @@ static bool make_plan(int64_t N, int64_t K, int64_t k64, TopkPlan *p) {
     p->pre_k = 0;
     p->pre_rows = 0;
     p->pre_bytes = 0;
-    if (tunable(kTopkPre) != 2 && p->splits == 1 && N >= 16384 && k <= 256) {
+    if (tunable(kTopkPre) != 2 && N >= 16384 && k <= 256) {
         static const int kStrides[] = {32, 16, 8};                  // sample one 32-row tile out of every `stride`
         for (int stride : kStrides) {
             const double lam = double(k) / stride;
@@ -625,8 +651,8 @@ static bool make_plan(int64_t N, int64_t K, int64_t k64, TopkPlan *p) {
                 p->pre_stride = stride;
                 p->pre_k = pk;
                 p->pre_rows = ntile * kTileRows;
-                p->pre_bytes = (size_t(K) * 4 + 255) / 256 * 256 + (size_t(ncb) * 4 + 255) / 256 * 256 +
-                               size_t(ntile) * size_t(K) * 4;          // tau, flags, tile maxima
+                p->pre_bytes = (size_t(K) * 4 + 255) / 256 * 256 + (size_t(K) * 4 + 255) / 256 * 256 +
+                               size_t(ntile) * size_t(K) * 4;          // tau, fill counts, tile maxima
                 break;
             }
         }
@@ -732,10 +758,10 @@ extern "C" int mcd_topk_cols_f32(const float *A, int64_t lda, int64_t N, int64_t
         char *pre = static_cast<char *>(workspace) + p.cand_bytes + p.kept_bytes;
         float *tau = reinterpret_cast<float *>(pre);
         int *flags = reinterpret_cast<int *>(pre + (size_t(K) * 4 + 255) / 256 * 256);
-        uint32_t *tilemax = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(flags) + (size_t(grid.x) * 4 + 255) / 256 * 256);
+        uint32_t *tilemax = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(flags) + (size_t(K) * 4 + 255) / 256 * 256);
         {
             // the sample is one 32-row tile out of every pre_stride tiles
-            if (cudaMemsetAsync(flags, 0, size_t(grid.x) * 4, st) != cudaSuccess) return MCD_ERR_CUDA;
+            if (cudaMemsetAsync(flags, 0, size_t(K) * 4, st) != cudaSuccess) return MCD_ERR_CUDA;
             const int nsample = static_cast<int>(p.pre_rows / kTileRows);
             dim3 sgrid(static_cast<unsigned>(ceil_div<int64_t>(K, kSampleCols)), static_cast<unsigned>(nsample));
             sample_tilemax_kernel<<<sgrid, kSampleThreads, 0, st>>>(A, lda, K, int64_t(kTileRows) * p.pre_stride, 1, tilemax);
@@ -755,10 +781,14 @@ extern "C" int mcd_topk_cols_f32(const float *A, int64_t lda, int64_t N, int64_t
     rc = launch_scan(grid, p, map, main_args, st);
     if (rc != MCD_OK) return rc;
 
-    if (p.mpad <= 128 && tunable(kTopkVariant) != 2) {
+    if (p.mpad <= 256 && tunable(kTopkVariant) != 2) {
         const unsigned fgrid = static_cast<unsigned>(ceil_div<int64_t>(K, kFinishRegWarps));
-        topk_finish128_kernel<<<fgrid, kFinishRegWarps * 32, 0, st>>>(cand, p.splits * int(k), int(k), K, A, lda,
-                                                                      idx64_out, idx32_out, vals_out);
+        if (p.mpad <= 128)
+            topk_finish_reg_kernel<4><<<fgrid, kFinishRegWarps * 32, 0, st>>>(cand, p.splits * int(k), int(k), K, A, lda,
+                                                                              idx64_out, idx32_out, vals_out);
+        else
+            topk_finish_reg_kernel<8><<<fgrid, kFinishRegWarps * 32, 0, st>>>(cand, p.splits * int(k), int(k), K, A, lda,
+                                                                              idx64_out, idx32_out, vals_out);
         return check_launch();
     }
     const size_t fsmem = size_t(kFinishWarps) * p.mpad * sizeof(unsigned long long);
