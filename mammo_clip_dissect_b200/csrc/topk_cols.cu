@@ -116,20 +116,60 @@ struct Kept {
     float floor_tau;            // threshold while the set still has empty slots (NaN = admit everything)
     uint32_t ch[GROUP], cl[GROUP];   // register copy of group rg (statically indexed only)
 
-    // the caller has filled ent[] with k empty-slot sentinels (0, 0) followed by all-ones padding
-    __device__ __forceinline__ void init(uint2 *ent_, ScanSmem &s, int lane, int G, int k) {
+    int cnt;                    // entries so far; the set is "full" (root valid, threshold live) once cnt == k
+
+    // the caller has written all-ones into the padding slots (>= k) of the last group: never a minimum
+    __device__ __forceinline__ void init(uint2 *ent_, ScanSmem &s, int lane) {
         ent = ent_;
         gmh = &s.gmh[0][lane];
         gml = &s.gml[0][lane];
         gms = &s.gms[0][lane];
         root_hi = root_lo = 0u;
         rg = rs = 0;
+        cnt = 0;
         for (int g = 0; g < kMaxGroups; ++g) {
-            gmh[g * kUnitCols] = gml[g * kUnitCols] = g < G ? 0u : 0xFFFFFFFFu;
+            gmh[g * kUnitCols] = gml[g * kUnitCols] = 0xFFFFFFFFu;
             gms[g * kUnitCols] = 0;
         }
 #pragma unroll
-        for (int i = 0; i < GROUP; ++i) ch[i] = cl[i] = i < k ? 0u : 0xFFFFFFFFu;
+        for (int i = 0; i < GROUP; ++i) ch[i] = cl[i] = 0xFFFFFFFFu;
+    }
+
+    // The first k entries of a column need no minimum search: store at the next free slot and keep the group's
+    // minimum up to date (entries are only added, so it is a running minimum).  The k-th entry makes the set full:
+    // the overall minimum is the smallest group minimum, and its group is loaded into the register copy.
+    __device__ __forceinline__ void fill(uint32_t eh, uint32_t el, int k) {
+        const int g = cnt / GROUP, sl = cnt % GROUP;
+        ent[cnt * kUnitCols] = make_uint2(eh, el);
+        if (key_gt(gmh[g * kUnitCols], gml[g * kUnitCols], eh, el)) {
+            gmh[g * kUnitCols] = eh;
+            gml[g * kUnitCols] = el;
+            gms[g * kUnitCols] = static_cast<uint8_t>(sl);
+        }
+        if (++cnt == k) {
+            uint32_t bh = 0xFFFFFFFFu, bl = 0xFFFFFFFFu;
+            int bg = 0;
+#pragma unroll
+            for (int gg = kMaxGroups - 1; gg >= 0; --gg) {
+                const uint32_t ah = gmh[gg * kUnitCols], al = gml[gg * kUnitCols];
+                if (!key_gt(ah, al, bh, bl)) {
+                    bh = ah;
+                    bl = al;
+                    bg = gg;
+                }
+            }
+            root_hi = bh;
+            root_lo = bl;
+            rg = bg;
+            rs = gms[bg * kUnitCols];
+            const uint2 *ng = ent + bg * (GROUP * kUnitCols);
+#pragma unroll
+            for (int i = 0; i < GROUP; ++i) {
+                const uint2 t = ng[i * kUnitCols];
+                ch[i] = t.x;
+                cl[i] = t.y;
+            }
+        }
     }
 
     // precondition: (eh, el) > root.  Overwrites the root entry with (eh, el) and re-establishes the minima.
@@ -141,8 +181,7 @@ struct Kept {
             ch[i] = (i == rs) ? eh : ch[i];
             cl[i] = (i == rs) ? el : cl[i];
         }
-        // minimum (key, ~row) of the group; a strictly smaller entry replaces, so among equal entries (the (0, 0)
-        // empty-slot sentinels) the first slot wins
+        // minimum (key, ~row) of the group (entries are distinct: the row index is part of them)
         uint32_t mh = ch[0], ml = cl[0];
         int ms = 0;
 #pragma unroll
@@ -167,7 +206,7 @@ struct Kept {
 #pragma unroll
         for (int gg = kMaxGroups - 1; gg >= 0; --gg) {
             const uint32_t ah = (gg == rg) ? mh : xh[gg], al = (gg == rg) ? ml : xl[gg];
-            if (!key_gt(ah, al, bh, bl)) {       // <= : on equal (sentinel) minima the lowest group wins
+            if (!key_gt(ah, al, bh, bl)) {
                 bh = ah;
                 bl = al;
                 bg = gg;
@@ -193,7 +232,7 @@ struct Kept {
 // whole warp: lane c folds the kQuads pending lists of column c into the column's kept set and publishes
 // the new threshold
 template <int GROUP>
-__device__ __forceinline__ void fold_pending(ScanSmem &s, Kept<GROUP> &kept, int lane) {
+__device__ __forceinline__ void fold_pending(ScanSmem &s, Kept<GROUP> &kept, int lane, int k) {
     int c[kQuads], total = 0;
 #pragma unroll
     for (int q = 0; q < kQuads; ++q) {
@@ -212,16 +251,17 @@ __device__ __forceinline__ void fold_pending(ScanSmem &s, Kept<GROUP> &kept, int
                 }
             const uint2 raw = s.pend[q * kListCap + e][lane];
             const uint32_t ch = ordered_key(__uint_as_float(raw.x)), cl = ~raw.y;
-            if (key_gt(ch, cl, kept.root_hi, kept.root_lo)) kept.replace_min(ch, cl);
+            if (kept.cnt < k) kept.fill(ch, cl, k);
+            else if (key_gt(ch, cl, kept.root_hi, kept.root_lo)) kept.replace_min(ch, cl);
         }
     }
-    s.tau[lane] = kept.root_hi == 0u ? kept.floor_tau : key_to_threshold(kept.root_hi);
+    s.tau[lane] = kept.cnt < k ? kept.floor_tau : key_to_threshold(kept.root_hi);
 }
 
 constexpr uint32_t kSlotBytes = kUnitCols * 8;       // one pending slot row
 
 template <int GROUP>
-__device__ __forceinline__ void publish_and_fold(ScanSmem &s, Kept<GROUP> &kept, int lane, int q, int colq,
+__device__ __forceinline__ void publish_and_fold(ScanSmem &s, Kept<GROUP> &kept, int lane, int k, int q, int colq,
                                                  uint32_t list_first, uint32_t &p0, uint32_t &p1, uint32_t &p2,
                                                  uint32_t &p3, float4 &tau4) {
     s.pcnt[q][colq + 0] = static_cast<int>((p0 - list_first) / kSlotBytes);
@@ -229,7 +269,7 @@ __device__ __forceinline__ void publish_and_fold(ScanSmem &s, Kept<GROUP> &kept,
     s.pcnt[q][colq + 2] = static_cast<int>((p2 - list_first) / kSlotBytes);
     s.pcnt[q][colq + 3] = static_cast<int>((p3 - list_first) / kSlotBytes);
     __syncwarp();
-    fold_pending<GROUP>(s, kept, lane);
+    fold_pending<GROUP>(s, kept, lane, k);
     __syncwarp();
     tau4 = *reinterpret_cast<const float4 *>(&s.tau[colq]);
     p0 = list_first; p1 = list_first + 8; p2 = list_first + 16; p3 = list_first + 24;
@@ -278,17 +318,13 @@ topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
             tma_tile_g2s(ring_addr + t * kTileBytes, &tmap, tx, ty0 + t * tile_row_stride, full_addr + t * 8, policy);
         }
     }
-    // kept sets start as k empty-slot sentinels (0, 0) that sort below every real entry; the NaN threshold
-    // admits everything until a column has seen k elements
+    // kept sets start empty; the NaN threshold admits everything until a column has seen k elements
     const int nslots = G * GROUP;
     uint2 *kept_ent = reinterpret_cast<uint2 *>(kept_ws) +
                       (size_t(blockIdx.y) * gridDim.x + blockIdx.x) * size_t(nslots) * kUnitCols + lane;
-    for (int slot = 0; slot < nslots; ++slot) {
-        const uint32_t fill = slot >= k ? 0xFFFFFFFFu : 0u;    // padding of the last group: never the minimum
-        kept_ent[slot * kUnitCols] = make_uint2(fill, fill);
-    }
+    for (int slot = k; slot < nslots; ++slot) kept_ent[slot * kUnitCols] = make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
     Kept<GROUP> kept;
-    kept.init(kept_ent, s, lane, G, k);
+    kept.init(kept_ent, s, lane);
     // Start threshold: NaN admits everything; with a pre-threshold (a value known -- with overwhelming
     // probability -- to have at least k elements of the column above it) the insert-heavy start of the scan
     // disappears.  If fewer than k elements turn out to beat it, the group is flagged and redone without it.
@@ -363,29 +399,23 @@ topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
                 // fold as soon as the next step could overflow a list
                 const bool want = (p0 > list_limit) | (p1 > list_limit + 8) | (p2 > list_limit + 16) | (p3 > list_limit + 24);
                 if (__any_sync(0xffffffffu, want))
-                    publish_and_fold<GROUP>(s, kept, lane, q, colq, list_first, p0, p1, p2, p3, tau4);
+                    publish_and_fold<GROUP>(s, kept, lane, k, q, colq, list_first, p0, p1, p2, p3, tau4);
             }
         }
     }
-    publish_and_fold<GROUP>(s, kept, lane, q, colq, list_first, p0, p1, p2, p3, tau4);
-    if (tau_out != nullptr && lane < ncols) tau_out[c0 + lane] = key_to_threshold(kept.root_hi);   // NaN if not full
+    publish_and_fold<GROUP>(s, kept, lane, k, q, colq, list_first, p0, p1, p2, p3, tau4);
+    if (tau_out != nullptr && lane < ncols)
+        tau_out[c0 + lane] = kept.cnt < k ? __uint_as_float(0x7FC00000u) : key_to_threshold(kept.root_hi);
     if (flags != nullptr && tau0 != nullptr && !only_flagged && lane < ncols) {
-        // how many real entries this (split, column) collected: k if the set filled up, else count them
-        int have = k;
-        if (kept.root_hi == 0u) {
-            have = 0;
-            for (int i = 0; i < k; ++i) {
-                const uint2 e = kept_ent[i * kUnitCols];
-                have += (e.x | e.y) != 0u;
-            }
-        }
+        // how many entries this (split, column) collected above the start threshold
+        const int have = kept.cnt;
         atomicAdd(&flags[c0 + lane], have);
     }
     if (cand != nullptr && lane < ncols) {
         unsigned long long *dst = cand + (int64_t(split) * k) * K + c0 + lane;
         for (int i = 0; i < k; ++i) {
             const uint2 e = kept_ent[i * kUnitCols];
-            dst[int64_t(i) * K] = pack_key(e.x, e.y);
+            dst[int64_t(i) * K] = i < kept.cnt ? pack_key(e.x, e.y) : 0ull;      // 0 sorts below every real entry
         }
     }
 }
