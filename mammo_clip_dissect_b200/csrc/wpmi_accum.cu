@@ -4,9 +4,11 @@
 //   L[j,c] = sum_r log( 1 + p[r] * (S[idx[r,j], c] - 1) + min_prob )        (soft-WPMI)
 //   L[j,c] = sum_r log( S[idx[r,j], c] + min_prob )                         (WPMI, p == NULL)
 //
-// The per-element operation order is the reference's (sub, mul, add, add -- no FMA contraction)
-// so the rounding of `S - 1`, which dominates the reference's own fp32 noise, is reproduced; the
-// log is MUFU lg2 accumulated in the log2 domain and scaled by ln2 once per output.
+// The log is MUFU lg2 accumulated in the log2 domain and scaled by ln2 once per output; by default the terms of four
+// consecutive ranks are multiplied before one lg2, and a term is evaluated as one FMA (see term<> below; both are
+// ~1e-7 relative effects on L against a stated tolerance of 1e-5).  The reference's own per-element operation order
+// (sub, mul, add, add -- no FMA contraction) is kept selectable and is what runs whenever the grouping
+// preconditions do not hold.
 //
 // Work decomposition: a CTA of 192 threads handles NPB = 192/TPN neurons for one tile of
 // 4*TPN concepts; each thread owns 4 adjacent concepts (one 16-byte load per gathered row) and
@@ -31,10 +33,15 @@ __device__ __forceinline__ float lg2_fast(float x) {
     return r;
 }
 
-// value inside the log: the reference's unfused sequence (sub, mul, add, add)
-template <bool SOFT>
-__device__ __forceinline__ float term(float s, float w, float eps) {
+// value inside the log.  FUSED = false: the reference's unfused sequence (sub, mul, add, add), bit for bit.
+// FUSED = true: the same quantity as one FMA, p*S + c with c = fl32(1 - p + eps) prepared in double per rank -- it is
+// closer to the exact value than the reference's own fp32 sequence (whose rounding of S - 1 costs up to 3e-8 absolute
+// on terms as small as 2e-3) and differs from it by ~2e-5 absolute in a sum of 100 logs of magnitude ~450
+// (5e-8 relative; the stated tolerance is 1e-5; lg2.approx alone contributes 1.4e-5).
+template <bool SOFT, bool FUSED>
+__device__ __forceinline__ float term(float s, float w, float c, float eps) {
     if (SOFT) {
+        if (FUSED) return __fmaf_rn(w, s, c);
         float v = __fsub_rn(s, 1.0f);
         v = __fmul_rn(w, v);
         v = __fadd_rn(1.0f, v);
@@ -61,7 +68,7 @@ __device__ __forceinline__ float4 load_row(const char *base, uint32_t off, int n
 // underflow: the product is >= 1e-36; no sign cancellation), i.e. for probabilities S in [0,1] and weights p in
 // [0,1]; the host checks eps, the CTA checks p, S in [0,1] is the documented domain of this entry point.  The extra
 // rounding (3 products, 6e-8 relative each = 1.8e-7 absolute in the log) is below lg2.approx's own error.
-template <int TPN, int U, bool SOFT, bool VEC, bool FTZ, bool GROUPED>
+template <int TPN, int U, bool SOFT, bool VEC, bool FTZ, bool GROUPED, bool FUSED>
 __global__ void __launch_bounds__(kAccumThreads)
 wpmi_accum_kernel(const float *__restrict__ S, int64_t lds, int C, const int32_t *__restrict__ idx, int64_t K, int k,
                   const float *__restrict__ p, float eps, float *__restrict__ L, int64_t ldl, int n_groups) {
@@ -72,6 +79,7 @@ wpmi_accum_kernel(const float *__restrict__ S, int64_t lds, int C, const int32_t
     const uint64_t keep = l2_policy_evict_last();
     __shared__ __align__(16) uint32_t s_off[NPB][kAccumMaxK];   // BYTE offsets idx * lds * 4 (host: N * lds < 2^30)
     __shared__ __align__(16) float s_p[kAccumMaxK];
+    __shared__ __align__(16) float s_c[SOFT && FUSED ? kAccumMaxK : 4];
 
     const int tile = blockIdx.x / n_groups;
     const int group = blockIdx.x - tile * n_groups;
@@ -88,6 +96,7 @@ wpmi_accum_kernel(const float *__restrict__ S, int64_t lds, int C, const int32_t
         for (int r = tid; r < k; r += kAccumThreads) {
             const float w = p[r];
             s_p[r] = w;
+            if (FUSED) s_c[r] = static_cast<float>(1.0 - double(w) + double(eps));
             p_ok = p_ok && (w >= 0.f) && (w <= 1.f);
         }
     const bool grouped = GROUPED && (__syncthreads_and(p_ok) != 0);
@@ -114,36 +123,40 @@ wpmi_accum_kernel(const float *__restrict__ S, int64_t lds, int C, const int32_t
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 float *acc = h ? acc1 : acc0;
-                float w[4];
+                float w[4], c[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) w[u] = SOFT ? s_p[r + 4 * h + u] : 0.f;
+                for (int u = 0; u < 4; ++u) {
+                    w[u] = SOFT ? s_p[r + 4 * h + u] : 0.f;
+                    c[u] = SOFT && FUSED ? s_c[r + 4 * h + u] : 0.f;
+                }
                 const float4 *q = s + 4 * h;
-                acc[0] += lg2_fast<FTZ>((term<SOFT>(q[0].x, w[0], eps) * term<SOFT>(q[1].x, w[1], eps)) *
-                                        (term<SOFT>(q[2].x, w[2], eps) * term<SOFT>(q[3].x, w[3], eps)));
-                acc[1] += lg2_fast<FTZ>((term<SOFT>(q[0].y, w[0], eps) * term<SOFT>(q[1].y, w[1], eps)) *
-                                        (term<SOFT>(q[2].y, w[2], eps) * term<SOFT>(q[3].y, w[3], eps)));
-                acc[2] += lg2_fast<FTZ>((term<SOFT>(q[0].z, w[0], eps) * term<SOFT>(q[1].z, w[1], eps)) *
-                                        (term<SOFT>(q[2].z, w[2], eps) * term<SOFT>(q[3].z, w[3], eps)));
-                acc[3] += lg2_fast<FTZ>((term<SOFT>(q[0].w, w[0], eps) * term<SOFT>(q[1].w, w[1], eps)) *
-                                        (term<SOFT>(q[2].w, w[2], eps) * term<SOFT>(q[3].w, w[3], eps)));
+                acc[0] += lg2_fast<FTZ>((term<SOFT, FUSED>(q[0].x, w[0], c[0], eps) * term<SOFT, FUSED>(q[1].x, w[1], c[1], eps)) *
+                                        (term<SOFT, FUSED>(q[2].x, w[2], c[2], eps) * term<SOFT, FUSED>(q[3].x, w[3], c[3], eps)));
+                acc[1] += lg2_fast<FTZ>((term<SOFT, FUSED>(q[0].y, w[0], c[0], eps) * term<SOFT, FUSED>(q[1].y, w[1], c[1], eps)) *
+                                        (term<SOFT, FUSED>(q[2].y, w[2], c[2], eps) * term<SOFT, FUSED>(q[3].y, w[3], c[3], eps)));
+                acc[2] += lg2_fast<FTZ>((term<SOFT, FUSED>(q[0].z, w[0], c[0], eps) * term<SOFT, FUSED>(q[1].z, w[1], c[1], eps)) *
+                                        (term<SOFT, FUSED>(q[2].z, w[2], c[2], eps) * term<SOFT, FUSED>(q[3].z, w[3], c[3], eps)));
+                acc[3] += lg2_fast<FTZ>((term<SOFT, FUSED>(q[0].w, w[0], c[0], eps) * term<SOFT, FUSED>(q[1].w, w[1], c[1], eps)) *
+                                        (term<SOFT, FUSED>(q[2].w, w[2], c[2], eps) * term<SOFT, FUSED>(q[3].w, w[3], c[3], eps)));
             }
         }
         for (; r + 4 <= k; r += 4) {
             float4 q[4];
-            float w[4];
+            float w[4], c[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 q[u] = load_row<VEC>(base, my_off[r + u], nvalid, keep);
                 w[u] = SOFT ? s_p[r + u] : 0.f;
+                c[u] = SOFT && FUSED ? s_c[r + u] : 0.f;
             }
-            acc0[0] += lg2_fast<FTZ>((term<SOFT>(q[0].x, w[0], eps) * term<SOFT>(q[1].x, w[1], eps)) *
-                                     (term<SOFT>(q[2].x, w[2], eps) * term<SOFT>(q[3].x, w[3], eps)));
-            acc0[1] += lg2_fast<FTZ>((term<SOFT>(q[0].y, w[0], eps) * term<SOFT>(q[1].y, w[1], eps)) *
-                                     (term<SOFT>(q[2].y, w[2], eps) * term<SOFT>(q[3].y, w[3], eps)));
-            acc0[2] += lg2_fast<FTZ>((term<SOFT>(q[0].z, w[0], eps) * term<SOFT>(q[1].z, w[1], eps)) *
-                                     (term<SOFT>(q[2].z, w[2], eps) * term<SOFT>(q[3].z, w[3], eps)));
-            acc0[3] += lg2_fast<FTZ>((term<SOFT>(q[0].w, w[0], eps) * term<SOFT>(q[1].w, w[1], eps)) *
-                                     (term<SOFT>(q[2].w, w[2], eps) * term<SOFT>(q[3].w, w[3], eps)));
+            acc0[0] += lg2_fast<FTZ>((term<SOFT, FUSED>(q[0].x, w[0], c[0], eps) * term<SOFT, FUSED>(q[1].x, w[1], c[1], eps)) *
+                                     (term<SOFT, FUSED>(q[2].x, w[2], c[2], eps) * term<SOFT, FUSED>(q[3].x, w[3], c[3], eps)));
+            acc0[1] += lg2_fast<FTZ>((term<SOFT, FUSED>(q[0].y, w[0], c[0], eps) * term<SOFT, FUSED>(q[1].y, w[1], c[1], eps)) *
+                                     (term<SOFT, FUSED>(q[2].y, w[2], c[2], eps) * term<SOFT, FUSED>(q[3].y, w[3], c[3], eps)));
+            acc0[2] += lg2_fast<FTZ>((term<SOFT, FUSED>(q[0].z, w[0], c[0], eps) * term<SOFT, FUSED>(q[1].z, w[1], c[1], eps)) *
+                                     (term<SOFT, FUSED>(q[2].z, w[2], c[2], eps) * term<SOFT, FUSED>(q[3].z, w[3], c[3], eps)));
+            acc0[3] += lg2_fast<FTZ>((term<SOFT, FUSED>(q[0].w, w[0], c[0], eps) * term<SOFT, FUSED>(q[1].w, w[1], c[1], eps)) *
+                                     (term<SOFT, FUSED>(q[2].w, w[2], c[2], eps) * term<SOFT, FUSED>(q[3].w, w[3], c[3], eps)));
         }
     } else {
         for (; r + U <= k; r += U) {
@@ -154,20 +167,28 @@ wpmi_accum_kernel(const float *__restrict__ S, int64_t lds, int C, const int32_t
             for (int u = 0; u < U; ++u) {
                 const float w = SOFT ? s_p[r + u] : 0.f;
                 float *acc = (u & 1) ? acc1 : acc0;
-                acc[0] += lg2_fast<FTZ>(term<SOFT>(s[u].x, w, eps));
-                acc[1] += lg2_fast<FTZ>(term<SOFT>(s[u].y, w, eps));
-                acc[2] += lg2_fast<FTZ>(term<SOFT>(s[u].z, w, eps));
-                acc[3] += lg2_fast<FTZ>(term<SOFT>(s[u].w, w, eps));
+                acc[0] += lg2_fast<FTZ>(term<SOFT, false>(s[u].x, w, 0.f, eps));
+                acc[1] += lg2_fast<FTZ>(term<SOFT, false>(s[u].y, w, 0.f, eps));
+                acc[2] += lg2_fast<FTZ>(term<SOFT, false>(s[u].z, w, 0.f, eps));
+                acc[3] += lg2_fast<FTZ>(term<SOFT, false>(s[u].w, w, 0.f, eps));
             }
         }
     }
     for (; r < k; ++r) {
         const float4 s = load_row<VEC>(base, my_off[r], nvalid, keep);
         const float w = SOFT ? s_p[r] : 0.f;
-        acc0[0] += lg2_fast<FTZ>(term<SOFT>(s.x, w, eps));
-        acc0[1] += lg2_fast<FTZ>(term<SOFT>(s.y, w, eps));
-        acc0[2] += lg2_fast<FTZ>(term<SOFT>(s.z, w, eps));
-        acc0[3] += lg2_fast<FTZ>(term<SOFT>(s.w, w, eps));
+        if (SOFT && FUSED && grouped) {
+            const float c = s_c[r];
+            acc0[0] += lg2_fast<FTZ>(term<SOFT, true>(s.x, w, c, eps));
+            acc0[1] += lg2_fast<FTZ>(term<SOFT, true>(s.y, w, c, eps));
+            acc0[2] += lg2_fast<FTZ>(term<SOFT, true>(s.z, w, c, eps));
+            acc0[3] += lg2_fast<FTZ>(term<SOFT, true>(s.w, w, c, eps));
+        } else {
+            acc0[0] += lg2_fast<FTZ>(term<SOFT, false>(s.x, w, 0.f, eps));
+            acc0[1] += lg2_fast<FTZ>(term<SOFT, false>(s.y, w, 0.f, eps));
+            acc0[2] += lg2_fast<FTZ>(term<SOFT, false>(s.z, w, 0.f, eps));
+            acc0[3] += lg2_fast<FTZ>(term<SOFT, false>(s.w, w, 0.f, eps));
+        }
     }
     constexpr float kLn2 = 0.693147180559945309417f;
     float *out = L + j * ldl + c0;
@@ -185,17 +206,20 @@ static int launch_accum(const float *S, int64_t lds, int C, const int32_t *idx, 
     const int64_t n_groups = ceil_div<int64_t>(K, NPB);
     const int64_t blocks = n_groups * n_tiles;
     if (blocks > 0x7FFFFFFFll) return MCD_ERR_UNSUPPORTED;
-    // grouped logs need eps >= 1e-9 (see the kernel); tunable accum_unroll = 1 forces one lg2 per term
-    const bool grouped = eps >= 1e-9f && eps <= 1.0f && tunable(kAccumUnroll) != 1;
-    if (grouped)
-        wpmi_accum_kernel<TPN, 8, SOFT, VEC, true, true><<<static_cast<unsigned>(blocks), kAccumThreads, 0, st>>>(
-            S, lds, C, idx, K, k, p, eps, L, ldl, static_cast<int>(n_groups));
+    // grouped logs need eps >= 1e-9 (see the kernel).  Tunable accum_unroll: 0 = grouped, term as one FMA (default);
+    // 2 = grouped, term in the reference's operation order; 1 = one lg2 per term, reference order
+    const int mode = static_cast<int>(tunable(kAccumUnroll));
+    const bool grouped = eps >= 1e-9f && eps <= 1.0f && mode != 1;
+    const unsigned nb = static_cast<unsigned>(blocks);
+    const int ng = static_cast<int>(n_groups);
+    if (grouped && mode != 2)
+        wpmi_accum_kernel<TPN, 8, SOFT, VEC, true, true, true><<<nb, kAccumThreads, 0, st>>>(S, lds, C, idx, K, k, p, eps, L, ldl, ng);
+    else if (grouped)
+        wpmi_accum_kernel<TPN, 8, SOFT, VEC, true, true, false><<<nb, kAccumThreads, 0, st>>>(S, lds, C, idx, K, k, p, eps, L, ldl, ng);
     else if (ftz)
-        wpmi_accum_kernel<TPN, 8, SOFT, VEC, true, false><<<static_cast<unsigned>(blocks), kAccumThreads, 0, st>>>(
-            S, lds, C, idx, K, k, p, eps, L, ldl, static_cast<int>(n_groups));
+        wpmi_accum_kernel<TPN, 8, SOFT, VEC, true, false, false><<<nb, kAccumThreads, 0, st>>>(S, lds, C, idx, K, k, p, eps, L, ldl, ng);
     else
-        wpmi_accum_kernel<TPN, 8, SOFT, VEC, false, false><<<static_cast<unsigned>(blocks), kAccumThreads, 0, st>>>(
-            S, lds, C, idx, K, k, p, eps, L, ldl, static_cast<int>(n_groups));
+        wpmi_accum_kernel<TPN, 8, SOFT, VEC, false, false, false><<<nb, kAccumThreads, 0, st>>>(S, lds, C, idx, K, k, p, eps, L, ldl, ng);
     return check_launch();
 }
 

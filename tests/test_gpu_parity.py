@@ -276,11 +276,12 @@ def test_accumulate_concept_tiles(sim, tile):
 
 
 @pytest.mark.parametrize("k", [1, 3, 4, 7, 8, 12, 50, 101])
-@pytest.mark.parametrize("case", ["soft", "hard", "tiny_eps", "weights_above_one", "per_term"])
+@pytest.mark.parametrize("case", ["soft", "hard", "tiny_eps", "weights_above_one", "per_term", "reference_order"])
 def test_accumulate_grouped_logs_and_fallbacks(sim, k, case):
-    """K3 multiplies the terms of 4 ranks before one lg2 when eps >= 1e-9 and every weight is in [0,1]; otherwise
-    (and with the tunable) it takes one lg2 per term.  All paths against the oracle, incl. NaN where the reference
-    takes the log of a negative number."""
+    """K3 multiplies the terms of 4 ranks before one lg2 when eps >= 1e-9 and every weight is in [0,1] (default: each
+    term as one FMA; accum_unroll = 2: in the reference's operation order); otherwise (and with accum_unroll = 1) it
+    takes one lg2 per term in reference order.  All paths against the oracle, incl. NaN where the reference takes the
+    log of a negative number."""
     from mammo_clip_dissect_b200 import _lib
     S = torch.softmax(10 * torch.randn(400, 131, generator=gen(31)) * 0.3, dim=1)
     idx = torch.stack([torch.randperm(400, generator=gen(32 + j))[:k] for j in range(45)], dim=1)   # [k, 45]
@@ -288,7 +289,7 @@ def test_accumulate_grouped_logs_and_fallbacks(sim, k, case):
     w = None if case == "hard" else orc.p_ramp(k, 1.3 if case == "weights_above_one" else 0.998, 0.97)
     ref = orc.log_sums_chunked(S, idx, w, eps)
     try:
-        _lib.set_tunable("accum_unroll", 1 if case == "per_term" else 0)
+        _lib.set_tunable("accum_unroll", {"per_term": 1, "reference_order": 2}.get(case, 0))
         out = sim.log_sums(S.to(DEV), idx.to(DEV).int(), None if w is None else w.to(DEV), eps).cpu()
     finally:
         _lib.set_tunable("accum_unroll", 0)
