@@ -203,7 +203,21 @@ def run_ours(args):
     # flight, the last one is waited for inside the timed region); "fused": the finalize kernel stores into all peers;
     # "nccl": torch.distributed all_gather.
     xmode = os.environ.get("MCD_EXCHANGE", "copy")
-    exchange = mdist.PeerScoreExchange(shard_sizes, C_CONCEPTS, dev, mode=xmode) if world > 1 and xmode != "nccl" else None
+    exchange = None
+    if world > 1 and xmode != "nccl":
+        # every rank must take the same path: agree on whether the symmetric-memory rendezvous worked everywhere
+        import torch.distributed as dist
+        try:
+            exchange = mdist.PeerScoreExchange(shard_sizes, C_CONCEPTS, dev, mode=xmode)
+            ok = 1
+        except Exception as exc:                                   # no peer access / no symmetric memory on this box
+            sys.stderr.write("rank %d: peer score exchange unavailable (%s); using NCCL all_gather\n" % (rank, exc))
+            ok = 0
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            exchange, xmode = None, "nccl"
+        os.environ["MCD_EXCHANGE"] = xmode                         # what workload_config() reports
     in_flight = []
 
     def step(P_in, A_in, overlap=False):
