@@ -13,7 +13,7 @@ ROLES = [
     ("sample_tilemax_kernel", "K2 sample: per-column maxima of 1 tile in 32"),
     ("sample_select_kernel", "K2 sample: j-th largest tile maximum = start threshold"),
     ("topk_scan_kernel", None),
-    ("topk_finish_kernel", "K2 finish (sort survivors, emit indices)"),
+    ("topk_finish", "K2 finish (sort survivors, emit indices)"),
     ("wpmi_accum_kernel", "K3 gather + rank-weighted log-sum"),
     ("col_lse_partials_kernel", "K3b 256-neuron block partials (max, sum exp)"),
     ("lse_combine_kernel", "K3b combine partials -> logsumexp per concept"),
