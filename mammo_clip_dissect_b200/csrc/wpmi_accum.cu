@@ -77,9 +77,13 @@ wpmi_accum_kernel(const float *__restrict__ S, int64_t lds, int C, const int32_t
     // the gathered rows of S are re-read ~k*K/N (33 at c4) times: ask L2 to keep them (evict-last), measured
     // 1.15 -> 0.80 ms at c4
     const uint64_t keep = l2_policy_evict_last();
-    __shared__ __align__(16) uint32_t s_off[NPB][kAccumMaxK];   // BYTE offsets idx * lds * 4 (host: N * lds < 2^30)
-    __shared__ __align__(16) float s_p[kAccumMaxK];
-    __shared__ __align__(16) float s_c[SOFT && FUSED ? kAccumMaxK : 4];
+    // dynamic shared memory, sized to k (a few KB at k = 100, so a CTA also fits beside other resident kernels):
+    // BYTE offsets idx * lds * 4 per neuron (host: N * lds < 2^30), then the rank weights p and the FMA constants c
+    extern __shared__ __align__(16) unsigned char accum_smem[];
+    const int kpad = (k + 3) & ~3;
+    uint32_t *s_off = reinterpret_cast<uint32_t *>(accum_smem);          // [NPB][kpad]
+    float *s_p = reinterpret_cast<float *>(s_off + NPB * kpad);           // [kpad]
+    float *s_c = s_p + kpad;                                              // [kpad]
 
     const int tile = blockIdx.x / n_groups;
     const int group = blockIdx.x - tile * n_groups;
@@ -89,7 +93,7 @@ wpmi_accum_kernel(const float *__restrict__ S, int64_t lds, int C, const int32_t
     for (int n = 0; n < NPB; ++n) {
         const int64_t j = j0 + n;
         for (int r = tid; r < k; r += kAccumThreads)
-            s_off[n][r] = j < K ? uint32_t(idx[int64_t(r) * K + j]) * uint32_t(lds) * 4u : 0u;
+            s_off[n * kpad + r] = j < K ? uint32_t(idx[int64_t(r) * K + j]) * uint32_t(lds) * 4u : 0u;
     }
     bool p_ok = true;
     if (SOFT)
@@ -111,7 +115,7 @@ wpmi_accum_kernel(const float *__restrict__ S, int64_t lds, int C, const int32_t
     // a vector load may run past C only inside the row's padding (c0 + 4 <= lds is guaranteed by
     // the host when VEC); the scalar path loads exactly the valid columns
     const char *base = reinterpret_cast<const char *>(S + c0);
-    const uint32_t *my_off = s_off[n];
+    const uint32_t *my_off = s_off + n * kpad;
 
     float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
     int r = 0;
@@ -211,15 +215,16 @@ static int launch_accum(const float *S, int64_t lds, int C, const int32_t *idx, 
     const int mode = static_cast<int>(tunable(kAccumUnroll));
     const bool grouped = eps >= 1e-9f && eps <= 1.0f && mode != 1;
     const unsigned nb = static_cast<unsigned>(blocks);
+    const size_t sm = size_t(NPB + 2) * size_t((k + 3) & ~3) * 4;
     const int ng = static_cast<int>(n_groups);
     if (grouped && mode != 2)
-        wpmi_accum_kernel<TPN, 8, SOFT, VEC, true, true, true><<<nb, kAccumThreads, 0, st>>>(S, lds, C, idx, K, k, p, eps, L, ldl, ng);
+        wpmi_accum_kernel<TPN, 8, SOFT, VEC, true, true, true><<<nb, kAccumThreads, sm, st>>>(S, lds, C, idx, K, k, p, eps, L, ldl, ng);
     else if (grouped)
-        wpmi_accum_kernel<TPN, 8, SOFT, VEC, true, true, false><<<nb, kAccumThreads, 0, st>>>(S, lds, C, idx, K, k, p, eps, L, ldl, ng);
+        wpmi_accum_kernel<TPN, 8, SOFT, VEC, true, true, false><<<nb, kAccumThreads, sm, st>>>(S, lds, C, idx, K, k, p, eps, L, ldl, ng);
     else if (ftz)
-        wpmi_accum_kernel<TPN, 8, SOFT, VEC, true, false, false><<<nb, kAccumThreads, 0, st>>>(S, lds, C, idx, K, k, p, eps, L, ldl, ng);
+        wpmi_accum_kernel<TPN, 8, SOFT, VEC, true, false, false><<<nb, kAccumThreads, sm, st>>>(S, lds, C, idx, K, k, p, eps, L, ldl, ng);
     else
-        wpmi_accum_kernel<TPN, 8, SOFT, VEC, false, false, false><<<nb, kAccumThreads, 0, st>>>(S, lds, C, idx, K, k, p, eps, L, ldl, ng);
+        wpmi_accum_kernel<TPN, 8, SOFT, VEC, false, false, false><<<nb, kAccumThreads, sm, st>>>(S, lds, C, idx, K, k, p, eps, L, ldl, ng);
     return check_launch();
 }
 

@@ -325,6 +325,37 @@ def test_lse_blocks_are_sharding_invariant(sim):
     assert torch.allclose(orc.lse_block_partials(L.cpu())[:, 0], full.cpu()[:, 0])
 
 
+@pytest.mark.parametrize("K,C", [(512, 763), (300, 131), (256, 5)])
+def test_finalize_broadcast_kernel_matches_finalize(sim, K, C):
+    """mcd_pmi_finalize_bcast_f32 (the fused finalize + score all-gather) on one GPU: every destination matrix
+    receives exactly mcd_pmi_finalize_f32's bits in rows [row_offset, row_offset + K), and nothing else is touched."""
+    from mammo_clip_dissect_b200 import _lib
+    L = (-400 - 60 * torch.rand(K, C, generator=gen(15))).to(DEV)
+    other = (-400 - 60 * torch.rand(256, C, generator=gen(16))).to(DEV)         # a second rank's neurons
+    parts = torch.cat([sim.lse_partials(other), sim.lse_partials(L)])
+    K_total, row0 = 256 + K, 256
+    want, pd = sim.pmi_finalize(L.clone(), parts, K_total, 0.7)
+    dests = [torch.full((K_total, C), 7.0, device=DEV) for _ in range(3)]
+    pd2 = sim.pmi_finalize_bcast(L, parts, K_total, 0.7, [d.data_ptr() for d in dests], row0)
+    assert torch.equal(pd, pd2)
+    for d in dests:
+        assert torch.equal(d[row0:], want) and bool((d[:row0] == 7.0).all())
+    # argument validation: slice outside the destination, too many destinations, misaligned slice
+    lib = _lib.lib()
+    import ctypes
+    arr = (ctypes.c_void_p * 1)(dests[0].data_ptr())
+    pdp, st = pd2.data_ptr(), torch.cuda.current_stream().cuda_stream
+    assert lib.mcd_pmi_finalize_bcast_f32(L.data_ptr(), K, C, parts.data_ptr(), parts.shape[0], K_total, 0.7, pdp, arr, 1,
+                                          row0 + 1, st) == -1
+    many = (ctypes.c_void_p * 17)(*[dests[0].data_ptr()] * 17)
+    assert lib.mcd_pmi_finalize_bcast_f32(L.data_ptr(), K, C, parts.data_ptr(), parts.shape[0], K_total, 0.7, pdp, many,
+                                          17, row0, st) == -2
+    if C % 4:
+        odd = (ctypes.c_void_p * 1)(dests[0].data_ptr())
+        assert lib.mcd_pmi_finalize_bcast_f32(L.data_ptr(), K - 1, C, parts.data_ptr(), parts.shape[0], K_total, 0.7, pdp,
+                                              odd, 1, row0 + 1, st) == -2
+
+
 # ------------------------------------------------------------------------------------------------
 # K1 similarity matrix, K4 hook
 # ------------------------------------------------------------------------------------------------
