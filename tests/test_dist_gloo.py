@@ -28,6 +28,23 @@ class OracleBackend:
         return L - lam * prob_d
 
 
+class HostExchange:
+    """Stands in for PeerScoreExchange (whose buffers are CUDA symmetric memory) to cover the wiring of the exchange
+    branch of pmi_scores_sharded: same attributes, same call, the push replaced by a gloo all_gather."""
+
+    class _Sim:
+        pass
+
+    def __init__(self, sizes, C):
+        self.sizes, self.C, self.calls = [int(x) for x in sizes], int(C), 0
+
+    def exchange(self, L, partials_all, lam, sim, wait=True):
+        self.calls += 1
+        local = OracleBackend().finalize(L, partials_all, sum(self.sizes), lam)
+        full = mdist._all_gather_var(local, self.sizes, None)
+        return full if wait else mdist.GatheredScores(full, None)
+
+
 def _inputs(K):
     g = torch.Generator().manual_seed(3)
     return torch.randn(300, 41, generator=g) * 0.1, torch.randn(300, K, generator=g)
@@ -52,6 +69,17 @@ def _worker(rank, world, port, K, q):
         full = mdist.soft_wpmi_sharded(P, shard, sizes, top_k=20, backend=OracleBackend())
         local = mdist.soft_wpmi_sharded(P, shard, sizes, top_k=20, backend=OracleBackend(), gather_scores=False)
         w = mdist.wpmi_sharded(P, shard, sizes, top_k=20, backend=OracleBackend())
+        be = OracleBackend()
+        be.sim = None
+        ex = HostExchange(sizes, P.shape[1])
+        via_ex = mdist.soft_wpmi_sharded(P, shard, sizes, top_k=20, backend=be, exchange=ex)
+        handle = mdist.soft_wpmi_sharded(P, shard, sizes, top_k=20, backend=be, exchange=ex, wait=False)
+        assert ex.calls == 2 and torch.equal(via_ex, full) and torch.equal(handle.wait(), full)
+        try:
+            mdist.soft_wpmi_sharded(P, shard, sizes, top_k=20, backend=be, exchange=HostExchange([1] * world, 41))
+            raise AssertionError("an exchange built for other shard sizes must be refused")
+        except RuntimeError:
+            pass
         q.put((rank, full.numpy(), local.numpy(), w.numpy(), b))      # numpy: no shared-memory handles to outlive the child
     finally:
         dist.destroy_process_group()
