@@ -58,9 +58,9 @@ int mcd_device_check(void) {
 }
 
 int mcd_set_tunable(const char *name, int64_t value) {
-    static const char *names[] = {"topk_splits", "accum_tile", "topk_variant", "accum_unroll", "topk_cols", "topk_stages", "topk_occ", "gemm_variant", "topk_pre"};
+    static const char *names[] = {"topk_splits", "accum_tile", "topk_variant", "accum_unroll", "topk_cols", "topk_stages", "topk_occ", "gemm_variant", "topk_pre", "topk_small"};
     if (!name) return MCD_ERR_INVALID_ARGUMENT;
-    for (int i = 0; i < 9; ++i)
+    for (int i = 0; i < 10; ++i)
         if (std::strcmp(name, names[i]) == 0) {
             mcd::g_tunables[i].store(value, std::memory_order_relaxed);
             return MCD_OK;

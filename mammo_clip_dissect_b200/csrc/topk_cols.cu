@@ -598,6 +598,146 @@ topk_finish_reg_kernel(const unsigned long long *__restrict__ cand, int M, int k
     }
 }
 
+// ---- short columns: exact radix select -----------------------------------------------------------------------------
+// With N up to a few thousand rows (the reference's real probe sets: 2 000 - 10 000 images, 24 - 768 neurons per layer)
+// the streaming scan is all start-up: a warp spends its time filling and refilling kept sets, one L2-latency-bound
+// replacement after the other (0.3 - 0.5 ms for 16 - 30 MB of input).  Such a matrix is L2-resident, so reading it a
+// few times is cheap: a CTA of 32 warps takes 32 adjacent columns (lane = column, coalesced 128-byte row segments),
+// the warps split the rows, and the k-th largest ordered key of every column is found by four 8-bit radix passes over
+// per-column histograms in shared memory (lane-private banks: conflict-free shared atomics).  A fifth pass counts the
+// elements equal to the k-th key per row slice -- the stated order takes the lowest image indices among equal values,
+// so slice w may take min(its ties, what is still needed) -- and a sixth writes the k selected (key, ~row) words to
+// the candidate array that the finish kernels sort.  Any base pointer / pitch (plain 4-byte loads).
+constexpr int kSmallWarps = 32;
+constexpr int kSmallMaxRows = 16384;
+constexpr int64_t kSmallMaxBytes = int64_t(64) << 20;      // L2-resident: the six passes re-read it from L2
+
+struct SmallSmem {
+    uint32_t hist[256][kUnitCols];
+    uint32_t ties[kSmallWarps][kUnitCols];      // ties in slice w, then (in place) how many of them slice w takes
+    uint32_t prefix[kUnitCols], need[kUnitCols], outpos[kUnitCols];
+};
+
+__global__ void __launch_bounds__(kSmallWarps * 32)
+topk_small_kernel(const float *__restrict__ A, int64_t lda, int N, int64_t K, int k,
+                  unsigned long long *__restrict__ cand) {
+    __shared__ SmallSmem s;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t col = int64_t(blockIdx.x) * kUnitCols + lane;
+    const bool active = col < K;
+    const int rps = (N + kSmallWarps - 1) / kSmallWarps;
+    const int r0 = min(N, warp * rps), r1 = min(N, r0 + rps);
+    const float *src = A + (active ? col : 0);
+    if (warp == 0) {
+        s.prefix[lane] = 0u;
+        s.need[lane] = static_cast<uint32_t>(k);
+        s.outpos[lane] = 0u;
+    }
+    constexpr int kU = 16;      // independent loads in flight per lane (the loop is L2-latency bound)
+#pragma unroll 1
+    for (int pass = 0; pass < 4; ++pass) {
+        const int shift = 24 - 8 * pass;
+        for (int i = threadIdx.x; i < 256 * kUnitCols; i += kSmallWarps * 32) (&s.hist[0][0])[i] = 0u;
+        __syncthreads();
+        const uint32_t pre = s.prefix[lane];
+        const uint32_t himask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+        if (active) {
+            int r = r0;
+            for (; r + kU <= r1; r += kU) {
+                float v[kU];
+#pragma unroll
+                for (int u = 0; u < kU; ++u) v[u] = __ldg(src + int64_t(r + u) * lda);
+#pragma unroll
+                for (int u = 0; u < kU; ++u) {
+                    const uint32_t key = ordered_key(v[u]);
+                    if ((key & himask) == pre) atomicAdd(&s.hist[(key >> shift) & 255u][lane], 1u);
+                }
+            }
+            for (; r < r1; ++r) {
+                const uint32_t key = ordered_key(__ldg(src + int64_t(r) * lda));
+                if ((key & himask) == pre) atomicAdd(&s.hist[(key >> shift) & 255u][lane], 1u);
+            }
+        }
+        __syncthreads();
+        if (warp == 0 && active) {
+            // walk the bins from the largest digit down to the one that holds the `need`-th element (8 bins per step
+            // so that the shared-memory loads overlap)
+            uint32_t need = s.need[lane], acc = 0u;
+            int b = 0;
+            bool found = false;
+            for (int hi8 = 255; hi8 >= 0 && !found; hi8 -= 8) {
+                uint32_t h[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) h[j] = s.hist[hi8 - j][lane];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (!found) {
+                        if (acc + h[j] >= need) {
+                            found = true;
+                            b = hi8 - j;
+                        } else {
+                            acc += h[j];
+                        }
+                    }
+                }
+            }
+            s.prefix[lane] = pre | (uint32_t(b) << shift);
+            s.need[lane] = need - acc;          // still to take among the elements that share the new prefix
+        }
+        __syncthreads();
+    }
+    const uint32_t T = s.prefix[lane];          // the column's k-th largest key
+    // ties: how many elements equal to T lie in each row slice
+    uint32_t t = 0u;
+    if (active) {
+        int r = r0;
+        for (; r + kU <= r1; r += kU) {
+            float v[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) v[u] = __ldg(src + int64_t(r + u) * lda);
+#pragma unroll
+            for (int u = 0; u < kU; ++u) t += ordered_key(v[u]) == T;
+        }
+        for (; r < r1; ++r) t += ordered_key(__ldg(src + int64_t(r) * lda)) == T;
+    }
+    s.ties[warp][lane] = t;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t left = s.need[lane];           // lowest image indices first: slices in order
+        for (int w = 0; w < kSmallWarps; ++w) {
+            const uint32_t q = min(s.ties[w][lane], left);
+            s.ties[w][lane] = q;
+            left -= q;
+        }
+    }
+    __syncthreads();
+    if (active) {
+        uint32_t quota = s.ties[warp][lane];
+        unsigned long long *dst = cand + col;
+        // in row order: the first `quota` ties of the slice are taken
+        auto offer = [&](uint32_t key, int r) {
+            bool take = key > T;
+            if (key == T && quota > 0u) {
+                take = true;
+                --quota;
+            }
+            if (take) {
+                const uint32_t pos = atomicAdd(&s.outpos[lane], 1u);
+                dst[int64_t(pos) * K] = pack_key(key, ~static_cast<uint32_t>(r));
+            }
+        };
+        int r = r0;
+        for (; r + kU <= r1; r += kU) {
+            float v[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u) v[u] = __ldg(src + int64_t(r + u) * lda);
+#pragma unroll
+            for (int u = 0; u < kU; ++u) offer(ordered_key(v[u]), r + u);
+        }
+        for (; r < r1; ++r) offer(ordered_key(__ldg(src + int64_t(r) * lda)), r);
+    }
+}
+
 // ---- host side ----------------------------------------------------------------------------------
 constexpr size_t kSmemPerSM = 228 * 1024, kSmemCtaReserve = 1024;
 
@@ -750,6 +890,27 @@ static int launch_scan(dim3 grid, const TopkPlan &p, const CUtensorMap &map, con
     }
 }
 
+static int launch_finish(const TopkPlan &p, const unsigned long long *cand, int k, int64_t K, const float *A, int64_t lda,
+                         int64_t *idx64_out, int32_t *idx32_out, float *vals_out, cudaStream_t st) {
+    if (p.mpad <= 256 && tunable(kTopkVariant) != 2) {
+        const unsigned fgrid = static_cast<unsigned>(ceil_div<int64_t>(K, kFinishRegWarps));
+        if (p.mpad <= 128)
+            topk_finish_reg_kernel<4><<<fgrid, kFinishRegWarps * 32, 0, st>>>(cand, p.splits * k, k, K, A, lda,
+                                                                              idx64_out, idx32_out, vals_out);
+        else
+            topk_finish_reg_kernel<8><<<fgrid, kFinishRegWarps * 32, 0, st>>>(cand, p.splits * k, k, K, A, lda,
+                                                                              idx64_out, idx32_out, vals_out);
+        return check_launch();
+    }
+    const size_t fsmem = size_t(kFinishWarps) * p.mpad * sizeof(unsigned long long);
+    if (cudaFuncSetAttribute(topk_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fsmem)) != cudaSuccess)
+        return MCD_ERR_CUDA;
+    const unsigned fgrid = static_cast<unsigned>(ceil_div<int64_t>(K, kFinishWarps));
+    topk_finish_kernel<<<fgrid, kFinishWarps * 32, fsmem, st>>>(cand, p.splits * k, p.mpad, k, K, A, lda,
+                                                                idx64_out, idx32_out, vals_out);
+    return check_launch();
+}
+
 }  // namespace mcd
 
 extern "C" size_t mcd_topk_cols_workspace_bytes(int64_t N, int64_t K, int64_t k) {
@@ -771,6 +932,18 @@ extern "C" int mcd_topk_cols_f32(const float *A, int64_t lda, int64_t N, int64_t
     auto *cand = static_cast<unsigned long long *>(workspace);
     auto *kept = reinterpret_cast<uint32_t *>(static_cast<char *>(workspace) + p.cand_bytes);
 
+    // short columns of an L2-resident matrix: exact radix select (tunable topk_small: 1 = never, else automatic)
+    if (N <= kSmallMaxRows && N * K * 4 <= kSmallMaxBytes && tunable(kTopkSmall) != 1 && tunable(kTopkSplits) <= 0 &&
+        tunable(kTopkCols) <= 0 && tunable(kTopkVariant) != 1) {
+        topk_small_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(K, kUnitCols)), kSmallWarps * 32, 0, st>>>(
+            A, lda, int(N), K, int(k), cand);
+        int rc0 = check_launch();
+        if (rc0 != MCD_OK) return rc0;
+        p.splits = 1;
+        p.mpad = 1;
+        while (p.mpad < int(k)) p.mpad <<= 1;
+        return launch_finish(p, cand, int(k), K, A, lda, idx64_out, idx32_out, vals_out, st);
+    }
     // feed: TMA tensor tiles need a 16-byte aligned base and row pitch; anything else takes element copies
     const bool aligned = (lda % 4 == 0) && (reinterpret_cast<uintptr_t>(A) % 16 == 0);
     int feed = aligned ? kFeedTensorTile : kFeedElements;
@@ -811,21 +984,5 @@ extern "C" int mcd_topk_cols_f32(const float *A, int64_t lda, int64_t N, int64_t
     rc = launch_scan(grid, p, map, main_args, st);
     if (rc != MCD_OK) return rc;
 
-    if (p.mpad <= 256 && tunable(kTopkVariant) != 2) {
-        const unsigned fgrid = static_cast<unsigned>(ceil_div<int64_t>(K, kFinishRegWarps));
-        if (p.mpad <= 128)
-            topk_finish_reg_kernel<4><<<fgrid, kFinishRegWarps * 32, 0, st>>>(cand, p.splits * int(k), int(k), K, A, lda,
-                                                                              idx64_out, idx32_out, vals_out);
-        else
-            topk_finish_reg_kernel<8><<<fgrid, kFinishRegWarps * 32, 0, st>>>(cand, p.splits * int(k), int(k), K, A, lda,
-                                                                              idx64_out, idx32_out, vals_out);
-        return check_launch();
-    }
-    const size_t fsmem = size_t(kFinishWarps) * p.mpad * sizeof(unsigned long long);
-    if (cudaFuncSetAttribute(topk_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fsmem)) != cudaSuccess)
-        return MCD_ERR_CUDA;
-    const unsigned fgrid = static_cast<unsigned>(ceil_div<int64_t>(K, kFinishWarps));
-    topk_finish_kernel<<<fgrid, kFinishWarps * 32, fsmem, st>>>(cand, p.splits * int(k), p.mpad, int(k), K, A, lda,
-                                                                idx64_out, idx32_out, vals_out);
-    return check_launch();
+    return launch_finish(p, cand, int(k), K, A, lda, idx64_out, idx32_out, vals_out, st);
 }

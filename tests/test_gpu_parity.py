@@ -31,6 +31,22 @@ def gen(seed):
     return torch.Generator().manual_seed(seed)
 
 
+class topk_path:
+    """K2 has two implementations: the radix select for short columns (N <= 16384, "auto") and the streaming scan
+    ("stream": tunable topk_small = 1 switches the short-column kernel off)."""
+
+    def __init__(self, path):
+        self.path = path
+
+    def __enter__(self):
+        from mammo_clip_dissect_b200 import _lib
+        _lib.set_tunable("topk_small", 1 if self.path == "stream" else 0)
+
+    def __exit__(self, *exc):
+        from mammo_clip_dissect_b200 import _lib
+        _lib.set_tunable("topk_small", 0)
+
+
 def check_scores(out, L, ref_out, ref_L, f64_out=None, label=""):
     out, L = out.cpu(), L.cpu()
     scale = ref_L.abs().max().item()
@@ -52,10 +68,13 @@ def check_scores(out, L, ref_out, ref_L, f64_out=None, label=""):
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("N,K,k", [(2000, 256, 100), (777, 33, 28), (300, 7, 1), (130, 33, 130), (5000, 40, 10),
                                    (1024, 64, 48), (1500, 129, 112), (3000, 68, 200), (4000, 36, 300),
-                                   (2048, 12, 496), (64, 4, 64), (1024, 70, 512), (700, 33, 129), (900, 40, 257)])
-def test_topk_tie_free(sim, N, K, k):
+                                   (2048, 12, 496), (64, 4, 64), (1024, 70, 512), (700, 33, 129), (900, 40, 257),
+                                   (16384, 40, 100), (16385, 33, 100), (31, 5, 31), (10000, 768, 100)])
+@pytest.mark.parametrize("path", ["auto", "stream"])
+def test_topk_tie_free(sim, N, K, k, path):
     A = torch.randn(N, K, generator=gen(N + K + k))
-    vals, idx = sim.topk_cols(A, k, device=DEV, want_values=True)
+    with topk_path(path):
+        vals, idx = sim.topk_cols(A, k, device=DEV, want_values=True)
     rv, ri = orc.topk_cols(A, k)
     assert torch.equal(idx.cpu(), ri)
     assert torch.equal(vals.cpu(), rv)
@@ -63,7 +82,8 @@ def test_topk_tie_free(sim, N, K, k):
 
 
 @pytest.mark.parametrize("kind", ["round1", "relu", "const", "nan_inf", "signed_zero", "sorted_up", "sorted_down"])
-def test_topk_ties_and_specials(sim, kind):
+@pytest.mark.parametrize("path", ["auto", "stream"])
+def test_topk_ties_and_specials(sim, kind, path):
     N, K, k = 3000, 96, 100
     A = torch.randn(N, K, generator=gen(5))
     if kind == "round1":
@@ -86,7 +106,8 @@ def test_topk_ties_and_specials(sim, kind):
         A = torch.sort(A, dim=0).values            # every element beats the running threshold
     elif kind == "sorted_down":
         A = torch.sort(A, dim=0, descending=True).values
-    idx = sim.topk_cols(A, k, device=DEV)
+    with topk_path(path):
+        idx = sim.topk_cols(A, k, device=DEV)
     assert torch.equal(idx.cpu(), orc.topk_cols(A, k)[1]), kind
 
 
