@@ -95,6 +95,19 @@ int mcd_pmi_finalize_f32(const float *L, int64_t ldl, int64_t K, int64_t C,
                          float lam, float *prob_d_out /* [C] scratch+result */,
                          float *out, int64_t ldo, mcd_stream_t stream);
 
+/* ---- K3b for several layers stacked along the neuron axis of one [sum K_l, C] matrix (SURVEY.md 8 f1:
+ *      the 12-39 layers of a real job in one pass of every kernel).  Same arithmetic, block by
+ *      block, as the single-layer functions, so each layer's rows get exactly the bits a separate
+ *      call would produce.  Device tables: block_tab [n_blocks][3] = (first row, rows <= 256,
+ *      segment) with every layer's blocks starting at its first row; seg_tab [n_seg][2] = (first
+ *      block, blocks); seg_log_count [n_seg] = log(K_l) in fp64.  prob_d_out [n_seg][C]. */
+int mcd_col_lse_partials_seg_f32(const float *L, int64_t ldl, int64_t C, const int32_t *block_tab,
+                                 int64_t n_blocks, float *partials, mcd_stream_t stream);
+int mcd_pmi_finalize_seg_f32(const float *L, int64_t ldl, int64_t C, const float *partials,
+                             const int32_t *block_tab, int64_t n_blocks, const int32_t *seg_tab,
+                             const double *seg_log_count, int64_t n_seg, float lam,
+                             float *prob_d_out, float *out, int64_t ldo, mcd_stream_t stream);
+
 /* ---- K3b fused with the all-gather of the scores (neuron-sharded multi-GPU call):
  *      same arithmetic as mcd_pmi_finalize_f32 on this rank's contiguous [K, C] log-sums, but the
  *      finalized slice is stored into rows [row_offset, row_offset + K) of EVERY destination

@@ -17,12 +17,14 @@ constexpr int kLseThreads = 128;
 // thread per concept, one pass over the block's 256 rows with an online (max, sum) pair: the running sum is
 // rescaled whenever the maximum rises (the rescale factor is exactly 1 otherwise), loads 4 rows ahead
 __global__ void __launch_bounds__(kLseThreads)
-col_lse_partials_kernel(const float *__restrict__ L, int64_t ldl, int64_t K, int C, float *__restrict__ partials) {
+col_lse_partials_kernel(const float *__restrict__ L, int64_t ldl, int64_t K, int C, float *__restrict__ partials,
+                        const int32_t *__restrict__ block_tab) {
     const int c = blockIdx.x * kLseThreads + threadIdx.x;
     const int64_t b = blockIdx.y;
     if (c >= C) return;
-    const int64_t j0 = b * MCD_LSE_BLOCK;
-    const int64_t j1 = min(K, j0 + MCD_LSE_BLOCK);
+    // one call: blocks of 256 neurons from row 0; several layers in one matrix: the table lists every block's rows
+    const int64_t j0 = block_tab ? block_tab[b * 3 + 0] : b * MCD_LSE_BLOCK;
+    const int64_t j1 = block_tab ? j0 + block_tab[b * 3 + 1] : min(K, j0 + MCD_LSE_BLOCK);
     const float *col = L + c;
     float m = -INFINITY, s = 0.f;
     int64_t j = j0;
@@ -56,11 +58,17 @@ col_lse_partials_kernel(const float *__restrict__ L, int64_t ldl, int64_t K, int
 // result is still independent of how the neurons were sharded.
 __global__ void __launch_bounds__(256)
 lse_combine_kernel(const float *__restrict__ partials, int64_t n_blocks, int C, double log_count,
-                   float *__restrict__ prob_d) {
+                   float *__restrict__ prob_d, const int32_t *__restrict__ seg_tab, const double *__restrict__ seg_log) {
     __shared__ float s_max[8][33];
     __shared__ double s_sum[8][33];
     const int cx = threadIdx.x & 31, sl = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cx;
+    if (seg_tab) {       // segment (layer) blockIdx.y: its own run of blocks, its own neuron count, its own output row
+        partials += int64_t(seg_tab[blockIdx.y * 2 + 0]) * 2 * C;
+        n_blocks = seg_tab[blockIdx.y * 2 + 1];
+        log_count = seg_log[blockIdx.y];
+        prob_d += int64_t(blockIdx.y) * C;
+    }
     float big = -INFINITY;
     if (c < C)
         for (int64_t b = sl; b < n_blocks; b += 8) big = fmaxf(big, partials[(b * 2) * C + c]);
@@ -93,6 +101,17 @@ pmi_finalize_kernel(const float *__restrict__ L, int64_t ldl, int64_t K, int C, 
     if (c >= C) return;
     const float shift = __fmul_rn(lam, prob_d[c]);
     for (int64_t j = blockIdx.y; j < K; j += gridDim.y) out[j * ldo + c] = __fsub_rn(L[j * ldl + c], shift);
+}
+
+// several layers in one matrix: CTA (x, b) finalizes the rows of block b with its segment's log p(d)
+__global__ void __launch_bounds__(256)
+pmi_finalize_seg_kernel(const float *__restrict__ L, int64_t ldl, int C, const float *__restrict__ prob_d /*[n_seg][C]*/,
+                        const int32_t *__restrict__ block_tab, float lam, float *__restrict__ out, int64_t ldo) {
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= C) return;
+    const int64_t j0 = block_tab[blockIdx.y * 3 + 0], j1 = j0 + block_tab[blockIdx.y * 3 + 1];
+    const float shift = __fmul_rn(lam, prob_d[int64_t(block_tab[blockIdx.y * 3 + 2]) * C + c]);
+    for (int64_t j = j0; j < j1; ++j) out[j * ldo + c] = __fsub_rn(L[j * ldl + c], shift);
 }
 
 // K3b fused with the score all-gather: the finalized slice is stored straight into the [K_total, C] score matrix
@@ -142,7 +161,7 @@ extern "C" int mcd_col_lse_partials_f32(const float *L, int64_t ldl, int64_t K, 
     const int64_t nb = ceil_div<int64_t>(K, MCD_LSE_BLOCK);
     if (nb > 65535) return MCD_ERR_UNSUPPORTED;
     dim3 grid(static_cast<unsigned>(ceil_div<int64_t>(C, kLseThreads)), static_cast<unsigned>(nb));
-    col_lse_partials_kernel<<<grid, kLseThreads, 0, static_cast<cudaStream_t>(stream)>>>(L, ldl, K, int(C), partials);
+    col_lse_partials_kernel<<<grid, kLseThreads, 0, static_cast<cudaStream_t>(stream)>>>(L, ldl, K, int(C), partials, nullptr);
     return check_launch();
 }
 
@@ -155,7 +174,7 @@ extern "C" int mcd_pmi_finalize_f32(const float *L, int64_t ldl, int64_t K, int6
         return MCD_ERR_INVALID_ARGUMENT;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     lse_combine_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(C, 32)), 256, 0, st>>>(
-        partials_all, n_blocks_total, int(C), log(double(K_total)), prob_d_out);
+        partials_all, n_blocks_total, int(C), log(double(K_total)), prob_d_out, nullptr, nullptr);
     int rc = check_launch();
     if (rc != MCD_OK) return rc;
     int64_t rows = int64_t(num_sms()) * 16 / ceil_div<int64_t>(C, 256);
@@ -186,7 +205,7 @@ extern "C" int mcd_pmi_finalize_bcast_f32(const float *L, int64_t K, int64_t C, 
     if (reinterpret_cast<uintptr_t>(L) % 16 != 0) return MCD_ERR_UNSUPPORTED;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     lse_combine_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(C, 32)), 256, 0, st>>>(
-        partials_all, n_blocks_total, int(C), log(double(K_total)), prob_d_out);
+        partials_all, n_blocks_total, int(C), log(double(K_total)), prob_d_out, nullptr, nullptr);
     int rc = check_launch();
     if (rc != MCD_OK) return rc;
     const int64_t total = K * C;
@@ -195,5 +214,35 @@ extern "C" int mcd_pmi_finalize_bcast_f32(const float *L, int64_t K, int64_t C, 
     if (blocks > cap) blocks = cap;
     pmi_finalize_bcast_kernel<<<static_cast<unsigned>(blocks), 256, 0, st>>>(L, total, int(C), prob_d_out, lam, dst,
                                                                              n_dest);
+    return check_launch();
+}
+
+// ---- several layers (segments of the neuron axis) in one matrix: SURVEY.md 8 f1 -------------------------------------
+extern "C" int mcd_col_lse_partials_seg_f32(const float *L, int64_t ldl, int64_t C, const int32_t *block_tab,
+                                            int64_t n_blocks, float *partials, mcd_stream_t stream) {
+    using namespace mcd;
+    if (!L || !partials || !block_tab || C < 1 || ldl < C || C > (1 << 24) || n_blocks < 1) return MCD_ERR_INVALID_ARGUMENT;
+    if (n_blocks > 65535) return MCD_ERR_UNSUPPORTED;
+    dim3 grid(static_cast<unsigned>(ceil_div<int64_t>(C, kLseThreads)), static_cast<unsigned>(n_blocks));
+    col_lse_partials_kernel<<<grid, kLseThreads, 0, static_cast<cudaStream_t>(stream)>>>(L, ldl, 0, int(C), partials, block_tab);
+    return check_launch();
+}
+
+extern "C" int mcd_pmi_finalize_seg_f32(const float *L, int64_t ldl, int64_t C, const float *partials,
+                                        const int32_t *block_tab, int64_t n_blocks, const int32_t *seg_tab,
+                                        const double *seg_log_count, int64_t n_seg, float lam, float *prob_d_out,
+                                        float *out, int64_t ldo, mcd_stream_t stream) {
+    using namespace mcd;
+    if (!L || !partials || !block_tab || !seg_tab || !seg_log_count || !prob_d_out || !out || C < 1 || ldl < C || ldo < C ||
+        C > (1 << 24) || n_blocks < 1 || n_seg < 1)
+        return MCD_ERR_INVALID_ARGUMENT;
+    if (n_blocks > 65535 || n_seg > 65535) return MCD_ERR_UNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 cgrid(static_cast<unsigned>(ceil_div<int64_t>(C, 32)), static_cast<unsigned>(n_seg));
+    lse_combine_kernel<<<cgrid, 256, 0, st>>>(partials, 0, int(C), 0.0, prob_d_out, seg_tab, seg_log_count);
+    int rc = check_launch();
+    if (rc != MCD_OK) return rc;
+    dim3 fgrid(static_cast<unsigned>(ceil_div<int64_t>(C, 256)), static_cast<unsigned>(n_blocks));
+    pmi_finalize_seg_kernel<<<fgrid, 256, 0, st>>>(L, ldl, int(C), prob_d_out, block_tab, lam, out, ldo);
     return check_launch();
 }

@@ -610,7 +610,7 @@ topk_finish_reg_kernel(const unsigned long long *__restrict__ cand, int M, int k
 // the candidate array that the finish kernels sort.  Any base pointer / pitch (plain 4-byte loads).
 constexpr int kSmallWarps = 32;
 constexpr int kSmallMaxRows = 16384;
-constexpr int64_t kSmallMaxBytes = int64_t(64) << 20;      // L2-resident: the six passes re-read it from L2
+constexpr int64_t kSmallMaxBytes = int64_t(192) << 20;     // (mostly) L2-resident: the six passes re-read it
 
 struct SmallSmem {
     uint32_t hist[256][kUnitCols];
@@ -810,14 +810,16 @@ static bool make_plan(int64_t N, int64_t K, int64_t k64, TopkPlan *p) {
     p->pre_k = 0;
     p->pre_rows = 0;
     p->pre_bytes = 0;
-    if (tunable(kTopkPre) != 2 && N >= 16384 && k <= 256) {
-        static const int kStrides[] = {32, 16, 8};                  // sample one 32-row tile out of every `stride`
+    if (tunable(kTopkPre) != 2 && N >= 8192 && k <= 256) {
+        // sample one 32-row tile out of every `stride`; the estimate "j * stride elements above the threshold" needs
+        // j well below the number of sampled tiles (correctness does not: the fill counts + exact redo guard it)
+        static const int kStrides[] = {32, 16, 8, 4};
         for (int stride : kStrides) {
             const double lam = double(k) / stride;
             int pk = static_cast<int>(lam + 6.0 * sqrt(lam) + 4.0 + 0.999);
             if (pk < 8) pk = 8;
             const int64_t ntile = N / (int64_t(kTileRows) * stride);
-            if (pk <= kSelectMaxJ && ntile >= 2 * pk) {
+            if (pk <= kSelectMaxJ && 4 * ntile >= 5 * pk) {
                 p->pre_stride = stride;
                 p->pre_k = pk;
                 p->pre_rows = ntile * kTileRows;
@@ -933,7 +935,7 @@ extern "C" int mcd_topk_cols_f32(const float *A, int64_t lda, int64_t N, int64_t
     auto *kept = reinterpret_cast<uint32_t *>(static_cast<char *>(workspace) + p.cand_bytes);
 
     // short columns of an L2-resident matrix: exact radix select (tunable topk_small: 1 = never, else automatic)
-    if (N <= kSmallMaxRows && N * K * 4 <= kSmallMaxBytes && tunable(kTopkSmall) != 1 && tunable(kTopkSplits) <= 0 &&
+    if (N <= kSmallMaxRows && (N <= 4096 || N * K * 4 <= kSmallMaxBytes) && tunable(kTopkSmall) != 1 && tunable(kTopkSplits) <= 0 &&
         tunable(kTopkCols) <= 0 && tunable(kTopkVariant) != 1) {
         topk_small_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(K, kUnitCols)), kSmallWarps * 32, 0, st>>>(
             A, lda, int(N), K, int(k), cand);

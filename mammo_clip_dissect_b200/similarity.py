@@ -28,7 +28,7 @@ import torch
 from . import _lib
 
 __all__ = ["soft_wpmi", "wpmi", "cos_similarity", "cos_similarity_cubed", "cos_similarity_cubed_single", "rank_reorder",
-           "topk_cols", "concept_probabilities", "pmi_scores"]
+           "soft_wpmi_layers", "wpmi_layers", "topk_cols", "concept_probabilities", "pmi_scores"]
 
 _S_ALIGN = 32  # leading dimension of the probability matrix: rows start on 128-byte boundaries
 
@@ -172,6 +172,21 @@ def _reference_ramp(top_k, p_start, p_end):
     return (p_start - steps).to(torch.float32).contiguous()
 
 
+_ramp_cache = {}
+
+
+def _device_ramp(ramp, top_k, p_start, p_end, dev):
+    """The ramp on the device, cached per (top_k, p_start, p_end, device): a job scores dozens of layers with the same
+    arguments, and a pageable host-to-device copy per call would be a host synchronisation per call."""
+    key = (int(top_k), float(p_start), float(p_end), str(dev))
+    t = _ramp_cache.get(key)
+    if t is None:
+        if len(_ramp_cache) > 64:
+            _ramp_cache.clear()
+        t = _ramp_cache[key] = ramp.to(dev)
+    return t
+
+
 def log_sums(S, idx32, weights, min_prob, out=None):
     """K3: L[j,c] = sum_r log(1 + w_r (S[idx[r,j],c]-1) + eps)  (weights=None: sum_r log(S+eps))."""
     dev = S.device
@@ -235,7 +250,7 @@ def pmi_scores(clip_feats, target_feats, top_k, a, lam, device, min_prob, ramp, 
             S = concept_probabilities(clip_feats, a, dev)
         with _Stage("topk_cols"):
             idx32 = _topk_int32(A, top_k, dev)
-        weights = ramp.to(dev) if ramp is not None else None
+        weights = ramp.to(dev) if ramp is not None else None      # no-op for a cached device ramp
         with _Stage("wpmi_accum"):
             L = log_sums(S, idx32, weights, min_prob)
         if return_parts:
@@ -248,14 +263,95 @@ def pmi_scores(clip_feats, target_feats, top_k, a, lam, device, min_prob, ramp, 
     return out
 
 
+_seg_cache = {}
+
+
+def _segment_tables(Ks, dev):
+    """Device tables for the segmented K3b kernels (cached per layer-width tuple): every layer's 256-neuron LSE
+    blocks start at the layer's first row, exactly as in a separate call."""
+    key = (tuple(int(k) for k in Ks), str(dev))
+    hit = _seg_cache.get(key)
+    if hit is not None:
+        return hit
+    import math
+    blocks, segs, logs, row = [], [], [], 0
+    for s_id, K in enumerate(key[0]):
+        first = len(blocks)
+        for j0 in range(0, K, _lib.LSE_BLOCK):
+            blocks.append((row + j0, min(_lib.LSE_BLOCK, K - j0), s_id))
+        segs.append((first, len(blocks) - first))
+        logs.append(math.log(float(K)))          # libm log of a double, like the single-layer entry point
+        row += K
+    out = (torch.tensor(blocks, dtype=torch.int32).to(dev), torch.tensor(segs, dtype=torch.int32).to(dev),
+           torch.tensor(logs, dtype=torch.float64).to(dev), len(blocks))
+    if len(_seg_cache) > 16:
+        _seg_cache.clear()
+    _seg_cache[key] = out
+    return out
+
+
+def pmi_scores_layers(clip_feats, target_feats_list, top_k, a, lam, device, min_prob, ramp):
+    """[pmi_scores(clip_feats, t, ...) for t in target_feats_list], bit for bit, with ONE pass of every kernel over
+    the layers stacked along the neuron axis: one softmax, one column top-k and one
+    gather/log-sum over [N, sum K_l], and log p(d) per layer from segment-wise 256-neuron blocks."""
+    dev = _cuda_device(device)
+    if len(target_feats_list) == 0:
+        return []
+    with torch.no_grad(), torch.cuda.device(dev):
+        mats = [_as_f32_matrix(t, dev, "target_feats") for t in target_feats_list]
+        N = mats[0].shape[0]
+        for t in mats:
+            if t.shape[0] != N or t.shape[1] < 1:
+                raise RuntimeError("every layer must be [N, K_l] with the same N and K_l >= 1")
+        if clip_feats.dim() != 2 or clip_feats.shape[0] != N:
+            raise RuntimeError("clip_feats %s and target_feats [%d, .] must share the probe-image axis"
+                               % (tuple(clip_feats.shape), N))
+        Ks = [t.shape[1] for t in mats]
+        A = mats[0] if len(mats) == 1 else torch.cat(mats, dim=1)
+        with _Stage("softmax_rows"):
+            S = concept_probabilities(clip_feats, a, dev)
+        with _Stage("topk_cols"):
+            idx32 = _topk_int32(A, int(top_k), dev)
+        with _Stage("wpmi_accum"):
+            L = log_sums(S, idx32, ramp, min_prob)
+        C = L.shape[1]
+        block_tab, seg_tab, seg_log, n_blocks = _segment_tables(Ks, dev)
+        lib = _lib.lib()
+        with _Stage("lse_finalize"):
+            part = torch.empty((n_blocks, 2, C), dtype=torch.float32, device=dev)
+            prob_d = torch.empty((len(Ks), C), dtype=torch.float32, device=dev)
+            _lib.check(lib.mcd_col_lse_partials_seg_f32(_ptr(L), _ld(L), C, _ptr(block_tab), n_blocks, _ptr(part),
+                                                        _stream(dev)), "mcd_col_lse_partials_seg_f32")
+            _lib.check(lib.mcd_pmi_finalize_seg_f32(_ptr(L), _ld(L), C, _ptr(part), _ptr(block_tab), n_blocks,
+                                                    _ptr(seg_tab), _ptr(seg_log), len(Ks), float(lam), _ptr(prob_d),
+                                                    _ptr(L), _ld(L), _stream(dev)), "mcd_pmi_finalize_seg_f32")
+    return list(torch.split(L, Ks, dim=0))
+
+
+def soft_wpmi_layers(clip_feats, target_feats_list, top_k=100, a=10, lam=1, device='cuda',
+                     min_prob=1e-7, p_start=0.998, p_end=0.97):
+    """soft_wpmi for all layers of a model in one pass: returns [soft_wpmi(clip_feats, t, ...) for t in the list]
+    (views of one [sum K_l, C] matrix), identical bits.  The reference scores layer by layer
+    (describe_broad_neurons.py:83-119); this is the same loop with the per-call work done once."""
+    dev = _cuda_device(device)
+    ramp = _device_ramp(_reference_ramp(int(top_k), p_start, p_end), top_k, p_start, p_end, dev)
+    return pmi_scores_layers(clip_feats, target_feats_list, top_k, a, lam, dev, min_prob, ramp)
+
+
+def wpmi_layers(clip_feats, target_feats_list, top_k=28, a=2, lam=0.6, device='cuda', min_prob=1e-7):
+    """wpmi for all layers of a model in one pass (see soft_wpmi_layers)."""
+    return pmi_scores_layers(clip_feats, target_feats_list, top_k, a, lam, device, min_prob, None)
+
+
 # ------------------------------------------------------------------------------------------------
 # the reference's call surface
 # ------------------------------------------------------------------------------------------------
 def soft_wpmi(clip_feats, target_feats, top_k=100, a=10, lam=1, device='cuda',
               min_prob=1e-7, p_start=0.998, p_end=0.97):
     """Soft-WPMI neuron x concept scores [K, C] on `device` (reference similarity.py:49-73)."""
-    return pmi_scores(clip_feats, target_feats, top_k, a, lam, device, min_prob,
-                      _reference_ramp(int(top_k), p_start, p_end))
+    dev = _cuda_device(device)
+    ramp = _device_ramp(_reference_ramp(int(top_k), p_start, p_end), top_k, p_start, p_end, dev)
+    return pmi_scores(clip_feats, target_feats, top_k, a, lam, dev, min_prob, ramp)
 
 
 def wpmi(clip_feats, target_feats, top_k=28, a=2, lam=0.6, device='cuda', min_prob=1e-7):

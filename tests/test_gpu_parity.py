@@ -377,6 +377,29 @@ def test_finalize_broadcast_kernel_matches_finalize(sim, K, C):
                                               odd, 1, row0 + 1, st) == -2
 
 
+@pytest.mark.parametrize("N", [1500, 20000])
+def test_layers_in_one_pass_equal_separate_calls(sim, N):
+    """soft_wpmi_layers / wpmi_layers: every layer gets exactly the bits of its own call -- the LSE
+    blocks restart at each layer's first neuron -- and the first layer also matches the oracle."""
+    widths = [24, 40, 300, 513, 7, 256]
+    P = torch.randn(N, 763, generator=gen(41)) * 0.05
+    layers = [torch.randn(N, w, generator=gen(50 + i)) for i, w in enumerate(widths)]
+    many = sim.soft_wpmi_layers(P, layers, top_k=50, device=DEV)
+    assert [tuple(m.shape) for m in many] == [(w, 763) for w in widths]
+    for t, m in zip(layers, many):
+        assert torch.equal(m, sim.soft_wpmi(P, t, top_k=50, device=DEV))
+    for t, m in zip(layers, sim.wpmi_layers(P, layers, device=DEV)):
+        assert torch.equal(m, sim.wpmi(P, t, device=DEV))
+    one = sim.soft_wpmi_layers(P, layers[2:3], top_k=50, device=DEV)
+    assert len(one) == 1 and torch.equal(one[0], many[2])
+    if N <= 2000:
+        ref, refL, _ = orc.soft_wpmi_fast(P, layers[0], top_k=50, return_parts=True)
+        assert (many[0].cpu() - ref).abs().max().item() <= 1e-5 * refL.abs().max().item()
+    assert sim.soft_wpmi_layers(P, [], device=DEV) == []
+    with pytest.raises(RuntimeError):
+        sim.soft_wpmi_layers(P, [layers[0], layers[1][:-1]], device=DEV)
+
+
 # ------------------------------------------------------------------------------------------------
 # K1 similarity matrix, K4 hook
 # ------------------------------------------------------------------------------------------------
