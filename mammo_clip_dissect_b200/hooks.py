@@ -79,3 +79,66 @@ def get_activation(outputs, mode):
         elif ndim == 2:    # FC layers
             outputs.append(output.detach())
     return hook
+
+
+class ActivationStack:
+    """Pooled activations of all hooked layers, kept on the device in ONE [n_images, sum K_l] fp32 matrix
+    (SURVEY.md section 8 f2): layer l owns columns [offset_l, offset_l + K_l), the hook of layer l writes the rows of
+    the current batch.  Replaces the reference's per-layer Python lists + ``torch.cat`` + ``torch.save`` / ``torch.load``
+    round trip (utils.py:151-200) when the activations are scored in the same process:
+
+        stack = ActivationStack(n_images, [24, 40, 64], "cuda")
+        for l, layer in enumerate(layers): layer.register_forward_hook(stack.hook(l, "avg"))
+        for batch in loader: model(batch)                         # hooks fill the matrix batch by batch
+        scores = similarity.soft_wpmi_layers(clip_feats, stack)   # no concatenation, no copy
+
+    ``stack.layer(l)`` is the [n_images, K_l] view the reference would have saved as one .pt file."""
+
+    def __init__(self, n_images, widths, device="cuda"):
+        self.widths = [int(w) for w in widths]
+        if n_images < 1 or not self.widths or min(self.widths) < 1:
+            raise ValueError("ActivationStack needs n_images >= 1 and positive layer widths")
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("mammo_clip_dissect_b200 has no CPU path: device=%r" % (device,))
+        self.offsets = [0]
+        for w in self.widths:
+            self.offsets.append(self.offsets[-1] + w)
+        self.matrix = torch.zeros((int(n_images), self.offsets[-1]), dtype=torch.float32, device=dev)
+        self.rows = [0] * len(self.widths)
+
+    def reset(self):
+        self.rows = [0] * len(self.widths)
+
+    def layer(self, l):
+        return self.matrix[:, self.offsets[l]:self.offsets[l + 1]]
+
+    def complete(self):
+        return all(r == self.matrix.shape[0] for r in self.rows)
+
+    def hook(self, l, mode):
+        """Forward hook for layer l with the summary rules of get_activation(outputs, mode)."""
+        if mode not in ("avg", "max"):
+            raise ValueError("mode must be 'avg' or 'max', got %r" % (mode,))
+        lo, hi = self.offsets[l], self.offsets[l + 1]
+
+        def hook(model, input, output):
+            if mode == "avg" and type(output) is tuple:
+                output = output[0]
+            ndim = len(output.shape)
+            if ndim == 4:
+                pooled = pool_nchw(output, mode)
+            elif ndim == 3:
+                pooled = output[:, 0]
+            elif ndim == 2:
+                pooled = output
+            else:
+                return
+            B = pooled.shape[0]
+            r = self.rows[l]
+            if pooled.shape[1] != hi - lo or r + B > self.matrix.shape[0]:
+                raise RuntimeError("ActivationStack: layer %d produced [%d, %d], expected width %d and at most %d more rows"
+                                   % (l, B, pooled.shape[1], hi - lo, self.matrix.shape[0] - r))
+            self.matrix[r:r + B, lo:hi].copy_(pooled.detach())
+            self.rows[l] = r + B
+        return hook

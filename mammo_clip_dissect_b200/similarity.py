@@ -295,19 +295,30 @@ def pmi_scores_layers(clip_feats, target_feats_list, top_k, a, lam, device, min_
     the layers stacked along the neuron axis: one softmax, one column top-k and one
     gather/log-sum over [N, sum K_l], and log p(d) per layer from segment-wise 256-neuron blocks."""
     dev = _cuda_device(device)
-    if len(target_feats_list) == 0:
+    stacked = hasattr(target_feats_list, "matrix") and hasattr(target_feats_list, "widths")   # hooks.ActivationStack
+    if not stacked and len(target_feats_list) == 0:
         return []
     with torch.no_grad(), torch.cuda.device(dev):
-        mats = [_as_f32_matrix(t, dev, "target_feats") for t in target_feats_list]
-        N = mats[0].shape[0]
-        for t in mats:
-            if t.shape[0] != N or t.shape[1] < 1:
-                raise RuntimeError("every layer must be [N, K_l] with the same N and K_l >= 1")
+        if stacked:
+            # the layers already sit side by side in one [N, sum K_l] matrix: nothing to concatenate
+            if hasattr(target_feats_list, "complete") and not target_feats_list.complete():
+                raise RuntimeError("ActivationStack is not full: some layer has not seen all probe images")
+            A = _as_f32_matrix(target_feats_list.matrix, dev, "target_feats")
+            Ks = [int(w) for w in target_feats_list.widths]
+            if sum(Ks) != A.shape[1] or min(Ks) < 1:
+                raise RuntimeError("layer widths %s do not add up to the stacked matrix width %d" % (Ks, A.shape[1]))
+            N = A.shape[0]
+        else:
+            mats = [_as_f32_matrix(t, dev, "target_feats") for t in target_feats_list]
+            N = mats[0].shape[0]
+            for t in mats:
+                if t.shape[0] != N or t.shape[1] < 1:
+                    raise RuntimeError("every layer must be [N, K_l] with the same N and K_l >= 1")
+            Ks = [t.shape[1] for t in mats]
+            A = mats[0] if len(mats) == 1 else torch.cat(mats, dim=1)
         if clip_feats.dim() != 2 or clip_feats.shape[0] != N:
             raise RuntimeError("clip_feats %s and target_feats [%d, .] must share the probe-image axis"
                                % (tuple(clip_feats.shape), N))
-        Ks = [t.shape[1] for t in mats]
-        A = mats[0] if len(mats) == 1 else torch.cat(mats, dim=1)
         with _Stage("softmax_rows"):
             S = concept_probabilities(clip_feats, a, dev)
         with _Stage("topk_cols"):

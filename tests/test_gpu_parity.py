@@ -400,6 +400,40 @@ def test_layers_in_one_pass_equal_separate_calls(sim, N):
         sim.soft_wpmi_layers(P, [layers[0], layers[1][:-1]], device=DEV)
 
 
+def test_activation_stack_feeds_the_layers_call(sim):
+    """hooks.ActivationStack: the hooks of all layers fill one [N, sum K] matrix batch by batch; its
+    layer views equal what get_activation's lists + torch.cat give, and scoring the stack equals scoring the list."""
+    from mammo_clip_dissect_b200 import hooks
+    torch.manual_seed(3)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 24, 3, padding=1), torch.nn.ReLU(), torch.nn.Conv2d(24, 40, 3, stride=2),
+                              torch.nn.ReLU(), torch.nn.Conv2d(40, 9, 1)).to(DEV).eval()
+    hooked, widths, n_img = [0, 2, 4], [24, 40, 9], 300
+    stack = hooks.ActivationStack(n_img, widths, DEV)
+    lists = [[] for _ in hooked]
+    handles = []
+    for l, i in enumerate(hooked):
+        handles.append(net[i].register_forward_hook(stack.hook(l, "avg")))
+        handles.append(net[i].register_forward_hook(hooks.get_activation(lists[l], "avg")))
+    x = torch.randn(n_img, 3, 20, 24, generator=gen(44))
+    with torch.no_grad():
+        for b0 in range(0, n_img, 64):                              # ragged last batch
+            net(x[b0:b0 + 64].to(DEV))
+            assert not stack.complete() or b0 + 64 >= n_img
+    for h in handles:
+        h.remove()
+    assert stack.complete()
+    cats = [torch.cat(v) for v in lists]
+    for l in range(3):
+        assert torch.equal(stack.layer(l), cats[l])
+    P = torch.randn(n_img, 763, generator=gen(45)) * 0.05
+    a = sim.soft_wpmi_layers(P, stack, top_k=20, device=DEV)
+    b = sim.soft_wpmi_layers(P, cats, top_k=20, device=DEV)
+    assert all(torch.equal(u, v) for u, v in zip(a, b)) and [t.shape[0] for t in a] == widths
+    stack.reset()
+    with pytest.raises(RuntimeError):
+        sim.soft_wpmi_layers(P, stack, top_k=20, device=DEV)       # not refilled yet
+
+
 # ------------------------------------------------------------------------------------------------
 # K1 similarity matrix, K4 hook
 # ------------------------------------------------------------------------------------------------
