@@ -198,7 +198,8 @@ int sim_matrix_fp32(const float *I, int64_t ldi, const float *T, int64_t ldt, in
 namespace mcd {
 size_t sim_matrix_tc_workspace(int64_t N, int64_t C, int64_t D);                       // gemm_tf32x3.cu
 int sim_matrix_tc(const float *I, int64_t ldi, const float *T, int64_t ldt, int64_t N, int64_t C, int64_t D,
-                  int normalize_rows, float *P, int64_t ldp, void *ws, size_t ws_bytes, cudaStream_t st);
+                  int normalize_rows, float *P, int64_t ldp, float *S, int64_t lds, float a, void *ws, size_t ws_bytes,
+                  cudaStream_t st);
 static size_t gemm_base_workspace(int64_t N, int64_t C) {
     const size_t ldp = size_t(ceil_div<int64_t>(C, 4) * 4);
     return ((size_t(N) + size_t(C)) * sizeof(float) + 255) / 256 * 256 + size_t(N) * ldp * sizeof(float) + 256;
@@ -226,11 +227,20 @@ extern "C" int mcd_gemm_nt_softmax_f32(const float *I, int64_t ldi, const float 
         P = reinterpret_cast<float *>(static_cast<char *>(workspace) + off);
         ld = ceil_div<int64_t>(C, 4) * 4;
     }
-    // tensor-core path (tcgen05 kind::tf32, 3-term split); tunable gemm_variant = 1 forces the fp32 CUDA-core kernel
+    // tensor-core path (tcgen05 kind::tf32, 3-term split) followed by the stand-alone softmax kernel.  Tunable
+    // gemm_variant = 1 forces the fp32 CUDA-core kernel; 3 selects the band kernel with the softmax fused into the
+    // GEMM epilogue -- correct, but measured 3.4x slower at N = 100k (3.05 ms against 0.77 + 0.13 ms): with one CTA
+    // per SM the exp / divide work of the four epilogue warps serialises with the tensor pipe instead of using the
+    // whole SM as the stand-alone kernel does
     int rc = MCD_ERR_UNSUPPORTED;
-    if (tunable(kGemmVariant) != 1) {
+    const int64_t variant = tunable(kGemmVariant);
+    bool fused = false;
+    if (variant != 1) {
         char *tc_ws = static_cast<char *>(workspace) + gemm_base_workspace(N, C);
-        rc = sim_matrix_tc(I, ldi, T, ldt, N, C, D, normalize_rows, P, ld, tc_ws, workspace_bytes - gemm_base_workspace(N, C), st);
+        fused = S_out != nullptr && variant == 3;
+        rc = sim_matrix_tc(I, ldi, T, ldt, N, C, D, normalize_rows, P, ld, fused ? S_out : nullptr, lds, a, tc_ws,
+                           workspace_bytes - gemm_base_workspace(N, C), st);
+        if (rc == MCD_OK && fused) return rc;
     }
     if (rc == MCD_ERR_UNSUPPORTED) rc = sim_matrix_fp32(I, ldi, T, ldt, N, C, D, normalize_rows, P, ld, norms, st);
     if (rc != MCD_OK || !S_out) return rc;

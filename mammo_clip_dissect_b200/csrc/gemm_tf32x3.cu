@@ -216,6 +216,174 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
     }
 }
 
+// ---- the same GEMM with the row softmax fused in: one CTA per 128-row band -------------------------------------------
+// A CTA walks all N-tiles of its band (6 for the 763-concept set), so the producer keeps prefetching operands of the
+// next tile while the epilogue drains the accumulators of the current one, and an epilogue thread -- which owns one
+// row of the band, TMEM lane = row -- sees every logit of its row: it keeps an online (max, sum of exponentials) pair
+// while it stores P.  When the last tile is done the four epilogue warps rescale the band row by row with coalesced
+// accesses (the band's P, 390 KB, is still in L2):  S = exp(a*P - max) / sum, per element the reference's operation
+// sequence (separately rounded a*P, expf, true division).  Only the order of the row sum differs from the stand-alone
+// kernel (softmax_rows.cu), by a few ulp.
+constexpr int kBandEpiThreads = 128;
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+gemm_tf32x3_band_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
+                        const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
+                        int64_t M, int64_t Nn, int num_kb, int n_tiles, float *__restrict__ P, int64_t ldp,
+                        float *__restrict__ S, int64_t lds, float a) {
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    unsigned char *aligned = smem_dyn + (base - smem_u32(smem_dyn));
+    uint64_t *full = reinterpret_cast<uint64_t *>(aligned + size_t(kGemmStages) * kStageBytes);
+    uint64_t *empty = full + kGemmStages;
+    uint64_t *tmem_full = empty + kGemmStages;
+    uint64_t *tmem_empty = tmem_full + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 1);
+    __shared__ float row_max[kBM], row_sum[kBM];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.x;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kGemmStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(tmem_full, 1);
+        mbar_init(tmem_empty, 4);            // one arrival per epilogue warp
+        fence_mbar_init();
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int g = 0;                       // k-block counter over all tiles: ring position and phase
+            for (int nt = 0; nt < n_tiles; ++nt)
+                for (int kb = 0; kb < num_kb; ++kb, ++g) {
+                    const int s = g % kGemmStages, use = g / kGemmStages;
+                    if (use > 0) mbar_wait_bounded(&empty[s], (use - 1) & 1);
+                    mbar_arrive_expect_tx(&full[s], kStageBytes);
+                    const uint32_t st = base + s * kStageBytes;
+                    const int kx = kb * kBK;
+                    tma_load_2d(st, &mapAhi, kx, m_tile * kBM, &full[s]);
+                    tma_load_2d(st + kATileBytes, &mapAlo, kx, m_tile * kBM, &full[s]);
+                    tma_load_2d(st + 2 * kATileBytes, &mapBhi, kx, nt * kBN, &full[s]);
+                    tma_load_2d(st + 2 * kATileBytes + kBTileBytes, &mapBlo, kx, nt * kBN, &full[s]);
+                }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            int g = 0;
+            for (int nt = 0; nt < n_tiles; ++nt) {
+                if (nt > 0) {                // the epilogue has read the previous tile's accumulators
+                    mbar_wait_bounded(tmem_empty, (nt - 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                for (int kb = 0; kb < num_kb; ++kb, ++g) {
+                    const int s = g % kGemmStages, use = g / kGemmStages;
+                    mbar_wait_bounded(&full[s], use & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t st = base + s * kStageBytes;
+                    const uint64_t ahi = umma_desc_k128(st), alo = umma_desc_k128(st + kATileBytes);
+                    const uint64_t bhi = umma_desc_k128(st + 2 * kATileBytes), blo = umma_desc_k128(st + 2 * kATileBytes + kBTileBytes);
+                    const uint32_t acc = tmem_base + uint32_t(kb % kAccSegs) * kBN;
+                    for (int kk = 0; kk < kBK / 8; ++kk) {
+                        const uint64_t adv = uint64_t((kk * 32) >> 4);
+                        umma_tf32(acc, ahi + adv, bhi + adv, kb >= kAccSegs || kk > 0);
+                        umma_tf32(acc, ahi + adv, blo + adv, true);
+                        umma_tf32(acc, alo + adv, bhi + adv, true);
+                    }
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(tmem_full);
+            }
+        }
+    } else {
+        const int quarter = warp & 3;
+        const int r_in_band = quarter * 32 + lane;
+        const int64_t row = int64_t(m_tile) * kBM + r_in_band;
+        const bool vec_ok = (ldp % 4 == 0) && (reinterpret_cast<uintptr_t>(P) % 16 == 0);
+        const int nseg = num_kb < kAccSegs ? num_kb : kAccSegs;
+        float m = -INFINITY, ssum = 0.f;
+#pragma unroll 1
+        for (int nt = 0; nt < n_tiles; ++nt) {
+            mbar_wait_bounded(tmem_full, nt & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int64_t col0 = int64_t(nt) * kBN;
+#pragma unroll 1
+            for (int c = 0; c < kBN; c += 32) {
+                float v[32];
+                tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(c), v);
+                for (int sgm = 1; sgm < nseg; ++sgm) {
+                    float w[32];
+                    tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(sgm * kBN + c), w);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __fadd_rn(v[i], w[i]);
+                }
+                if (row < M && col0 + c < Nn) {
+                    float *dst = P + row * ldp + col0 + c;
+                    const bool whole = col0 + c + 32 <= Nn;
+                    if (vec_ok && whole) {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4 *>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            if (col0 + c + i < Nn) dst[i] = v[i];
+                    }
+                    if (S != nullptr) {
+                        float z[32], mx = -INFINITY;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            z[i] = (whole || col0 + c + i < Nn) ? __fmul_rn(a, v[i]) : -INFINITY;
+                            mx = fmaxf(mx, z[i]);
+                        }
+                        if (mx > m) {
+                            ssum *= (m == -INFINITY) ? 0.f : expf(m - mx);
+                            m = mx;
+                        }
+                        const float ms = (m == -INFINITY) ? 0.f : m;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) ssum += expf(__fsub_rn(z[i], ms));     // exp(-inf) = 0 for the padding
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty);
+        }
+        if (S != nullptr) {
+            row_max[r_in_band] = m;
+            row_sum[r_in_band] = ssum;
+            // the P values below were written by other threads of these four warps: make them visible, then meet
+            __threadfence_block();
+            asm volatile("bar.sync 1, %0;" ::"n"(kBandEpiThreads) : "memory");
+            for (int r = quarter; r < kBM; r += 4) {        // warp per row, coalesced
+                const int64_t grow = int64_t(m_tile) * kBM + r;
+                if (grow >= M) break;
+                const float rm = row_max[r], rs = row_sum[r];
+                const float *src = P + grow * ldp;
+                float *dst = S + grow * lds;
+                for (int64_t c = lane; c < lds; c += 32)
+                    dst[c] = c < Nn ? __fdiv_rn(expf(__fsub_rn(__fmul_rn(a, src[c]), rm)), rs) : 0.f;
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    }
+}
+
 // ---- host ---------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn2)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -252,10 +420,11 @@ size_t sim_matrix_tc_workspace(int64_t N, int64_t C, int64_t D) {
 
 // returns MCD_ERR_UNSUPPORTED when the tensor-map encoder is unavailable (caller then uses the CUDA-core kernel)
 int sim_matrix_tc(const float *I, int64_t ldi, const float *T, int64_t ldt, int64_t N, int64_t C, int64_t D,
-                  int normalize_rows, float *P, int64_t ldp, void *ws, size_t ws_bytes, cudaStream_t st) {
+                  int normalize_rows, float *P, int64_t ldp, float *S, int64_t lds, float a, void *ws, size_t ws_bytes,
+                  cudaStream_t st) {
     const int64_t Np = ceil_div<int64_t>(N, kBM) * kBM, Cp = ceil_div<int64_t>(C, kBN) * kBN, Dp = ceil_div<int64_t>(D, kBK) * kBK;
     if (ws_bytes < sim_matrix_tc_workspace(N, C, D)) return MCD_ERR_WORKSPACE;
-    if (Np / kBM > 65535) return MCD_ERR_UNSUPPORTED;
+    if (Np / kBM > 65535 && S == nullptr) return MCD_ERR_UNSUPPORTED;
     char *w = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
     float *Ihi = reinterpret_cast<float *>(w);
     float *Ilo = Ihi + Np * Dp;
@@ -268,6 +437,14 @@ int sim_matrix_tc(const float *I, int64_t ldi, const float *T, int64_t ldt, int6
     prepare_rows_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(Np, 8)), 256, 0, st>>>(I, ldi, N, D, normalize_rows, Ihi, Ilo, Np, Dp);
     prepare_rows_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(Cp, 8)), 256, 0, st>>>(T, ldt, C, D, normalize_rows, Thi, Tlo, Cp, Dp);
     count_launch(2);
+    if (S != nullptr) {
+        // one CTA per 128-row band, softmax fused (opt-in: tunable gemm_variant = 3, see dense_sim.cu)
+        if (cudaFuncSetAttribute(gemm_tf32x3_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTcSmemBytes)) != cudaSuccess)
+            return MCD_ERR_CUDA;
+        gemm_tf32x3_band_kernel<<<static_cast<unsigned>(Np / kBM), kTcThreads, kTcSmemBytes, st>>>(
+            mAhi, mAlo, mBhi, mBlo, N, C, static_cast<int>(Dp / kBK), static_cast<int>(Cp / kBN), P, ldp, S, lds, a);
+        return check_launch();
+    }
     if (cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTcSmemBytes)) != cudaSuccess)
         return MCD_ERR_CUDA;
     dim3 grid(static_cast<unsigned>(Cp / kBN), static_cast<unsigned>(Np / kBM));

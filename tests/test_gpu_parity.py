@@ -486,6 +486,21 @@ def test_similarity_matrix_tensor_core_vs_fp32(sim, N, C, D, normalize):
         e_s = ((S.cpu().double() - refS).abs() / refS).max().item()
         print("   softmax(10 P) max rel err through the tensor-core path: %.3g" % e_s)
         assert e_s <= 1e-5
+    # the opt-in band kernel with the softmax fused into the GEMM epilogue (gemm_variant = 3) against the default
+    # GEMM + stand-alone softmax: same P bits (same accumulation order), S within a few ulp (only the order of the row
+    # sum differs)
+    P_s, S_s = features.similarity_matrix(I, T, device=DEV, normalize=normalize, softmax_scale=10)
+    try:
+        _lib.set_tunable("gemm_variant", 3)
+        n0 = _lib.launch_count()
+        P_f, S_f = features.similarity_matrix(I, T, device=DEV, normalize=normalize, softmax_scale=10)
+        assert _lib.launch_count() - n0 == 3             # 2 x prepare_rows + the band kernel: no softmax launch
+    finally:
+        _lib.set_tunable("gemm_variant", 0)
+    assert torch.equal(P_f, P_s) and torch.equal(P_f.cpu(), P_tc)
+    rel = ((S_f - S_s).abs() / S_s.clamp_min(1e-30)).max().item()
+    print("   fused vs stand-alone softmax: max rel diff %.3g" % rel)
+    assert rel <= 2e-6 and abs(S_f.sum(dim=1) - 1).max().item() < 1e-5
 
 
 def test_hook_matches_reference(sim, golden):

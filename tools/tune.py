@@ -95,10 +95,10 @@ def main():
         I = torch.randn(N, 512, generator=g, device=dev)
         T = torch.randn(C, 512, generator=g, device=dev)
         fl = 2.0 * N * C * 512
-        for var in (0, 1):
+        for var in (0, 3, 1):
             _lib.set_tunable("gemm_variant", var)
             ms = timeit(lambda: features.similarity_matrix(I, T, device=dev))
-            print("K1 I.T^T variant=%d (%s): %.3f ms  %.1f TFLOP/s (algorithmic 2NCD)" % (var, "tcgen05 3xTF32" if var == 0 else "fp32 FFMA", ms, fl / ms / 1e9), flush=True)
+            print("K1 I.T^T variant=%d (%s): %.3f ms  %.1f TFLOP/s (algorithmic 2NCD)" % (var, {0: "tcgen05 3xTF32 + stand-alone softmax", 3: "tcgen05 3xTF32 band kernel, softmax fused in the epilogue"}.get(var, "fp32 FFMA"), ms, fl / ms / 1e9), flush=True)
             ms = timeit(lambda: features.similarity_matrix(I, T, device=dev, softmax_scale=10))
             print("   + softmax: %.3f ms" % ms, flush=True)
         _lib.set_tunable("gemm_variant", 0)
