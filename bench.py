@@ -151,7 +151,7 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args.gpus),
+            "config": dict(workload_config(args.gpus), score_exchange="n/a (CPU reference arm)"),
             "cpu_baseline": {"value": round(value, 1), "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "each step: oracle loop port (torch CPU ops, %d threads) on P[100000,763] and "
                                        "%d of the 32768 neuron columns, top_k=100" % (cores, sample)},
