@@ -616,24 +616,37 @@ struct SmallSmem {
     uint32_t hist[256][kUnitCols];
     uint32_t ties[kSmallWarps][kUnitCols];      // ties in slice w, then (in place) how many of them slice w takes
     uint32_t prefix[kUnitCols], need[kUnitCols], outpos[kUnitCols];
+    uint32_t cta_ties[kUnitCols], cta_quota[kUnitCols];
 };
 
+// A thread-block CLUSTER of R CTAs shares one group of 32 columns: CTA `rank` takes rows [rank*rpc, (rank+1)*rpc) with
+// its 32 warps, so that a 768-neuron layer (24 column groups) still covers the machine (R = 4: 96 CTAs).  After each
+// counting pass rank 0 adds the other CTAs' histograms to its own through distributed shared memory, walks the bins
+// and the others fetch the new prefix; the tie quotas go rank by rank (lowest image indices first) and the output
+// slots come from rank 0's counter (DSMEM atomics, k of them per column).
 __global__ void __launch_bounds__(kSmallWarps * 32)
 topk_small_kernel(const float *__restrict__ A, int64_t lda, int N, int64_t K, int k,
                   unsigned long long *__restrict__ cand) {
     __shared__ SmallSmem s;
+    const unsigned R = cluster_nctarank(), rank = cluster_ctarank();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t col = int64_t(blockIdx.x) * kUnitCols + lane;
+    const int64_t col = int64_t(blockIdx.x / R) * kUnitCols + lane;
     const bool active = col < K;
-    const int rps = (N + kSmallWarps - 1) / kSmallWarps;
-    const int r0 = min(N, warp * rps), r1 = min(N, r0 + rps);
+    const int rpc = (N + int(R) - 1) / int(R);                       // rows per CTA
+    const int c0 = min(N, int(rank) * rpc), c1 = min(N, c0 + rpc);
+    const int rps = (c1 - c0 + kSmallWarps - 1) / kSmallWarps;       // rows per warp
+    const int r0 = min(c1, c0 + warp * rps), r1 = min(c1, r0 + rps);
     const float *src = A + (active ? col : 0);
+    const uint32_t s_base = smem_u32(&s);
+    // address of a field of rank q's SmallSmem
+    auto remote = [&](const void *field, unsigned q) { return dsmem_addr(smem_u32(field), q); };
+    (void)s_base;
     if (warp == 0) {
         s.prefix[lane] = 0u;
         s.need[lane] = static_cast<uint32_t>(k);
         s.outpos[lane] = 0u;
     }
-    constexpr int kU = 16;      // independent loads in flight per lane (the loop is L2-latency bound)
+    constexpr int kU = 16;      // independent loads in flight per lane
 #pragma unroll 1
     for (int pass = 0; pass < 4; ++pass) {
         const int shift = 24 - 8 * pass;
@@ -658,31 +671,54 @@ topk_small_kernel(const float *__restrict__ A, int64_t lda, int N, int64_t K, in
                 if ((key & himask) == pre) atomicAdd(&s.hist[(key >> shift) & 255u][lane], 1u);
             }
         }
-        __syncthreads();
-        if (warp == 0 && active) {
-            // walk the bins from the largest digit down to the one that holds the `need`-th element (8 bins per step
-            // so that the shared-memory loads overlap)
-            uint32_t need = s.need[lane], acc = 0u;
-            int b = 0;
-            bool found = false;
-            for (int hi8 = 255; hi8 >= 0 && !found; hi8 -= 8) {
-                uint32_t h[8];
+        cluster_sync_all();                     // every CTA's histogram is complete
+        if (R > 1) {
+            // CTA `rank` adds up its share of the bins over all CTAs and puts the totals into rank 0's histogram
+            // (only the owner of a share reads or writes it, so rank 0's own counts are not raced on)
+            const int per = 256 * kUnitCols / int(R);
+            for (int i = int(rank) * per + threadIdx.x; i < int(rank + 1) * per; i += kSmallWarps * 32) {
+                uint32_t *mine = &s.hist[0][0] + i;
+                uint32_t part[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) h[j] = s.hist[hi8 - j][lane];
+                for (unsigned q = 0; q < 8; ++q) part[q] = q < R ? ld_dsmem_u32(remote(mine, q)) : 0u;
+                uint32_t sum = 0u;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    if (!found) {
-                        if (acc + h[j] >= need) {
-                            found = true;
-                            b = hi8 - j;
-                        } else {
-                            acc += h[j];
+                for (unsigned q = 0; q < 8; ++q) sum += part[q];
+                st_dsmem_u32(remote(mine, 0), sum);
+            }
+            cluster_sync_all();                 // the totals are in rank 0
+        }
+        if (rank == 0) {
+            if (warp == 0 && active) {
+                // walk the bins from the largest digit down to the one that holds the `need`-th element (8 bins per
+                // step so that the shared-memory loads overlap)
+                uint32_t need = s.need[lane], acc = 0u;
+                int b = 0;
+                bool found = false;
+                for (int hi8 = 255; hi8 >= 0 && !found; hi8 -= 8) {
+                    uint32_t h[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) h[j] = s.hist[hi8 - j][lane];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (!found) {
+                            if (acc + h[j] >= need) {
+                                found = true;
+                                b = hi8 - j;
+                            } else {
+                                acc += h[j];
+                            }
                         }
                     }
                 }
+                s.prefix[lane] = pre | (uint32_t(b) << shift);
+                s.need[lane] = need - acc;      // still to take among the elements that share the new prefix
             }
-            s.prefix[lane] = pre | (uint32_t(b) << shift);
-            s.need[lane] = need - acc;          // still to take among the elements that share the new prefix
+        }
+        cluster_sync_all();                     // rank 0 has published prefix / need (and is done with the histograms)
+        if (rank != 0 && warp == 0) {
+            s.prefix[lane] = ld_dsmem_u32(remote(&s.prefix[lane], 0));
+            s.need[lane] = ld_dsmem_u32(remote(&s.need[lane], 0));
         }
         __syncthreads();
     }
@@ -703,7 +739,24 @@ topk_small_kernel(const float *__restrict__ A, int64_t lda, int N, int64_t K, in
     s.ties[warp][lane] = t;
     __syncthreads();
     if (warp == 0) {
-        uint32_t left = s.need[lane];           // lowest image indices first: slices in order
+        uint32_t tot = 0u;
+        for (int w = 0; w < kSmallWarps; ++w) tot += s.ties[w][lane];
+        s.cta_ties[lane] = tot;
+    }
+    cluster_sync_all();
+    if (rank == 0 && warp == 0) {
+        uint32_t left = s.need[lane];           // lowest image indices first: CTAs in rank order, then their slices
+        for (unsigned q = 0; q < R; ++q) {
+            const uint32_t have = q == 0 ? s.cta_ties[lane] : ld_dsmem_u32(remote(&s.cta_ties[lane], q));
+            const uint32_t give = min(have, left);
+            if (q == 0) s.cta_quota[lane] = give;
+            else st_dsmem_u32(remote(&s.cta_quota[lane], q), give);
+            left -= give;
+        }
+    }
+    cluster_sync_all();
+    if (warp == 0) {
+        uint32_t left = s.cta_quota[lane];
         for (int w = 0; w < kSmallWarps; ++w) {
             const uint32_t q = min(s.ties[w][lane], left);
             s.ties[w][lane] = q;
@@ -714,6 +767,7 @@ topk_small_kernel(const float *__restrict__ A, int64_t lda, int N, int64_t K, in
     if (active) {
         uint32_t quota = s.ties[warp][lane];
         unsigned long long *dst = cand + col;
+        const uint32_t counter = remote(&s.outpos[lane], 0);
         // in row order: the first `quota` ties of the slice are taken
         auto offer = [&](uint32_t key, int r) {
             bool take = key > T;
@@ -722,7 +776,7 @@ topk_small_kernel(const float *__restrict__ A, int64_t lda, int N, int64_t K, in
                 --quota;
             }
             if (take) {
-                const uint32_t pos = atomicAdd(&s.outpos[lane], 1u);
+                const uint32_t pos = atom_add_dsmem_u32(counter, 1u);
                 dst[int64_t(pos) * K] = pack_key(key, ~static_cast<uint32_t>(r));
             }
         };
@@ -736,6 +790,7 @@ topk_small_kernel(const float *__restrict__ A, int64_t lda, int N, int64_t K, in
         }
         for (; r < r1; ++r) offer(ordered_key(__ldg(src + int64_t(r) * lda)), r);
     }
+    cluster_sync_all();                         // nobody leaves while its shared memory may still be addressed
 }
 
 // ---- host side ----------------------------------------------------------------------------------
@@ -937,8 +992,27 @@ extern "C" int mcd_topk_cols_f32(const float *A, int64_t lda, int64_t N, int64_t
     // short columns of an L2-resident matrix: exact radix select (tunable topk_small: 1 = never, else automatic)
     if (N <= kSmallMaxRows && (N <= 4096 || N * K * 4 <= kSmallMaxBytes) && tunable(kTopkSmall) != 1 && tunable(kTopkSplits) <= 0 &&
         tunable(kTopkCols) <= 0 && tunable(kTopkVariant) != 1) {
-        topk_small_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(K, kUnitCols)), kSmallWarps * 32, 0, st>>>(
-            A, lda, int(N), K, int(k), cand);
+        // rows of a column group split over a cluster of R CTAs when the column groups alone would leave SMs idle
+        const int64_t ncb_s = ceil_div<int64_t>(K, kUnitCols);
+        int R = 1;
+        while (R < 8 && ncb_s * R * 2 <= num_sms() && N / (R * 2) >= 512) R *= 2;
+        if (tunable(kTopkSmall) >= 2 && tunable(kTopkSmall) <= 16) R = int(tunable(kTopkSmall)) / 2;   // test knob: 2,4,8,16 -> R = 1,2,4,8
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(static_cast<unsigned>(ncb_s * R));
+        cfg.blockDim = dim3(kSmallWarps * 32);
+        cfg.stream = st;
+        cudaLaunchAttribute attr;
+        attr.id = cudaLaunchAttributeClusterDimension;
+        attr.val.clusterDim.x = static_cast<unsigned>(R);
+        attr.val.clusterDim.y = 1;
+        attr.val.clusterDim.z = 1;
+        cfg.attrs = &attr;
+        cfg.numAttrs = 1;
+        if (cudaLaunchKernelEx(&cfg, topk_small_kernel, A, lda, int(N), K, int(k), cand) != cudaSuccess) {
+            count_launch(1);
+            return MCD_ERR_CUDA;
+        }
         int rc0 = check_launch();
         if (rc0 != MCD_OK) return rc0;
         p.splits = 1;

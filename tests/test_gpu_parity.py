@@ -32,15 +32,16 @@ def gen(seed):
 
 
 class topk_path:
-    """K2 has two implementations: the radix select for short columns (N <= 16384, "auto") and the streaming scan
-    ("stream": tunable topk_small = 1 switches the short-column kernel off)."""
+    """K2 has two implementations: the radix select for short columns (N <= 16384, "auto"; "cluster1/2/8" force the
+    number of CTAs that share a column group's rows) and the streaming scan ("stream": tunable topk_small = 1 switches
+    the short-column kernel off)."""
 
     def __init__(self, path):
         self.path = path
 
     def __enter__(self):
         from mammo_clip_dissect_b200 import _lib
-        _lib.set_tunable("topk_small", 1 if self.path == "stream" else 0)
+        _lib.set_tunable("topk_small", {"stream": 1, "cluster1": 2, "cluster2": 4, "cluster8": 16}.get(self.path, 0))
 
     def __exit__(self, *exc):
         from mammo_clip_dissect_b200 import _lib
@@ -70,7 +71,7 @@ def check_scores(out, L, ref_out, ref_L, f64_out=None, label=""):
                                    (1024, 64, 48), (1500, 129, 112), (3000, 68, 200), (4000, 36, 300),
                                    (2048, 12, 496), (64, 4, 64), (1024, 70, 512), (700, 33, 129), (900, 40, 257),
                                    (16384, 40, 100), (16385, 33, 100), (31, 5, 31), (10000, 768, 100)])
-@pytest.mark.parametrize("path", ["auto", "stream"])
+@pytest.mark.parametrize("path", ["auto", "stream", "cluster8"])
 def test_topk_tie_free(sim, N, K, k, path):
     A = torch.randn(N, K, generator=gen(N + K + k))
     with topk_path(path):
@@ -82,7 +83,7 @@ def test_topk_tie_free(sim, N, K, k, path):
 
 
 @pytest.mark.parametrize("kind", ["round1", "relu", "const", "nan_inf", "signed_zero", "sorted_up", "sorted_down"])
-@pytest.mark.parametrize("path", ["auto", "stream"])
+@pytest.mark.parametrize("path", ["auto", "stream", "cluster1", "cluster2", "cluster8"])
 def test_topk_ties_and_specials(sim, kind, path):
     N, K, k = 3000, 96, 100
     A = torch.randn(N, K, generator=gen(5))
