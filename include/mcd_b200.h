@@ -95,6 +95,16 @@ int mcd_pmi_finalize_f32(const float *L, int64_t ldl, int64_t K, int64_t C,
                          float lam, float *prob_d_out /* [C] scratch+result */,
                          float *out, int64_t ldo, mcd_stream_t stream);
 
+/* ---- the whole soft_wpmi / wpmi call (similarity.py:49-73 / :75-97) behind one entry point:
+ *      softmax(a P) -> column top-k of A -> gather / log-sum -> block LSE -> out = L - lam log p(d),
+ *      the same kernels as the functions above with the intermediates in `workspace` (256-byte
+ *      aligned).  p: device ramp [k] for soft_wpmi, NULL for wpmi.  out [K, C] (ldo). */
+size_t mcd_pmi_scores_workspace_bytes(int64_t N, int64_t K, int64_t C, int64_t k);
+int mcd_pmi_scores_f32(const float *P, int64_t ldp, const float *A, int64_t lda, int64_t N, int64_t K,
+                       int64_t C, int64_t k, float a, float lam, const float *p, float min_prob,
+                       float *out, int64_t ldo, void *workspace, size_t workspace_bytes,
+                       mcd_stream_t stream);
+
 /* ---- K3b for several layers stacked along the neuron axis of one [sum K_l, C] matrix (SURVEY.md 8 f1:
  *      the 12-39 layers of a real job in one pass of every kernel).  Same arithmetic, block by
  *      block, as the single-layer functions, so each layer's rows get exactly the bits a separate

@@ -105,6 +105,22 @@ def _workspace(nbytes, dev):
     return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=dev)
 
 
+_CALL_WS = {}          # (device, stream) -> grow-only workspace for the single-entry call, small calls only
+_CALL_WS_MAX = 256 << 20
+
+
+def _call_workspace(nbytes, dev):
+    """Workspace of mcd_pmi_scores_f32.  Calls on one stream are ordered, so small workspaces are kept and reused
+    (a job scores dozens of small layers back to back); big ones come from the caching allocator per call."""
+    if nbytes > _CALL_WS_MAX:
+        return torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    buf = _CALL_WS.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = _CALL_WS[key] = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
+    return buf
+
+
 # ------------------------------------------------------------------------------------------------
 # building blocks (also used by the multi-GPU path and the tests)
 # ------------------------------------------------------------------------------------------------
@@ -246,6 +262,27 @@ def pmi_scores(clip_feats, target_feats, top_k, a, lam, device, min_prob, ramp, 
             raise RuntimeError("clip_feats %s and target_feats %s must share the probe-image axis"
                                % (tuple(clip_feats.shape), tuple(A.shape)))
         top_k = int(top_k)
+        if PROFILE is None and not return_parts:
+            # the whole call behind one FFI entry point (same kernels, intermediates in one workspace): a small layer
+            # is launch-bound from Python otherwise
+            P = _as_f32_matrix(clip_feats, dev, "clip_feats")
+            N, C = P.shape
+            K = A.shape[1]
+            if C < 1 or K < 1:
+                raise RuntimeError("clip_feats / target_feats must be non-empty")
+            if top_k < 1 or top_k > N:
+                raise RuntimeError("selected index k out of range")
+            lib = _lib.lib()
+            need = int(lib.mcd_pmi_scores_workspace_bytes(N, K, C, top_k))
+            if need == 0:
+                raise RuntimeError("top_k=%d is outside the supported range of the column top-k kernel (<= 512)" % top_k)
+            ws = _call_workspace(need, dev)
+            weights = ramp.to(dev) if ramp is not None else None
+            out = torch.empty((K, C), dtype=torch.float32, device=dev)
+            _lib.check(lib.mcd_pmi_scores_f32(_ptr(P), _ld(P), _ptr(A), _ld(A), N, K, C, top_k, float(a), float(lam),
+                                              _ptr(weights), float(min_prob), _ptr(out), _ld(out), _ptr(ws), ws.numel(),
+                                              _stream(dev)), "mcd_pmi_scores_f32")
+            return out
         with _Stage("softmax_rows"):
             S = concept_probabilities(clip_feats, a, dev)
         with _Stage("topk_cols"):

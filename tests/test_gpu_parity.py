@@ -378,6 +378,33 @@ def test_finalize_broadcast_kernel_matches_finalize(sim, K, C):
                                               odd, 1, row0 + 1, st) == -2
 
 
+@pytest.mark.parametrize("N,K,k", [(700, 130, 50), (20000, 70, 100), (300, 5, 300)])
+def test_single_entry_call_equals_the_staged_path(sim, N, K, k):
+    """soft_wpmi / wpmi normally run behind ONE C entry point (mcd_pmi_scores_f32); with per-stage profiling on, the
+    Python wrapper launches the same kernels stage by stage.  Same bits; workspace errors are reported."""
+    from mammo_clip_dissect_b200 import _lib
+    P = torch.randn(N, 763, generator=gen(61)) * 0.05
+    A = torch.randn(N, K, generator=gen(62))
+    fast, fast_w = sim.soft_wpmi(P, A, top_k=k, device=DEV), sim.wpmi(P, A, top_k=min(k, 28), device=DEV)
+    try:
+        sim.PROFILE = []
+        staged, staged_w = sim.soft_wpmi(P, A, top_k=k, device=DEV), sim.wpmi(P, A, top_k=min(k, 28), device=DEV)
+        assert {"softmax_rows", "topk_cols", "wpmi_accum", "lse_finalize"} <= set(sim.profile_summary())
+    finally:
+        sim.PROFILE = None
+    assert torch.equal(fast, staged) and torch.equal(fast_w, staged_w)
+    lib = _lib.lib()
+    need = lib.mcd_pmi_scores_workspace_bytes(N, K, 763, k)
+    assert need > 0 and lib.mcd_pmi_scores_workspace_bytes(N, K, 763, N + 1) == 0
+    Pd, Ad, out = P.to(DEV), A.to(DEV), torch.empty(K, 763, device=DEV)
+    ws = torch.empty(need, dtype=torch.uint8, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    assert lib.mcd_pmi_scores_f32(Pd.data_ptr(), 763, Ad.data_ptr(), K, N, K, 763, k, 10.0, 1.0, None, 1e-7,
+                                  out.data_ptr(), 763, ws.data_ptr(), need - 1, st) == -3
+    assert lib.mcd_pmi_scores_f32(Pd.data_ptr(), 762, Ad.data_ptr(), K, N, K, 763, k, 10.0, 1.0, None, 1e-7,
+                                  out.data_ptr(), 763, ws.data_ptr(), need, st) == -1
+
+
 @pytest.mark.parametrize("N", [1500, 20000])
 def test_layers_in_one_pass_equal_separate_calls(sim, N):
     """soft_wpmi_layers / wpmi_layers: every layer gets exactly the bits of its own call -- the LSE
