@@ -131,6 +131,13 @@ int mcd_pmi_finalize_bcast_f32(const float *L, int64_t K, int64_t C, const float
                                float *prob_d_out, float *const *dest_bases, int n_dest,
                                int64_t row_offset, mcd_stream_t stream);
 
+/* ---- per-neuron top concepts: the t largest entries of every row of the score matrix, sorted
+ *      descending (value desc, concept index asc, NaN largest)   replaces torch.topk(sim, 10, dim=1)
+ *      / torch.max(sim, 1) in the callers (describe_broad_neurons.py:101, describe_clip_neurons.py:64).
+ *      X [n_rows, n_cols] (ldx), n_cols <= 1024, t <= 64; vals_out / idx_out [n_rows, t]. */
+int mcd_row_topk_f32(const float *X, int64_t ldx, int64_t n_rows, int64_t n_cols, int64_t t,
+                     float *vals_out, int64_t *idx_out, mcd_stream_t stream);
+
 /* ---- K4: spatial pooling of a hooked NCHW activation   replaces utils.py:38 / :47 -------
  *      x [B,C,H,W] contiguous, dtype f32/f16/bf16; out [B,C] same dtype (fp32 accumulation).
  *      workspace: mcd_pool_nchw_workspace_bytes (partials for planes split across CTAs). */

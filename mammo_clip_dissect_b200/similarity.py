@@ -28,7 +28,7 @@ import torch
 from . import _lib
 
 __all__ = ["soft_wpmi", "wpmi", "cos_similarity", "cos_similarity_cubed", "cos_similarity_cubed_single", "rank_reorder",
-           "soft_wpmi_layers", "wpmi_layers", "topk_cols", "concept_probabilities", "pmi_scores"]
+           "soft_wpmi_layers", "wpmi_layers", "top_concepts", "topk_cols", "concept_probabilities", "pmi_scores"]
 
 _S_ALIGN = 32  # leading dimension of the probability matrix: rows start on 128-byte boundaries
 
@@ -389,6 +389,25 @@ def soft_wpmi_layers(clip_feats, target_feats_list, top_k=100, a=10, lam=1, devi
 def wpmi_layers(clip_feats, target_feats_list, top_k=28, a=2, lam=0.6, device='cuda', min_prob=1e-7):
     """wpmi for all layers of a model in one pass (see soft_wpmi_layers)."""
     return pmi_scores_layers(clip_feats, target_feats_list, top_k, a, lam, device, min_prob, None)
+
+
+def top_concepts(scores, k=10):
+    """(values [K, k], indices [K, k] int64) of the k best concepts of every neuron, best first -- what the reference's
+    callers compute with torch.topk(similarities, k=10, dim=1) (describe_broad_neurons.py:101) or torch.max(similarities,
+    1) (describe_clip_neurons.py:64), under the stated order (value desc, concept index asc, NaN largest)."""
+    if scores.dim() != 2 or not scores.is_cuda:
+        raise RuntimeError("top_concepts expects a 2-D CUDA score matrix (mammo_clip_dissect_b200 has no CPU path)")
+    X = _as_f32_matrix(scores, scores.device, "scores")
+    K, C = X.shape
+    k = int(k)
+    if k < 1 or k > C:
+        raise RuntimeError("selected index k out of range")
+    vals = torch.empty((K, k), dtype=torch.float32, device=X.device)
+    idx = torch.empty((K, k), dtype=torch.int64, device=X.device)
+    with torch.cuda.device(X.device):
+        _lib.check(_lib.lib().mcd_row_topk_f32(_ptr(X), _ld(X), K, C, k, _ptr(vals), _ptr(idx), _stream(X.device)),
+                   "mcd_row_topk_f32")
+    return vals, idx
 
 
 # ------------------------------------------------------------------------------------------------

@@ -462,6 +462,28 @@ def test_activation_stack_feeds_the_layers_call(sim):
         sim.soft_wpmi_layers(P, stack, top_k=20, device=DEV)       # not refilled yet
 
 
+@pytest.mark.parametrize("K,C,t", [(300, 763, 10), (33, 763, 1), (70, 29, 29), (5, 1000, 64), (257, 200, 5)])
+def test_top_concepts_per_neuron(sim, K, C, t):
+    """mcd_row_topk_f32 = torch.topk(scores, t, dim=1) of the reference's callers, under the stated order."""
+    X = torch.randn(K, C, generator=gen(71))
+    v, i = sim.top_concepts(X.to(DEV), t)
+    rv, ri = torch.topk(X, t, dim=1)
+    assert torch.equal(i.cpu(), ri) and torch.equal(v.cpu(), rv)                  # tie-free: equals torch.topk
+    Y = (X * 4).round() / 4                                                     # heavy ties + specials
+    Y[0, :3] = float("nan")
+    Y[1, 5] = float("inf")
+    Y[2] = 0.5
+    want = torch.sort(Y, dim=1, descending=True, stable=True)                   # NaN first (largest), ties by index
+    v, i = sim.top_concepts(Y.to(DEV), t)
+    assert torch.equal(i.cpu(), want.indices[:, :t])
+    assert torch.equal(v.cpu().nan_to_num(9.0), want.values[:, :t].nan_to_num(9.0))
+    wide = torch.zeros(K, C + 7)
+    wide[:, 3:C + 3] = X
+    assert torch.equal(sim.top_concepts(wide.to(DEV)[:, 3:C + 3], t)[1].cpu(), ri)      # strided rows
+    with pytest.raises(RuntimeError):
+        sim.top_concepts(X.to(DEV), C + 1)
+
+
 # ------------------------------------------------------------------------------------------------
 # K1 similarity matrix, K4 hook
 # ------------------------------------------------------------------------------------------------
