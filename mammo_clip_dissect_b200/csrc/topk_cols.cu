@@ -4,19 +4,21 @@
 // A is [N images, K neurons] row-major, so one neuron's activations are strided by K floats and the
 // only coalesced way through A is "a row segment per warp".  The unit of work is ONE WARP (a 32-thread
 // CTA) that owns 32 adjacent neuron columns (128-byte row segments) and one slice of the image axis;
-// 6-8 such warps are resident per SM and none of them ever synchronises with another:
+// 7 such warps are resident per SM and none of them ever synchronises with another:
 //
 //   feed    the warp streams [32 rows x 32 cols] tiles of A into its private shared-memory ring with
 //           TMA tensor-tile loads (cp.async.bulk.tensor.2d, mbarrier completion, L2 evict-first: A is
 //           read exactly once); lane 0 re-arms a stage as soon as its rows are in registers.
-//   scan    a lane reads 4 adjacent columns of a row with one 16-byte LDS (the 4 quarter-warps take 4
-//           consecutive rows) and compares them with the 4 column thresholds it keeps in registers
-//           (threshold = value of the column's current k-th best).  The few elements that beat their
-//           threshold (~k ln(N/k) per column over the whole scan) are appended -- predicated stores,
-//           no atomics, no divergence -- to the pending list private to (quarter-warp, column).
-//   fold    when a pending list is nearly full, lane c folds the lists of column c into the column's
-//           kept set (an unsorted two-level min structure of (key, ~index) words in L2-resident
-//           global memory) and publishes the new threshold.  Only this warp's stream pauses.
+//   scan    a lane reads 4 adjacent columns of a row with one 16-byte LDS (quarter-warp q takes rows
+//           q, q+4, ..., q+28 of the tile) and compares them with the 4 column thresholds it keeps in
+//           registers (threshold = value of the column's current k-th best).  The few elements that
+//           beat their threshold are appended -- predicated stores, no atomics, no divergence -- to
+//           the pending list private to (quarter-warp, column).
+//   fold    when a pending list could overflow in the next tile, lane c folds the lists of column c
+//           into the column's kept set (an unsorted two-level min structure of (key, ~index) words:
+//           groups in L2-resident global memory, group minima in shared memory, the group holding
+//           the overall minimum mirrored in registers) and publishes the new threshold.  Only this
+//           warp's stream pauses.
 //
 // A warp's kept sets only change between its scan steps and it scans rows in order, so when a step is
 // scanned every kept entry has a smaller image index than every element of the step: "strictly greater
@@ -25,9 +27,18 @@
 // NaN is the largest value, -0.0 == +0.0 (common.cuh).
 //
 // The image axis may be split across warps (grid.y) so that the warp count fills whole waves of the
-// resident-warp slots; each (split, column) writes its k survivors to the workspace and
-// topk_finish_kernel sorts the splits*k candidates of a column (warp-level bitonic sort) and emits
-// indices / values.
+// resident-warp slots; each (split, column) writes its survivors to the workspace and a finish kernel
+// sorts the splits*k candidates of a column (bitonic network, in registers up to 256 candidates) and
+// emits indices / values.
+//
+// Around the scan (mcd_topk_cols_f32 at the end of the file):
+//   start threshold   sample_tilemax_kernel + sample_select_kernel: per column a value that, with
+//                     overwhelming probability, has at least k column elements above it; the scan
+//                     starts from it instead of -inf, column groups that come up short are rescanned
+//                     exactly (per-column fill counts, only_flagged pass).
+//   short columns     topk_small_kernel: for N <= 16384 rows of an L2-resident matrix an exact radix
+//                     select (thread-block cluster per column group, DSMEM histogram reduction)
+//                     replaces the scan, which would be all start-up there.
 #include <cuda.h>
 #include <cstring>
 
