@@ -318,7 +318,7 @@ def run_ours(args):
     roof = None
     if topk_ms:
         ach = alg_topk / (topk_ms / 1e3) / 1e9
-        roof = {"bound": "hbm", "kernel": "topk_scan_kernel (+topk_finish_kernel), stage timed with CUDA events",
+        roof = {"bound": "hbm", "kernel": "topk_scan_kernel; timed as the whole topk_cols stage (sample_tilemax + sample_select + scan + redo + finish) with CUDA events, so the fraction is a lower bound for the scan kernel itself",
                 "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
                 "traffic": tr.get("topk_scan_kernel"), "peak_source": peak_src, "ms_per_launch": round(topk_ms, 4),
                 "algorithmic_bytes_per_launch": alg_topk}
