@@ -47,7 +47,8 @@
 namespace mcd {
 
 constexpr int kUnitCols = 32;                        // columns per scan warp (= per CTA)
-constexpr int kTileRows = 32;                        // rows per TMA tile
+constexpr int kTileRows = 64;                        // rows per TMA tile
+constexpr int kSampleRows = 32;                      // rows per tile of the sample pass (its own, smaller tiles)
 constexpr int kScanThreads = 32;
 constexpr int kQuads = 4;                            // quarter-warps: quarter q takes rows q, q+4, ..., q+28 of a tile
 constexpr int kListCap = 12;                         // pending slots per (quarter, column) list
@@ -446,7 +447,7 @@ sample_tilemax_kernel(const float *__restrict__ A, int64_t lda, int64_t K, int64
     const int64_t c = int64_t(blockIdx.x) * kSampleCols + lane * 4;
     const int64_t r0 = int64_t(blockIdx.y) * tile_row_stride;
     uint32_t m[4] = {0u, 0u, 0u, 0u};
-    for (int r = warp; r < kTileRows; r += kSampleThreads / 32) {
+    for (int r = warp; r < kSampleRows; r += kSampleThreads / 32) {
         const float *src = A + (r0 + r) * lda + c;
         float v[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
         if (vec_ok && c + 3 < K) {
@@ -825,12 +826,12 @@ static bool make_plan(int64_t N, int64_t K, int64_t k64, TopkPlan *p) {
     const int64_t sms = num_sms();
     // ring depth: enough scan warps per SM (the scan is latency-bound per warp) with a few tiles in flight each
     int nstage = static_cast<int>(tunable(kTopkStages));
-    if (nstage < 2 || nstage > kMaxStages) nstage = 4;      // measured: 2..5 stages are the same speed
+    if (nstage < 2 || nstage > kMaxStages) nstage = 2;      // 2 x 8 KB tiles in flight per warp (measured: depth does not matter)
     p->nstage = nstage;
     p->smem = scan_smem_bytes(nstage);
     int occ = static_cast<int>(kSmemPerSM / (p->smem + kSmemCtaReserve));
-    // registers: the kept set's root group lives in registers (topk_scan_kernel<16|32|64>: 112 / 154 / 235 per thread)
-    const int regs = k <= 128 ? 112 : (k <= 256 ? 160 : 240);
+    // registers: the kept set's root group and a 64-row tile live in registers (topk_scan_kernel<16|32|64>: 158 / 204 / 245)
+    const int regs = k <= 128 ? 160 : (k <= 256 ? 208 : 248);
     if (occ > 65536 / (32 * regs)) occ = 65536 / (32 * regs);
     if (occ > 16) occ = 16;
     if (occ < 1) occ = 1;
@@ -884,11 +885,11 @@ static bool make_plan(int64_t N, int64_t K, int64_t k64, TopkPlan *p) {
             const double lam = double(k) / stride;
             int pk = static_cast<int>(lam + 6.0 * sqrt(lam) + 4.0 + 0.999);
             if (pk < 8) pk = 8;
-            const int64_t ntile = N / (int64_t(kTileRows) * stride);
+            const int64_t ntile = N / (int64_t(kSampleRows) * stride);
             if (pk <= kSelectMaxJ && 4 * ntile >= 5 * pk) {
                 p->pre_stride = stride;
                 p->pre_k = pk;
-                p->pre_rows = ntile * kTileRows;
+                p->pre_rows = ntile * kSampleRows;
                 p->pre_bytes = (size_t(K) * 4 + 255) / 256 * 256 + (size_t(K) * 4 + 255) / 256 * 256 +
                                size_t(ntile) * size_t(K) * 4;          // tau, fill counts, tile maxima
                 break;
@@ -1052,9 +1053,9 @@ extern "C" int mcd_topk_cols_f32(const float *A, int64_t lda, int64_t N, int64_t
         {
             // the sample is one 32-row tile out of every pre_stride tiles
             if (cudaMemsetAsync(flags, 0, size_t(K) * 4, st) != cudaSuccess) return MCD_ERR_CUDA;
-            const int nsample = static_cast<int>(p.pre_rows / kTileRows);
+            const int nsample = static_cast<int>(p.pre_rows / kSampleRows);
             dim3 sgrid(static_cast<unsigned>(ceil_div<int64_t>(K, kSampleCols)), static_cast<unsigned>(nsample));
-            sample_tilemax_kernel<<<sgrid, kSampleThreads, 0, st>>>(A, lda, K, int64_t(kTileRows) * p.pre_stride, 1, tilemax);
+            sample_tilemax_kernel<<<sgrid, kSampleThreads, 0, st>>>(A, lda, K, int64_t(kSampleRows) * p.pre_stride, 1, tilemax);
             rc = check_launch();
             if (rc != MCD_OK) return rc;
             sample_select_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(K, kSelectThreads)), kSelectThreads, 0, st>>>(
