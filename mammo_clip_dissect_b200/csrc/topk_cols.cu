@@ -294,8 +294,8 @@ template <int GROUP>
 __global__ void __launch_bounds__(kScanThreads)
 topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ A, int64_t lda, int64_t N,
                  int64_t K, int k, int nstage, int64_t rows_per_split, unsigned long long *__restrict__ cand,
-                 uint32_t *__restrict__ kept_ws, int feed, const float *__restrict__ tau0, float *__restrict__ tau_out,
-                 int *__restrict__ flags, int only_flagged, int tile_row_stride) {
+                 uint32_t *__restrict__ kept_ws, int feed, const float *__restrict__ tau0, int *__restrict__ flags,
+                 int only_flagged) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // the ring is declared with kMaxStages but only nstage stages are allocated: everything behind it moves up
     ScanSmem &s = *reinterpret_cast<ScanSmem *>(smem_raw - size_t(kMaxStages - nstage) * kTileRows * kUnitCols * 4);
@@ -327,7 +327,7 @@ topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
     if (feed == kFeedTensorTile && lane == 0) {
         for (int t = 0; t < nstage && t < ntiles; ++t) {
             mbar_arrive_expect_tx(&s.full[t], kTileBytes);
-            tma_tile_g2s(ring_addr + t * kTileBytes, &tmap, tx, ty0 + t * tile_row_stride, full_addr + t * 8, policy);
+            tma_tile_g2s(ring_addr + t * kTileBytes, &tmap, tx, ty0 + t * kTileRows, full_addr + t * 8, policy);
         }
     }
     // kept sets start empty; the NaN threshold admits everything until a column has seen k elements
@@ -378,7 +378,7 @@ topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
         if (feed == kFeedTensorTile && lane == 0 && t + nstage < ntiles) {
             fence_proxy_async();                         // generic-proxy reads before the async-proxy refill
             mbar_arrive_expect_tx(&s.full[stage], kTileBytes);
-            tma_tile_g2s(tile_addr, &tmap, tx, ty0 + (t + nstage) * tile_row_stride, full_addr + stage * 8, policy);
+            tma_tile_g2s(tile_addr, &tmap, tx, ty0 + (t + nstage) * kTileRows, full_addr + stage * 8, policy);
         }
         if (++stage == nstage) {
             stage = 0;
@@ -416,8 +416,6 @@ topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
         }
     }
     publish_and_fold<GROUP>(s, kept, lane, k, q, colq, list_first, p0, p1, p2, p3, tau4);
-    if (tau_out != nullptr && lane < ncols)
-        tau_out[c0 + lane] = kept.cnt < k ? __uint_as_float(0x7FC00000u) : key_to_threshold(kept.root_hi);
     if (flags != nullptr && tau0 != nullptr && !only_flagged && lane < ncols) {
         // how many entries this (split, column) collected above the start threshold
         const int have = kept.cnt;
@@ -935,10 +933,8 @@ struct ScanArgs {
     unsigned long long *cand;
     uint32_t *kept;
     const float *tau0;
-    float *tau_out;
     int *flags;
     int only_flagged;
-    int tile_row_stride;      // kTileRows for a real scan; larger for the sample pass (tile t starts at row t * stride)
 };
 
 template <int GROUP>
@@ -947,7 +943,7 @@ static int launch_scan_t(dim3 grid, const TopkPlan &p, const CUtensorMap &map, c
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(p.smem)) != cudaSuccess)
         return MCD_ERR_CUDA;
     kern<<<grid, kScanThreads, p.smem, st>>>(map, a.A, a.lda, a.N, a.K, a.k, p.nstage, a.rows_per_split, a.cand, a.kept,
-                                             a.feed, a.tau0, a.tau_out, a.flags, a.only_flagged, a.tile_row_stride);
+                                             a.feed, a.tau0, a.flags, a.only_flagged);
     return check_launch();
 }
 
@@ -1003,7 +999,7 @@ extern "C" int mcd_topk_cols_f32(const float *A, int64_t lda, int64_t N, int64_t
 
     // short columns of an L2-resident matrix: exact radix select (tunable topk_small: 1 = never, else automatic)
     if (N <= kSmallMaxRows && (N <= 4096 || N * K * 4 <= kSmallMaxBytes) && tunable(kTopkSmall) != 1 && tunable(kTopkSplits) <= 0 &&
-        tunable(kTopkCols) <= 0 && tunable(kTopkVariant) != 1) {
+        tunable(kTopkVariant) != 1) {
         // rows of a column group split over a cluster of R CTAs when the column groups alone would leave SMs idle
         const int64_t ncb_s = ceil_div<int64_t>(K, kUnitCols);
         int R = 1;
@@ -1041,7 +1037,7 @@ extern "C" int mcd_topk_cols_f32(const float *A, int64_t lda, int64_t N, int64_t
     if (feed == kFeedTensorTile && !make_tile_map(&map, A, lda, N, K, kUnitCols, kTileRows)) feed = kFeedElements;
 
     dim3 grid(static_cast<unsigned>(ceil_div<int64_t>(K, kUnitCols)), static_cast<unsigned>(p.splits));
-    ScanArgs main_args{A, lda, N, K, p.rows_per_split, int(k), feed, cand, kept, nullptr, nullptr, nullptr, 0, kTileRows};
+    ScanArgs main_args{A, lda, N, K, p.rows_per_split, int(k), feed, cand, kept, nullptr, nullptr, 0};
     int rc;
     if (p.pre_stride > 0 && feed == kFeedTensorTile) {
         // pass 0: k'-th largest of a 1/32 row sample -> start threshold per column; pass 1: the real scan starting
