@@ -105,3 +105,27 @@ def test_product_does_not_import_the_oracle():
     code = "import sys; import mammo_clip_dissect_b200.similarity, mammo_clip_dissect_b200.hooks, " \
            "mammo_clip_dissect_b200.features; sys.exit(any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules))"
     assert subprocess.run([sys.executable, "-c", code], cwd=os.path.dirname(pkg)).returncode == 0
+
+
+def test_segment_tables_restart_the_lse_blocks_at_every_layer():
+    """Host logic of soft_wpmi_layers: block / segment tables of the stacked call (no GPU needed)."""
+    import math
+    import torch
+    from mammo_clip_dissect_b200 import similarity as sim
+    blocks, segs, logs, n = sim._segment_tables([24, 300, 513, 256], torch.device("cpu"))
+    assert n == 7 and blocks.dtype == torch.int32 and logs.dtype == torch.float64
+    assert blocks.tolist() == [[0, 24, 0], [24, 256, 1], [280, 44, 1], [324, 256, 2], [580, 256, 2], [836, 1, 2],
+                               [837, 256, 3]]
+    assert segs.tolist() == [[0, 1], [1, 2], [3, 3], [6, 1]]
+    assert logs.tolist() == [math.log(24.0), math.log(300.0), math.log(513.0), math.log(256.0)]
+    # rows are covered exactly once, in order
+    assert sum(b[1] for b in blocks.tolist()) == 24 + 300 + 513 + 256
+
+
+def test_activation_stack_and_exchange_refuse_cpu():
+    import pytest
+    from mammo_clip_dissect_b200 import hooks
+    with pytest.raises(RuntimeError):
+        hooks.ActivationStack(10, [4, 5], "cpu")
+    with pytest.raises(ValueError):
+        hooks.ActivationStack(0, [4], "cuda")
