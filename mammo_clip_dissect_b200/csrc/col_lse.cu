@@ -140,7 +140,10 @@ pmi_finalize_bcast_kernel(const float *__restrict__ L, int64_t total, int C, con
         v.y = __fsub_rn(v.y, __fmul_rn(lam, __ldg(prob_d + c1)));
         v.z = __fsub_rn(v.z, __fmul_rn(lam, __ldg(prob_d + c2)));
         v.w = __fsub_rn(v.w, __fmul_rn(lam, __ldg(prob_d + c3)));
-        for (int p = 0; p < n_dst; ++p) reinterpret_cast<float4 *>(dst.ptr[p])[e] = v;
+        // statically indexed (a dynamic index would copy the pointer table to local memory)
+#pragma unroll
+        for (int p = 0; p < kMaxPeers; ++p)
+            if (p < n_dst) reinterpret_cast<float4 *>(dst.ptr[p])[e] = v;
         c += step_c;
         if (c >= C) c -= C;
     }
@@ -148,7 +151,9 @@ pmi_finalize_bcast_kernel(const float *__restrict__ L, int64_t total, int C, con
     if (blockIdx.x == 0 && threadIdx.x < total - nvec * 4) {
         const int64_t i = nvec * 4 + threadIdx.x;
         const float v = __fsub_rn(L[i], __fmul_rn(lam, prob_d[i % C]));
-        for (int p = 0; p < n_dst; ++p) dst.ptr[p][i] = v;
+#pragma unroll
+        for (int p = 0; p < kMaxPeers; ++p)
+            if (p < n_dst) dst.ptr[p][i] = v;
     }
 }
 
