@@ -106,3 +106,21 @@ def test_block_lse_matches_logsumexp():
     L = -400 - 50 * torch.rand(700, 19, generator=g)
     lse = orc.lse_combine(orc.lse_block_partials(L))
     assert torch.allclose(lse, torch.logsumexp(L.double(), dim=0), rtol=0, atol=1e-4)
+
+
+def test_rank_weights_have_the_reference_bits():
+    """The ramp p_r of soft_wpmi (reference similarity.py:58): the values probed from the reference expression
+     and equality of the oracle's and the product's host-side construction."""
+    import torch
+    from mammo_clip_dissect_b200.similarity import _reference_ramp
+    from oracle import similarity_oracle as orc
+    p = _reference_ramp(100, 0.998, 0.97)
+    assert p.dtype == torch.float32 and p.shape == (100,)
+    probed = {0: "0x1.fef9dcp-1", 1: "0x1.fed528p-1", 50: "0x1.f7cedap-1", 99: "0x1.f0c88cp-1"}
+    for r, h in probed.items():
+        assert float(p[r]) == float.fromhex(h), (r, float(p[r]).hex(), h)
+    assert torch.equal(p, orc.p_ramp(100, 0.998, 0.97).to(torch.float32).reshape(-1))
+    ref = 0.998 - torch.arange(start=0, end=100) / 100 * (0.998 - 0.97)         # the reference's expression, verbatim
+    assert torch.equal(p, ref.to(torch.float32))
+    for k, ps, pe in ((28, 0.9, 0.5), (1, 0.998, 0.97), (7, 1.0, 0.0)):
+        assert torch.equal(_reference_ramp(k, ps, pe), orc.p_ramp(k, ps, pe).to(torch.float32).reshape(-1))
