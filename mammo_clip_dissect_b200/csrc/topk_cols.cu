@@ -361,7 +361,7 @@ topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
     for (int t = 0; t < ntiles; ++t, row_tile += kTileRows) {
         const uint32_t tile_addr = ring_addr + stage * kTileBytes;
         if (feed == kFeedTensorTile) {
-            mbar_wait(&s.full[stage], use & 1);
+            mbar_wait_addr(full_addr + stage * 8, use & 1);
         } else {
             // base pointer / row pitch not 16-byte aligned: the warp copies the tile itself
             const int rows_here = min(kTileRows, nrows - t * kTileRows);
@@ -377,7 +377,7 @@ topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
         __syncwarp();                                    // every lane has the tile's rows in registers
         if (feed == kFeedTensorTile && lane == 0 && t + nstage < ntiles) {
             fence_proxy_async();                         // generic-proxy reads before the async-proxy refill
-            mbar_arrive_expect_tx(&s.full[stage], kTileBytes);
+            mbar_arrive_expect_tx_addr(full_addr + stage * 8, kTileBytes);
             tma_tile_g2s(tile_addr, &tmap, tx, ty0 + (t + nstage) * kTileRows, full_addr + stage * 8, policy);
         }
         if (++stage == nstage) {
