@@ -61,6 +61,7 @@ int mcd_softmax_rows_f32(const float *P, int64_t ldp, float *S, int64_t lds,
  *      (+ similarity.py:54).  I [N,D] (ldi), T [C,D] (ldt).  P_out and/or S_out may be NULL.
  *      Tensor-core path: tcgen05 kind::tf32 with a 3-term hi/lo split (fp32-grade result). */
 size_t mcd_gemm_nt_softmax_workspace_bytes(int64_t N, int64_t C, int64_t D);
+int mcd_last_gemm_path(void);          /* what the last K1 call ran: 1 tcgen05 3xTF32, 2 tcgen05 with fused softmax, 3 fp32 FFMA */
 int mcd_gemm_nt_softmax_f32(const float *I, int64_t ldi, const float *T, int64_t ldt,
                             int64_t N, int64_t C, int64_t D, int normalize_rows, float a,
                             float *P_out, int64_t ldp, float *S_out, int64_t lds,
@@ -104,6 +105,17 @@ int mcd_pmi_scores_f32(const float *P, int64_t ldp, const float *A, int64_t lda,
                        int64_t C, int64_t k, float a, float lam, const float *p, float min_prob,
                        float *out, int64_t ldo, void *workspace, size_t workspace_bytes,
                        mcd_stream_t stream);
+
+/* ---- the same call up to the log-sums (what one rank of the neuron-sharded multi-GPU call runs before the partials
+ *      are exchanged): L [K, C] (ldl) and the 256-neuron block partials [ceil(K/256), 2, C].
+ *      Workspace as for mcd_pmi_scores_f32.  For long columns (N >= 8192) and K >= 8192 the neurons are cut into a few
+ *      column chunks and chunk q's select + K3 + partials run on a library-owned side stream under K2's scan of chunk
+ *      q + 1 (the side stream and its events are created once per device on first use; the call still only enqueues
+ *      work and everything is ordered behind `stream` on return).  mcd_pmi_scores_f32 = this + mcd_pmi_finalize_f32. */
+int mcd_pmi_logsums_f32(const float *P, int64_t ldp, const float *A, int64_t lda, int64_t N, int64_t K,
+                        int64_t C, int64_t k, float a, const float *p, float min_prob,
+                        float *L, int64_t ldl, float *partials, void *workspace, size_t workspace_bytes,
+                        mcd_stream_t stream);
 
 /* ---- K3b for several layers stacked along the neuron axis of one [sum K_l, C] matrix (SURVEY.md 8 f1:
  *      the 12-39 layers of a real job in one pass of every kernel).  Same arithmetic, block by

@@ -28,6 +28,7 @@ SIGNATURES = {
     "mcd_device_check": (_i32, []),
     "mcd_set_tunable": (_i32, [_c.c_char_p, _i64]),
     "mcd_softmax_rows_f32": (_i32, [_p, _i64, _p, _i64, _i64, _i64, _f32, _p]),
+    "mcd_last_gemm_path": (_i32, []),
     "mcd_gemm_nt_softmax_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "mcd_gemm_nt_softmax_f32": (_i32, [_p, _i64, _p, _i64, _i64, _i64, _i64, _i32, _f32, _p, _i64, _p, _i64, _p, _sz, _p]),
     "mcd_topk_cols_workspace_bytes": (_sz, [_i64, _i64, _i64]),
@@ -38,6 +39,7 @@ SIGNATURES = {
     "mcd_pmi_finalize_bcast_f32": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _f32, _p, _p, _i32, _i64, _p]),
     "mcd_pmi_scores_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64]),
     "mcd_pmi_scores_f32": (_i32, [_p, _i64, _p, _i64, _i64, _i64, _i64, _i64, _f32, _f32, _p, _f32, _p, _i64, _p, _sz, _p]),
+    "mcd_pmi_logsums_f32": (_i32, [_p, _i64, _p, _i64, _i64, _i64, _i64, _i64, _f32, _p, _f32, _p, _i64, _p, _p, _sz, _p]),
     "mcd_col_lse_partials_seg_f32": (_i32, [_p, _i64, _i64, _p, _i64, _p, _p]),
     "mcd_pmi_finalize_seg_f32": (_i32, [_p, _i64, _i64, _p, _p, _i64, _p, _p, _i64, _f32, _p, _p, _i64, _p]),
     "mcd_row_topk_f32": (_i32, [_p, _i64, _i64, _i64, _i64, _p, _p, _p]),

@@ -1,8 +1,10 @@
 // Library-level entry points of include/mcd_b200.h: version, errors, launch accounting, tunables.
 #include <atomic>
 #include <cstring>
+#include <mutex>
 
 #include "common.cuh"
+#include "topk_api.cuh"
 
 namespace mcd {
 
@@ -58,9 +60,10 @@ int mcd_device_check(void) {
 }
 
 int mcd_set_tunable(const char *name, int64_t value) {
-    static const char *names[] = {"topk_splits", "accum_tile", "topk_variant", "accum_unroll", "topk_cols", "topk_stages", "topk_occ", "gemm_variant", "topk_pre", "topk_small"};
+    static const char *names[] = {"topk_splits", "accum_tile", "topk_variant", "accum_unroll", "topk_cols", "topk_stages", "topk_occ", "gemm_variant", "topk_pre", "topk_small", "topk_filter", "filter_stages", "filter_chunk_tiles", "pipe_chunks"};
+    constexpr int n_names = sizeof(names) / sizeof(names[0]);
     if (!name) return MCD_ERR_INVALID_ARGUMENT;
-    for (int i = 0; i < 10; ++i)
+    for (int i = 0; i < n_names; ++i)
         if (std::strcmp(name, names[i]) == 0) {
             mcd::g_tunables[i].store(value, std::memory_order_relaxed);
             return MCD_OK;
@@ -99,6 +102,129 @@ extern "C" size_t mcd_pmi_scores_workspace_bytes(int64_t N, int64_t K, int64_t C
     return l.total;
 }
 
+namespace {
+
+// ---- column-chunk pipeline -------------------------------------------------------------------------------------------
+// The filter scan of K2 is HBM-bound and leaves most issue slots of an SM idle; the gather / log-sum of K3 is L2-bound.
+// With the neurons cut into a few column chunks, chunk q's select + K3 + LSE partials run on a side stream under the scan
+// of chunk q + 1 (and the softmax under the sample pass and the first scan), so that only the last, smallest chunk's K3
+// is exposed.  The side stream and the events are created once per device, on first use.
+constexpr int kMaxPipeChunks = 8;
+struct PipeRes {
+    cudaStream_t side = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr, scanned[kMaxPipeChunks] = {};
+    bool ok = false, tried = false;
+};
+std::mutex g_pipe_mu;
+PipeRes g_pipe[64];
+
+PipeRes *pipe_resources() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(g_pipe_mu);
+    PipeRes &r = g_pipe[dev];
+    if (!r.tried) {
+        r.tried = true;
+        bool ok = cudaStreamCreateWithFlags(&r.side, cudaStreamNonBlocking) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&r.fork, cudaEventDisableTiming) == cudaSuccess;
+        ok = ok && cudaEventCreateWithFlags(&r.join, cudaEventDisableTiming) == cudaSuccess;
+        for (int i = 0; ok && i < kMaxPipeChunks; ++i)
+            ok = cudaEventCreateWithFlags(&r.scanned[i], cudaEventDisableTiming) == cudaSuccess;
+        r.ok = ok;
+    }
+    return r.ok ? &r : nullptr;
+}
+
+// chunk boundaries (multiples of the 256-neuron LSE block) with geometrically shrinking widths: chunk q's K3 has to fit
+// under the scan of chunk q + 1, and the last chunk's K3 is the exposed tail
+int pipe_bounds(int64_t K, int64_t *bounds) {
+    int64_t q = mcd::tunable(mcd::kPipeChunks);
+    const int64_t units = (K + MCD_LSE_BLOCK - 1) / MCD_LSE_BLOCK;
+    if (q <= 0) q = K >= 8192 ? 4 : 1;
+    if (q > kMaxPipeChunks) q = kMaxPipeChunks;
+    if (q > units) q = units;
+    bounds[0] = 0;
+    if (q <= 1) {
+        bounds[1] = K;
+        return 1;
+    }
+    double w[kMaxPipeChunks], sum = 0.0, x = 1.0;
+    for (int i = 0; i < q; ++i, x *= 0.72) sum += (w[i] = x);
+    double acc = 0.0;
+    int n = 0;
+    for (int i = 0; i < q; ++i) {
+        acc += w[i] / sum;
+        int64_t b = i == q - 1 ? units : static_cast<int64_t>(acc * double(units) + 0.5);
+        if (b > units) b = units;
+        if (b * MCD_LSE_BLOCK > bounds[n]) bounds[++n] = b * MCD_LSE_BLOCK < K ? b * MCD_LSE_BLOCK : K;
+    }
+    bounds[n] = K;
+    return n;
+}
+
+// softmax -> column top-k -> gather / log-sum -> 256-neuron block partials; L [K, C] and partials are outputs
+int pmi_logsums(const float *P, int64_t ldp, const float *A, int64_t lda, int64_t N, int64_t K, int64_t C, int64_t k,
+                float a, const float *p, float min_prob, float *L, int64_t ldl, float *part, const PmiLayout &l, char *w,
+                size_t workspace_bytes, mcd_stream_t stream) {
+    using namespace mcd;
+    float *S = reinterpret_cast<float *>(w + l.s_off);
+    int32_t *idx = reinterpret_cast<int32_t *>(w + l.idx_off);
+    cudaStream_t main = static_cast<cudaStream_t>(stream);
+    TopkFilterCall call;
+    int64_t bounds[kMaxPipeChunks + 1];
+    const int nq = pipe_bounds(K, bounds);
+    // tunable pipe_chunks: 0 = automatic, n > 0 = n chunks (1: only the softmax runs beside the scan), -1 = one stream
+    PipeRes *pr = tunable(kPipeChunks) >= 0 ? pipe_resources() : nullptr;
+    int rc = pr ? topk_filter_prepare(A, lda, N, K, k, w + l.topk_off, workspace_bytes - l.topk_off, &call) : MCD_ERR_UNSUPPORTED;
+    if (rc != MCD_OK && rc != MCD_ERR_UNSUPPORTED) return rc;
+    if (rc == MCD_ERR_UNSUPPORTED) {
+        // one stream, stage after stage
+        rc = mcd_softmax_rows_f32(P, ldp, S, l.lds, N, C, a, stream);
+        if (rc != MCD_OK) return rc;
+        rc = mcd_topk_cols_f32(A, lda, N, K, k, nullptr, idx, nullptr, w + l.topk_off, workspace_bytes - l.topk_off, stream);
+        if (rc != MCD_OK) return rc;
+        rc = mcd_wpmi_accum_f32(S, l.lds, N, C, idx, K, k, p, min_prob, L, ldl, stream);
+        if (rc != MCD_OK) return rc;
+        return mcd_col_lse_partials_f32(L, ldl, K, C, part, stream);
+    }
+    cudaStream_t side = pr->side;
+    if (cudaEventRecord(pr->fork, main) != cudaSuccess || cudaStreamWaitEvent(side, pr->fork, 0) != cudaSuccess) return MCD_ERR_CUDA;
+    rc = mcd_softmax_rows_f32(P, ldp, S, l.lds, N, C, a, side);
+    if (rc != MCD_OK) return rc;
+    rc = topk_filter_begin(call, main);
+    if (rc != MCD_OK) return rc;
+    for (int q = 0; q < nq; ++q) {
+        const int64_t c0 = bounds[q], c1 = bounds[q + 1];
+        rc = topk_filter_scan(call, c0, c1, q, main);
+        if (rc != MCD_OK) return rc;
+        if (cudaEventRecord(pr->scanned[q], main) != cudaSuccess || cudaStreamWaitEvent(side, pr->scanned[q], 0) != cudaSuccess)
+            return MCD_ERR_CUDA;
+        rc = topk_filter_finish(call, c0, c1, nullptr, idx, nullptr, side);
+        if (rc != MCD_OK) return rc;
+        rc = wpmi_accum_range(S, l.lds, N, C, idx + c0, K, c1 - c0, k, p, min_prob, L + c0 * ldl, ldl, side);
+        if (rc != MCD_OK) return rc;
+        rc = mcd_col_lse_partials_f32(L + c0 * ldl, ldl, c1 - c0, C, part + (c0 / MCD_LSE_BLOCK) * 2 * C, side);
+        if (rc != MCD_OK) return rc;
+    }
+    if (cudaEventRecord(pr->join, side) != cudaSuccess || cudaStreamWaitEvent(main, pr->join, 0) != cudaSuccess) return MCD_ERR_CUDA;
+    return MCD_OK;
+}
+
+}  // namespace
+
+extern "C" int mcd_pmi_logsums_f32(const float *P, int64_t ldp, const float *A, int64_t lda, int64_t N, int64_t K,
+                                   int64_t C, int64_t k, float a, const float *p, float min_prob, float *L, int64_t ldl,
+                                   float *partials, void *workspace, size_t workspace_bytes, mcd_stream_t stream) {
+    if (!P || !A || !L || !partials || !workspace || N < 1 || K < 1 || C < 1 || k < 1 || k > N || ldp < C || lda < K || ldl < C)
+        return MCD_ERR_INVALID_ARGUMENT;
+    PmiLayout l;
+    if (!pmi_layout(N, K, C, k, &l)) return MCD_ERR_UNSUPPORTED;
+    if (workspace_bytes < l.total) return MCD_ERR_WORKSPACE;
+    if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0) return MCD_ERR_INVALID_ARGUMENT;
+    return pmi_logsums(P, ldp, A, lda, N, K, C, k, a, p, min_prob, L, ldl, partials, l, static_cast<char *>(workspace),
+                       workspace_bytes, stream);
+}
+
 extern "C" int mcd_pmi_scores_f32(const float *P, int64_t ldp, const float *A, int64_t lda, int64_t N, int64_t K,
                                   int64_t C, int64_t k, float a, float lam, const float *p, float min_prob, float *out,
                                   int64_t ldo, void *workspace, size_t workspace_bytes, mcd_stream_t stream) {
@@ -109,17 +235,9 @@ extern "C" int mcd_pmi_scores_f32(const float *P, int64_t ldp, const float *A, i
     if (workspace_bytes < l.total) return MCD_ERR_WORKSPACE;
     if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0) return MCD_ERR_INVALID_ARGUMENT;
     char *w = static_cast<char *>(workspace);
-    float *S = reinterpret_cast<float *>(w + l.s_off);
-    int32_t *idx = reinterpret_cast<int32_t *>(w + l.idx_off);
     float *part = reinterpret_cast<float *>(w + l.part_off);
     float *prob_d = reinterpret_cast<float *>(w + l.probd_off);
-    int rc = mcd_softmax_rows_f32(P, ldp, S, l.lds, N, C, a, stream);
-    if (rc != MCD_OK) return rc;
-    rc = mcd_topk_cols_f32(A, lda, N, K, k, nullptr, idx, nullptr, w + l.topk_off, workspace_bytes - l.topk_off, stream);
-    if (rc != MCD_OK) return rc;
-    rc = mcd_wpmi_accum_f32(S, l.lds, N, C, idx, K, k, p, min_prob, out, ldo, stream);
-    if (rc != MCD_OK) return rc;
-    rc = mcd_col_lse_partials_f32(out, ldo, K, C, part, stream);
+    int rc = pmi_logsums(P, ldp, A, lda, N, K, C, k, a, p, min_prob, out, ldo, part, l, w, workspace_bytes, stream);
     if (rc != MCD_OK) return rc;
     return mcd_pmi_finalize_f32(out, ldo, K, C, part, (K + MCD_LSE_BLOCK - 1) / MCD_LSE_BLOCK, K, lam, prob_d, out, ldo,
                                 stream);

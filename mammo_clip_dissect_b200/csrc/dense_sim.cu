@@ -200,11 +200,14 @@ size_t sim_matrix_tc_workspace(int64_t N, int64_t C, int64_t D);                
 int sim_matrix_tc(const float *I, int64_t ldi, const float *T, int64_t ldt, int64_t N, int64_t C, int64_t D,
                   int normalize_rows, float *P, int64_t ldp, float *S, int64_t lds, float a, void *ws, size_t ws_bytes,
                   cudaStream_t st);
+static int g_last_gemm_path = 0;        // what the last mcd_gemm_nt_softmax_f32 call ran (mcd_last_gemm_path)
 static size_t gemm_base_workspace(int64_t N, int64_t C) {
     const size_t ldp = size_t(ceil_div<int64_t>(C, 4) * 4);
     return ((size_t(N) + size_t(C)) * sizeof(float) + 255) / 256 * 256 + size_t(N) * ldp * sizeof(float) + 256;
 }
 }  // namespace mcd
+
+extern "C" int mcd_last_gemm_path(void) { return mcd::g_last_gemm_path; }
 
 extern "C" size_t mcd_gemm_nt_softmax_workspace_bytes(int64_t N, int64_t C, int64_t D) {
     if (N < 1 || C < 1 || D < 1) return 0;
@@ -240,9 +243,13 @@ extern "C" int mcd_gemm_nt_softmax_f32(const float *I, int64_t ldi, const float 
         fused = S_out != nullptr && variant == 3;
         rc = sim_matrix_tc(I, ldi, T, ldt, N, C, D, normalize_rows, P, ld, fused ? S_out : nullptr, lds, a, tc_ws,
                            workspace_bytes - gemm_base_workspace(N, C), st);
+        if (rc == MCD_OK) g_last_gemm_path = fused ? 2 : 1;
         if (rc == MCD_OK && fused) return rc;
     }
-    if (rc == MCD_ERR_UNSUPPORTED) rc = sim_matrix_fp32(I, ldi, T, ldt, N, C, D, normalize_rows, P, ld, norms, st);
+    if (rc == MCD_ERR_UNSUPPORTED) {
+        rc = sim_matrix_fp32(I, ldi, T, ldt, N, C, D, normalize_rows, P, ld, norms, st);
+        if (rc == MCD_OK) g_last_gemm_path = 3;
+    }
     if (rc != MCD_OK || !S_out) return rc;
     return mcd_softmax_rows_f32(P, ld, S_out, lds, N, C, a, stream);
 }

@@ -40,9 +40,11 @@
 //                     select (thread-block cluster per column group, DSMEM histogram reduction)
 //                     replaces the scan, which would be all start-up there.
 #include <cuda.h>
+#include <cmath>
 #include <cstring>
 
 #include "common.cuh"
+#include "topk_api.cuh"
 
 namespace mcd {
 
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(kScanThreads)
 topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restrict__ A, int64_t lda, int64_t N,
                  int64_t K, int k, int nstage, int64_t rows_per_split, unsigned long long *__restrict__ cand,
                  uint32_t *__restrict__ kept_ws, int feed, const float *__restrict__ tau0, int *__restrict__ flags,
-                 int only_flagged) {
+                 int only_flagged, int group0) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // the ring is declared with kMaxStages but only nstage stages are allocated: everything behind it moves up
     ScanSmem &s = *reinterpret_cast<ScanSmem *>(smem_raw - size_t(kMaxStages - nstage) * kTileRows * kUnitCols * 4);
@@ -303,7 +305,7 @@ topk_scan_kernel(const __grid_constant__ CUtensorMap tmap, const float *__restri
     constexpr uint32_t kTileBytes = kTileRows * kUnitCols * 4;
 
     const int lane = threadIdx.x;
-    const int64_t c0 = int64_t(blockIdx.x) * kUnitCols;
+    const int64_t c0 = (int64_t(blockIdx.x) + group0) * kUnitCols;      // group0: first column group of a range launch
     const int ncols = static_cast<int>(min(int64_t(kUnitCols), K - c0));
     // second pass of the pre-threshold scheme: only column groups with a column that collected fewer than k elements
     // (over all splits) above its start threshold are redone, exactly, without one
@@ -512,11 +514,13 @@ constexpr int kFinishWarps = 4;
 __global__ void __launch_bounds__(kFinishWarps * 32)
 topk_finish_kernel(const unsigned long long *__restrict__ cand, int M, int Mpad, int k, int64_t K,
                    const float *__restrict__ A, int64_t lda, int64_t *__restrict__ idx64,
-                   int32_t *__restrict__ idx32, float *__restrict__ vals) {
+                   int32_t *__restrict__ idx32, float *__restrict__ vals, int64_t col_first, int64_t col_end,
+                   const int *__restrict__ redo_flags) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t col = int64_t(blockIdx.x) * kFinishWarps + warp;
-    if (col >= K) return;
+    const int64_t col = col_first + int64_t(blockIdx.x) * kFinishWarps + warp;
+    if (col >= col_end) return;
+    if (redo_flags && redo_flags[col] >= k) return;      // resolved by the select kernel: only flagged columns are redone
     unsigned long long *buf = reinterpret_cast<unsigned long long *>(smem_raw) + size_t(warp) * Mpad;
     for (int i = lane; i < Mpad; i += 32) buf[i] = i < M ? cand[int64_t(i) * K + col] : 0ull;
     __syncwarp();
@@ -555,11 +559,13 @@ template <int PER>
 __global__ void __launch_bounds__(kFinishRegWarps * 32)
 topk_finish_reg_kernel(const unsigned long long *__restrict__ cand, int M, int k, int64_t K,
                        const float *__restrict__ A, int64_t lda, int64_t *__restrict__ idx64,
-                       int32_t *__restrict__ idx32, float *__restrict__ vals) {
+                       int32_t *__restrict__ idx32, float *__restrict__ vals, int64_t col_first, int64_t col_end,
+                       const int *__restrict__ redo_flags) {
     constexpr int TOTAL = 32 * PER;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t col = int64_t(blockIdx.x) * kFinishRegWarps + warp;
-    if (col >= K) return;
+    const int64_t col = col_first + int64_t(blockIdx.x) * kFinishRegWarps + warp;
+    if (col >= col_end) return;
+    if (redo_flags && redo_flags[col] >= k) return;
     unsigned long long v[PER];
 #pragma unroll
     for (int e = 0; e < PER; ++e) {
@@ -803,20 +809,14 @@ topk_small_kernel(const float *__restrict__ A, int64_t lda, int N, int64_t K, in
     cluster_sync_all();                         // nobody leaves while its shared memory may still be addressed
 }
 
+}  // namespace mcd
+
+#include "topk_filter.cuh"
+
+namespace mcd {
+
 // ---- host side ----------------------------------------------------------------------------------
 constexpr size_t kSmemPerSM = 228 * 1024, kSmemCtaReserve = 1024;
-
-struct TopkPlan {
-    int nstage, occ, splits, mpad;
-    int64_t rows_per_split;
-    size_t smem;
-    size_t cand_bytes, kept_bytes;      // workspace: candidates [splits*k][K], then one kept region per scan warp
-    // pre-threshold pass (single-split scans of long columns): every pre_stride-th row, k-th largest = pre_k
-    int pre_stride, pre_k;
-    int64_t pre_rows;
-    size_t pre_bytes;                   // tau [K] floats, flags [ncb] ints, kept regions of the pre-pass
-};
-
 
 static bool make_plan(int64_t N, int64_t K, int64_t k64, TopkPlan *p) {
     if (k64 < 1 || k64 > 512) return false;     // kept-set groups: 8 x 64 entries at most
@@ -894,7 +894,46 @@ static bool make_plan(int64_t N, int64_t K, int64_t k64, TopkPlan *p) {
             }
         }
     }
+    // Filter form (topk_filter.cuh) for long columns: survivor lists sized for the expected pre_k * pre_stride
+    // elements above the start threshold plus 7 standard deviations (the count of column elements above the j-th
+    // largest of a 1/stride sample has relative spread ~ 1/sqrt(j)); an overflowing column is redone exactly.
+    p->filter = 0;
+    p->f_cap = p->f_chunk_tiles = p->f_chunks = p->f_nstage = 0;
+    p->f_cnt_bytes = p->f_list_bytes = 0;
+    if (p->pre_stride > 0 && N < (int64_t(1) << 30) && tunable(kTopkFilter) != 1 && tunable(kTopkVariant) == 0 &&
+        tunable(kTopkSplits) <= 0) {
+        const double mean = double(p->pre_k) * p->pre_stride;
+        int cap = static_cast<int>(mean * (1.0 + 7.0 / sqrt(double(p->pre_k)))) + 31;
+        if (cap < 2 * k + 64) cap = 2 * k + 64;
+        cap = cap / 32 * 32;
+        const size_t list_bytes = size_t(K) * size_t(cap) * 8;
+        if (list_bytes <= (size_t(16) << 30)) {
+            p->filter = 1;
+            p->f_cap = cap;
+            int ns = static_cast<int>(tunable(kFilterStages));
+            if (ns < 2 || ns > kFMaxStages) ns = 6;
+            p->f_nstage = ns;
+            const int64_t tiles_total = ceil_div<int64_t>(N, kFRows), nblk = ceil_div<int64_t>(K, kFCols);
+            int64_t ct = tunable(kFilterChunkTiles);
+            if (ct <= 0) ct = ceil_div<int64_t>(tiles_total * nblk, sms * 64);     // ~64 work items per SM
+            if (ct < 4) ct = 4;
+            if (ct > tiles_total) ct = tiles_total;
+            p->f_chunk_tiles = static_cast<int>(ct);
+            p->f_chunks = static_cast<int>(ceil_div<int64_t>(tiles_total, ct));
+            p->f_cnt_bytes = ((size_t(K) + kFMaxLaunches) * 4 + 255) / 256 * 256;
+            p->f_list_bytes = (list_bytes + 255) / 256 * 256;
+        }
+    }
     return true;
+}
+
+static size_t plan_pre_bytes_aligned(const TopkPlan &p) { return (p.pre_bytes + 255) / 256 * 256; }
+static size_t plan_total_bytes(const TopkPlan &p) {
+    return p.cand_bytes + p.kept_bytes + plan_pre_bytes_aligned(p) + p.f_cnt_bytes + p.f_list_bytes;
+}
+static bool takes_small_path(int64_t N, int64_t K) {
+    return N <= kSmallMaxRows && (N <= 4096 || N * K * 4 <= kSmallMaxBytes) && tunable(kTopkSmall) != 1 &&
+           tunable(kTopkSplits) <= 0 && tunable(kTopkVariant) != 1;
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -935,6 +974,7 @@ struct ScanArgs {
     const float *tau0;
     int *flags;
     int only_flagged;
+    int group0;          // first 32-column group of a range launch (grid.x counts from it)
 };
 
 template <int GROUP>
@@ -943,7 +983,7 @@ static int launch_scan_t(dim3 grid, const TopkPlan &p, const CUtensorMap &map, c
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(p.smem)) != cudaSuccess)
         return MCD_ERR_CUDA;
     kern<<<grid, kScanThreads, p.smem, st>>>(map, a.A, a.lda, a.N, a.K, a.k, p.nstage, a.rows_per_split, a.cand, a.kept,
-                                             a.feed, a.tau0, a.flags, a.only_flagged);
+                                             a.feed, a.tau0, a.flags, a.only_flagged, a.group0);
     return check_launch();
 }
 
@@ -956,24 +996,130 @@ static int launch_scan(dim3 grid, const TopkPlan &p, const CUtensorMap &map, con
 }
 
 static int launch_finish(const TopkPlan &p, const unsigned long long *cand, int k, int64_t K, const float *A, int64_t lda,
-                         int64_t *idx64_out, int32_t *idx32_out, float *vals_out, cudaStream_t st) {
+                         int64_t *idx64_out, int32_t *idx32_out, float *vals_out, cudaStream_t st, int64_t col_first = 0,
+                         int64_t col_end = -1, const int *redo_flags = nullptr) {
+    if (col_end < 0) col_end = K;
+    const int64_t ncol = col_end - col_first;
+    if (ncol <= 0) return MCD_OK;
     if (p.mpad <= 256 && tunable(kTopkVariant) != 2) {
-        const unsigned fgrid = static_cast<unsigned>(ceil_div<int64_t>(K, kFinishRegWarps));
+        const unsigned fgrid = static_cast<unsigned>(ceil_div<int64_t>(ncol, kFinishRegWarps));
         if (p.mpad <= 128)
-            topk_finish_reg_kernel<4><<<fgrid, kFinishRegWarps * 32, 0, st>>>(cand, p.splits * k, k, K, A, lda,
-                                                                              idx64_out, idx32_out, vals_out);
+            topk_finish_reg_kernel<4><<<fgrid, kFinishRegWarps * 32, 0, st>>>(cand, p.splits * k, k, K, A, lda, idx64_out, idx32_out,
+                                                                              vals_out, col_first, col_end, redo_flags);
         else
-            topk_finish_reg_kernel<8><<<fgrid, kFinishRegWarps * 32, 0, st>>>(cand, p.splits * k, k, K, A, lda,
-                                                                              idx64_out, idx32_out, vals_out);
+            topk_finish_reg_kernel<8><<<fgrid, kFinishRegWarps * 32, 0, st>>>(cand, p.splits * k, k, K, A, lda, idx64_out, idx32_out,
+                                                                              vals_out, col_first, col_end, redo_flags);
         return check_launch();
     }
     const size_t fsmem = size_t(kFinishWarps) * p.mpad * sizeof(unsigned long long);
     if (cudaFuncSetAttribute(topk_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fsmem)) != cudaSuccess)
         return MCD_ERR_CUDA;
-    const unsigned fgrid = static_cast<unsigned>(ceil_div<int64_t>(K, kFinishWarps));
-    topk_finish_kernel<<<fgrid, kFinishWarps * 32, fsmem, st>>>(cand, p.splits * k, p.mpad, k, K, A, lda,
-                                                                idx64_out, idx32_out, vals_out);
+    const unsigned fgrid = static_cast<unsigned>(ceil_div<int64_t>(ncol, kFinishWarps));
+    topk_finish_kernel<<<fgrid, kFinishWarps * 32, fsmem, st>>>(cand, p.splits * k, p.mpad, k, K, A, lda, idx64_out, idx32_out,
+                                                                vals_out, col_first, col_end, redo_flags);
     return check_launch();
+}
+
+// ---- filter form: prepare / begin / scan / finish (topk_api.cuh) ------------------------------------------------------
+int topk_filter_prepare(const float *A, int64_t lda, int64_t N, int64_t K, int64_t k, void *workspace,
+                        size_t workspace_bytes, TopkFilterCall *c) {
+    if (!A || N < 1 || K < 1 || k < 1 || k > N || lda < K || N >= 0x7FFFFFFFll) return MCD_ERR_INVALID_ARGUMENT;
+    TopkPlan p;
+    if (!make_plan(N, K, k, &p)) return MCD_ERR_UNSUPPORTED;
+    if (!p.filter || takes_small_path(N, K)) return MCD_ERR_UNSUPPORTED;
+    const bool aligned = (lda % 4 == 0) && (reinterpret_cast<uintptr_t>(A) % 16 == 0);
+    if (!aligned) return MCD_ERR_UNSUPPORTED;
+    if (!workspace || workspace_bytes < plan_total_bytes(p)) return MCD_ERR_WORKSPACE;
+    if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0) return MCD_ERR_INVALID_ARGUMENT;
+    memset(&c->map_filter, 0, sizeof(CUtensorMap));
+    memset(&c->map_scan, 0, sizeof(CUtensorMap));
+    if (!make_tile_map(&c->map_filter, A, lda, N, K, kFCols, kFRows) || !make_tile_map(&c->map_scan, A, lda, N, K, kUnitCols, kTileRows))
+        return MCD_ERR_UNSUPPORTED;
+    c->plan = p;
+    c->A = A;
+    c->lda = lda;
+    c->N = N;
+    c->K = K;
+    c->k = static_cast<int>(k);
+    char *w = static_cast<char *>(workspace);
+    c->cand = reinterpret_cast<unsigned long long *>(w);
+    c->kept = reinterpret_cast<uint32_t *>(w + p.cand_bytes);
+    char *pre = w + p.cand_bytes + p.kept_bytes;
+    c->tau = reinterpret_cast<float *>(pre);
+    c->flags = reinterpret_cast<int *>(pre + (size_t(K) * 4 + 255) / 256 * 256);
+    c->tilemax = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(c->flags) + (size_t(K) * 4 + 255) / 256 * 256);
+    c->cnt = reinterpret_cast<int *>(pre + plan_pre_bytes_aligned(p));
+    c->lists = reinterpret_cast<unsigned long long *>(reinterpret_cast<char *>(c->cnt) + p.f_cnt_bytes);
+    return MCD_OK;
+}
+
+int topk_filter_begin(const TopkFilterCall &c, cudaStream_t st) {
+    const TopkPlan &p = c.plan;
+    if (cudaMemsetAsync(c.cnt, 0, (size_t(c.K) + kFMaxLaunches) * 4, st) != cudaSuccess) return MCD_ERR_CUDA;
+    const int nsample = static_cast<int>(p.pre_rows / kSampleRows);
+    dim3 sgrid(static_cast<unsigned>(ceil_div<int64_t>(c.K, kSampleCols)), static_cast<unsigned>(nsample));
+    sample_tilemax_kernel<<<sgrid, kSampleThreads, 0, st>>>(c.A, c.lda, c.K, int64_t(kSampleRows) * p.pre_stride, 1, c.tilemax);
+    int rc = check_launch();
+    if (rc != MCD_OK) return rc;
+    sample_select_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(c.K, kSelectThreads)), kSelectThreads, 0, st>>>(
+        c.tilemax, nsample, c.K, p.pre_k, c.tau);
+    return check_launch();
+}
+
+int topk_filter_scan(const TopkFilterCall &c, int64_t col0, int64_t col1, int launch_id, cudaStream_t st) {
+    const TopkPlan &p = c.plan;
+    if (col0 % kFCols != 0 || col1 <= col0 || col1 > c.K || launch_id < 0 || launch_id >= kFMaxLaunches)
+        return MCD_ERR_INVALID_ARGUMENT;
+    FilterArgs a;
+    a.N = c.N;
+    a.K = c.K;
+    a.col_block0 = static_cast<int>(col0 / kFCols);
+    a.n_col_blocks = static_cast<int>(ceil_div<int64_t>(col1 - col0, kFCols));
+    a.chunk_tiles = p.f_chunk_tiles;
+    a.n_chunks = p.f_chunks;
+    a.nstage = p.f_nstage;
+    a.cap = p.f_cap;
+    a.tau = c.tau;
+    a.cnt = c.cnt;
+    a.lists = c.lists;
+    a.item_ctr = c.cnt + c.K + launch_id;
+    const size_t smem = filter_smem_bytes(p.f_nstage);
+    if (cudaFuncSetAttribute(filter_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
+        return MCD_ERR_CUDA;
+    const int64_t items = int64_t(a.n_col_blocks) * a.n_chunks;
+    const unsigned grid = static_cast<unsigned>(items < num_sms() ? items : num_sms());
+    filter_scan_kernel<<<grid, kFThreads, smem, st>>>(c.map_filter, a);
+    return check_launch();
+}
+
+int topk_filter_finish(const TopkFilterCall &c, int64_t col0, int64_t col1, int64_t *idx64, int32_t *idx32, float *vals,
+                       cudaStream_t st) {
+    const TopkPlan &p = c.plan;
+    if (col0 % kUnitCols != 0 || col1 <= col0 || col1 > c.K) return MCD_ERR_INVALID_ARGUMENT;
+    const unsigned sgrid = static_cast<unsigned>(ceil_div<int64_t>(col1 - col0, kSelWarps));
+    int kpad = 32;
+    while (kpad < c.k) kpad <<= 1;
+#define MCD_SELECT(PER)                                                                                               \
+    topk_select_kernel<PER><<<sgrid, kSelWarps * 32, 0, st>>>(c.lists, c.cnt, p.f_cap, c.k, col0, col1, c.K, c.A, c.lda, \
+                                                             idx64, idx32, vals, c.flags)
+    switch (kpad) {
+        case 32: MCD_SELECT(1); break;
+        case 64: MCD_SELECT(2); break;
+        case 128: MCD_SELECT(4); break;
+        default: MCD_SELECT(8); break;          // make_plan: k <= 256 on this path
+    }
+#undef MCD_SELECT
+    int rc = check_launch();
+    if (rc != MCD_OK) return rc;
+    // exact redo of the column groups with a flagged column (normally none: every CTA exits at once), then the
+    // flagged columns' outputs from the redo's candidates
+    const int64_t g0 = col0 / kUnitCols;
+    dim3 grid(static_cast<unsigned>(ceil_div<int64_t>(col1 - col0, kUnitCols)), static_cast<unsigned>(p.splits));
+    ScanArgs redo{c.A, c.lda, c.N, c.K, p.rows_per_split, c.k, kFeedTensorTile, c.cand, c.kept, nullptr, c.flags, 1,
+                  static_cast<int>(g0)};
+    rc = launch_scan(grid, p, c.map_scan, redo, st);
+    if (rc != MCD_OK) return rc;
+    return launch_finish(p, c.cand, c.k, c.K, c.A, c.lda, idx64, idx32, vals, st, col0, col1, c.flags);
 }
 
 }  // namespace mcd
@@ -981,7 +1127,7 @@ static int launch_finish(const TopkPlan &p, const unsigned long long *cand, int 
 extern "C" size_t mcd_topk_cols_workspace_bytes(int64_t N, int64_t K, int64_t k) {
     mcd::TopkPlan p;
     if (N < 1 || K < 1 || k < 1 || k > N || !mcd::make_plan(N, K, k, &p)) return 0;
-    return p.cand_bytes + p.kept_bytes + p.pre_bytes;
+    return plan_total_bytes(p);
 }
 
 extern "C" int mcd_topk_cols_f32(const float *A, int64_t lda, int64_t N, int64_t K, int64_t k, int64_t *idx64_out,
@@ -991,15 +1137,14 @@ extern "C" int mcd_topk_cols_f32(const float *A, int64_t lda, int64_t N, int64_t
     if (!A || N < 1 || K < 1 || k < 1 || k > N || lda < K || N >= 0x7FFFFFFFll) return MCD_ERR_INVALID_ARGUMENT;
     TopkPlan p;
     if (!make_plan(N, K, k, &p)) return MCD_ERR_UNSUPPORTED;
-    if (!workspace || workspace_bytes < p.cand_bytes + p.kept_bytes + p.pre_bytes) return MCD_ERR_WORKSPACE;
+    if (!workspace || workspace_bytes < plan_total_bytes(p)) return MCD_ERR_WORKSPACE;
     if (reinterpret_cast<uintptr_t>(workspace) % 8 != 0) return MCD_ERR_INVALID_ARGUMENT;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     auto *cand = static_cast<unsigned long long *>(workspace);
     auto *kept = reinterpret_cast<uint32_t *>(static_cast<char *>(workspace) + p.cand_bytes);
 
     // short columns of an L2-resident matrix: exact radix select (tunable topk_small: 1 = never, else automatic)
-    if (N <= kSmallMaxRows && (N <= 4096 || N * K * 4 <= kSmallMaxBytes) && tunable(kTopkSmall) != 1 && tunable(kTopkSplits) <= 0 &&
-        tunable(kTopkVariant) != 1) {
+    if (takes_small_path(N, K)) {
         // rows of a column group split over a cluster of R CTAs when the column groups alone would leave SMs idle
         const int64_t ncb_s = ceil_div<int64_t>(K, kUnitCols);
         int R = 1;
@@ -1036,8 +1181,21 @@ extern "C" int mcd_topk_cols_f32(const float *A, int64_t lda, int64_t N, int64_t
     memset(&map, 0, sizeof(map));
     if (feed == kFeedTensorTile && !make_tile_map(&map, A, lda, N, K, kUnitCols, kTileRows)) feed = kFeedElements;
 
+    if (p.filter && feed == kFeedTensorTile && reinterpret_cast<uintptr_t>(workspace) % 256 == 0) {
+        // long columns: sample -> filter scan -> select (+ exact redo of flagged groups)
+        TopkFilterCall call;
+        int frc = topk_filter_prepare(A, lda, N, K, k, workspace, workspace_bytes, &call);
+        if (frc == MCD_OK) {
+            frc = topk_filter_begin(call, st);
+            if (frc != MCD_OK) return frc;
+            frc = topk_filter_scan(call, 0, K, 0, st);
+            if (frc != MCD_OK) return frc;
+            return topk_filter_finish(call, 0, K, idx64_out, idx32_out, vals_out, st);
+        }
+        if (frc != MCD_ERR_UNSUPPORTED) return frc;
+    }
     dim3 grid(static_cast<unsigned>(ceil_div<int64_t>(K, kUnitCols)), static_cast<unsigned>(p.splits));
-    ScanArgs main_args{A, lda, N, K, p.rows_per_split, int(k), feed, cand, kept, nullptr, nullptr, 0};
+    ScanArgs main_args{A, lda, N, K, p.rows_per_split, int(k), feed, cand, kept, nullptr, nullptr, 0, 0};
     int rc;
     if (p.pre_stride > 0 && feed == kFeedTensorTile) {
         // pass 0: k'-th largest of a 1/32 row sample -> start threshold per column; pass 1: the real scan starting

@@ -16,6 +16,7 @@
 // grid dimension so that, when a tile's slice of S fits in L2, the gathers of all neurons hit it
 // before the next slice is touched (S is 305 MB at N=100k: larger than the 126 MB L2).
 #include "common.cuh"
+#include "topk_api.cuh"
 
 namespace mcd {
 
@@ -70,8 +71,9 @@ __device__ __forceinline__ float4 load_row(const char *base, uint32_t off, int n
 // rounding (3 products, 6e-8 relative each = 1.8e-7 absolute in the log) is below lg2.approx's own error.
 template <int TPN, int U, bool SOFT, bool VEC, bool FTZ, bool GROUPED, bool FUSED>
 __global__ void __launch_bounds__(kAccumThreads)
-wpmi_accum_kernel(const float *__restrict__ S, int64_t lds, int C, const int32_t *__restrict__ idx, int64_t K, int k,
-                  const float *__restrict__ p, float eps, float *__restrict__ L, int64_t ldl, int n_groups) {
+wpmi_accum_kernel(const float *__restrict__ S, int64_t lds, int C, const int32_t *__restrict__ idx, int64_t idx_ld,
+                  int64_t K, int k, const float *__restrict__ p, float eps, float *__restrict__ L, int64_t ldl,
+                  int n_groups) {
     static_assert(U == 8, "two groups of four ranks per iteration");
     constexpr int NPB = kAccumThreads / TPN;
     // the gathered rows of S are re-read ~k*K/N (33 at c4) times: ask L2 to keep them (evict-last), measured
@@ -93,7 +95,7 @@ wpmi_accum_kernel(const float *__restrict__ S, int64_t lds, int C, const int32_t
     for (int n = 0; n < NPB; ++n) {
         const int64_t j = j0 + n;
         for (int r = tid; r < k; r += kAccumThreads)
-            s_off[n * kpad + r] = j < K ? uint32_t(idx[int64_t(r) * K + j]) * uint32_t(lds) * 4u : 0u;
+            s_off[n * kpad + r] = j < K ? uint32_t(idx[int64_t(r) * idx_ld + j]) * uint32_t(lds) * 4u : 0u;
     }
     bool p_ok = true;
     if (SOFT)
@@ -202,8 +204,8 @@ wpmi_accum_kernel(const float *__restrict__ S, int64_t lds, int C, const int32_t
 }
 
 template <int TPN, bool SOFT, bool VEC>
-static int launch_accum(const float *S, int64_t lds, int C, const int32_t *idx, int64_t K, int k, const float *p,
-                        float eps, float *L, int64_t ldl, cudaStream_t st) {
+static int launch_accum(const float *S, int64_t lds, int C, const int32_t *idx, int64_t idx_ld, int64_t K, int k,
+                        const float *p, float eps, float *L, int64_t ldl, cudaStream_t st) {
     const bool ftz = eps >= 1.17549435e-38f;
     constexpr int NPB = kAccumThreads / TPN;
     const int n_tiles = ceil_div(C, TPN * 4);
@@ -218,38 +220,33 @@ static int launch_accum(const float *S, int64_t lds, int C, const int32_t *idx, 
     const size_t sm = size_t(NPB + 2) * size_t((k + 3) & ~3) * 4;
     const int ng = static_cast<int>(n_groups);
     if (grouped && mode != 2)
-        wpmi_accum_kernel<TPN, 8, SOFT, VEC, true, true, true><<<nb, kAccumThreads, sm, st>>>(S, lds, C, idx, K, k, p, eps, L, ldl, ng);
+        wpmi_accum_kernel<TPN, 8, SOFT, VEC, true, true, true><<<nb, kAccumThreads, sm, st>>>(S, lds, C, idx, idx_ld, K, k, p, eps, L, ldl, ng);
     else if (grouped)
-        wpmi_accum_kernel<TPN, 8, SOFT, VEC, true, true, false><<<nb, kAccumThreads, sm, st>>>(S, lds, C, idx, K, k, p, eps, L, ldl, ng);
+        wpmi_accum_kernel<TPN, 8, SOFT, VEC, true, true, false><<<nb, kAccumThreads, sm, st>>>(S, lds, C, idx, idx_ld, K, k, p, eps, L, ldl, ng);
     else if (ftz)
-        wpmi_accum_kernel<TPN, 8, SOFT, VEC, true, false, false><<<nb, kAccumThreads, sm, st>>>(S, lds, C, idx, K, k, p, eps, L, ldl, ng);
+        wpmi_accum_kernel<TPN, 8, SOFT, VEC, true, false, false><<<nb, kAccumThreads, sm, st>>>(S, lds, C, idx, idx_ld, K, k, p, eps, L, ldl, ng);
     else
-        wpmi_accum_kernel<TPN, 8, SOFT, VEC, false, false, false><<<nb, kAccumThreads, sm, st>>>(S, lds, C, idx, K, k, p, eps, L, ldl, ng);
+        wpmi_accum_kernel<TPN, 8, SOFT, VEC, false, false, false><<<nb, kAccumThreads, sm, st>>>(S, lds, C, idx, idx_ld, K, k, p, eps, L, ldl, ng);
     return check_launch();
 }
 
 template <bool SOFT, bool VEC>
-static int dispatch_tile(int tpn, const float *S, int64_t lds, int C, const int32_t *idx, int64_t K, int k,
+static int dispatch_tile(int tpn, const float *S, int64_t lds, int C, const int32_t *idx, int64_t idx_ld, int64_t K, int k,
                          const float *p, float eps, float *L, int64_t ldl, cudaStream_t st) {
     switch (tpn) {
-        case 192: return launch_accum<192, SOFT, VEC>(S, lds, C, idx, K, k, p, eps, L, ldl, st);
-        case 96: return launch_accum<96, SOFT, VEC>(S, lds, C, idx, K, k, p, eps, L, ldl, st);
-        case 64: return launch_accum<64, SOFT, VEC>(S, lds, C, idx, K, k, p, eps, L, ldl, st);
-        case 48: return launch_accum<48, SOFT, VEC>(S, lds, C, idx, K, k, p, eps, L, ldl, st);
-        case 16: return launch_accum<16, SOFT, VEC>(S, lds, C, idx, K, k, p, eps, L, ldl, st);
-        default: return launch_accum<32, SOFT, VEC>(S, lds, C, idx, K, k, p, eps, L, ldl, st);
+        case 192: return launch_accum<192, SOFT, VEC>(S, lds, C, idx, idx_ld, K, k, p, eps, L, ldl, st);
+        case 96: return launch_accum<96, SOFT, VEC>(S, lds, C, idx, idx_ld, K, k, p, eps, L, ldl, st);
+        case 64: return launch_accum<64, SOFT, VEC>(S, lds, C, idx, idx_ld, K, k, p, eps, L, ldl, st);
+        case 48: return launch_accum<48, SOFT, VEC>(S, lds, C, idx, idx_ld, K, k, p, eps, L, ldl, st);
+        case 16: return launch_accum<16, SOFT, VEC>(S, lds, C, idx, idx_ld, K, k, p, eps, L, ldl, st);
+        default: return launch_accum<32, SOFT, VEC>(S, lds, C, idx, idx_ld, K, k, p, eps, L, ldl, st);
     }
 }
 
-}  // namespace mcd
-
-extern "C" int mcd_wpmi_accum_f32(const float *S, int64_t lds, int64_t N, int64_t C, const int32_t *idx, int64_t K,
-                                  int64_t k, const float *p, float min_prob, float *L, int64_t ldl,
-                                  mcd_stream_t stream) {
-    using namespace mcd;
-    if (!S || !idx || !L || N < 1 || C < 1 || K < 1 || k < 1 || lds < C || ldl < C) return MCD_ERR_INVALID_ARGUMENT;
+int wpmi_accum_range(const float *S, int64_t lds, int64_t N, int64_t C, const int32_t *idx, int64_t idx_ld, int64_t K,
+                     int64_t k, const float *p, float min_prob, float *L, int64_t ldl, cudaStream_t st) {
+    if (!S || !idx || !L || N < 1 || C < 1 || K < 1 || k < 1 || lds < C || ldl < C || idx_ld < K) return MCD_ERR_INVALID_ARGUMENT;
     if (k > kAccumMaxK || C > (1 << 24) || N * lds >= (int64_t(1) << 30)) return MCD_ERR_UNSUPPORTED;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     // 16-byte loads need aligned rows and must stay inside a row (padding included)
     const bool vec = (lds % 4 == 0) && (reinterpret_cast<uintptr_t>(S) % 16 == 0) && (ceil_div<int64_t>(C, 4) * 4 <= lds);
     // threads per neuron: tunable "accum_tile" = concepts per tile (multiple of 4).  Default: 128-concept tiles
@@ -266,8 +263,16 @@ extern "C" int mcd_wpmi_accum_f32(const float *S, int64_t lds, int64_t N, int64_
     else if (want > 16) tpn = 32;
     else tpn = 16;
     const int Ci = static_cast<int>(C), ki = static_cast<int>(k);
-    if (p) return vec ? dispatch_tile<true, true>(tpn, S, lds, Ci, idx, K, ki, p, min_prob, L, ldl, st)
-                      : dispatch_tile<true, false>(tpn, S, lds, Ci, idx, K, ki, p, min_prob, L, ldl, st);
-    return vec ? dispatch_tile<false, true>(tpn, S, lds, Ci, idx, K, ki, p, min_prob, L, ldl, st)
-               : dispatch_tile<false, false>(tpn, S, lds, Ci, idx, K, ki, p, min_prob, L, ldl, st);
+    if (p) return vec ? dispatch_tile<true, true>(tpn, S, lds, Ci, idx, idx_ld, K, ki, p, min_prob, L, ldl, st)
+                      : dispatch_tile<true, false>(tpn, S, lds, Ci, idx, idx_ld, K, ki, p, min_prob, L, ldl, st);
+    return vec ? dispatch_tile<false, true>(tpn, S, lds, Ci, idx, idx_ld, K, ki, p, min_prob, L, ldl, st)
+               : dispatch_tile<false, false>(tpn, S, lds, Ci, idx, idx_ld, K, ki, p, min_prob, L, ldl, st);
+}
+
+}  // namespace mcd
+
+extern "C" int mcd_wpmi_accum_f32(const float *S, int64_t lds, int64_t N, int64_t C, const int32_t *idx, int64_t K,
+                                  int64_t k, const float *p, float min_prob, float *L, int64_t ldl,
+                                  mcd_stream_t stream) {
+    return mcd::wpmi_accum_range(S, lds, N, C, idx, K, K, k, p, min_prob, L, ldl, static_cast<cudaStream_t>(stream));
 }

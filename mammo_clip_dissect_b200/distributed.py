@@ -54,24 +54,46 @@ class CudaBackend:
         from . import similarity
         self.sim = similarity
         self.device = similarity._cuda_device(device)
+        self._ramps = {}            # top_k -> (host ramp, device copy): no pageable H2D copy per call
+
+    def _ramp(self, ramp, top_k):
+        if ramp is None:
+            return None
+        if ramp.is_cuda:
+            return ramp if ramp.device == self.device else ramp.to(self.device)
+        hit = self._ramps.get(int(top_k))
+        if hit is None or not torch.equal(hit[0], ramp):
+            hit = self._ramps[int(top_k)] = (ramp.clone(), ramp.to(self.device))
+        return hit[1]
 
     def log_sums(self, clip_feats, target_shard, top_k, a, min_prob, ramp):
         sim = self.sim
-        A = sim._as_f32_matrix(target_shard, self.device, "target_feats")
-        with sim._Stage("softmax_rows"):
-            S = sim.concept_probabilities(clip_feats, a, self.device)
-        with sim._Stage("topk_cols"):
-            idx32 = sim._topk_int32(A, int(top_k), self.device)
-        weights = ramp.to(self.device) if ramp is not None else None
-        with sim._Stage("wpmi_accum"):
-            return sim.log_sums(S, idx32, weights, min_prob)
+        with torch.no_grad(), torch.cuda.device(self.device):
+            A = sim._as_f32_matrix(target_shard, self.device, "target_feats")
+            with sim._Stage("softmax_rows"):
+                S = sim.concept_probabilities(clip_feats, a, self.device)
+            with sim._Stage("topk_cols"):
+                idx32 = sim._topk_int32(A, int(top_k), self.device)
+            weights = self._ramp(ramp, top_k)
+            with sim._Stage("wpmi_accum"):
+                return sim.log_sums(S, idx32, weights, min_prob)
 
     def lse_partials(self, L):
-        with self.sim._Stage("lse_partials"):
+        with torch.no_grad(), torch.cuda.device(self.device), self.sim._Stage("lse_partials"):
             return self.sim.lse_partials(L)
 
+    def log_sums_and_partials(self, clip_feats, target_shard, top_k, a, min_prob, ramp):
+        """Both of the above behind one entry point (mcd_pmi_logsums_f32: column chunks pipelined, K3 of chunk q under
+        the scan of chunk q + 1).  Per-stage profiling needs the staged kernels, so it takes the two-call route."""
+        sim = self.sim
+        if sim.PROFILE is not None:
+            L = self.log_sums(clip_feats, target_shard, top_k, a, min_prob, ramp)
+            return L, self.lse_partials(L)
+        with torch.no_grad(), torch.cuda.device(self.device):
+            return sim.pmi_logsums(clip_feats, target_shard, top_k, a, self.device, min_prob, self._ramp(ramp, top_k))
+
     def finalize(self, L, partials_all, K_total, lam):
-        with self.sim._Stage("lse_finalize"):
+        with torch.no_grad(), torch.cuda.device(self.device), self.sim._Stage("lse_finalize"):
             return self.sim.pmi_finalize(L, partials_all, K_total, lam)[0]
 
 
@@ -125,6 +147,10 @@ class PeerScoreExchange:
     def exchange(self, L, partials_all, lam, sim, wait: bool = True):
         """L: this rank's [K_g, C] log-sums (finalized in place in mode "copy").  Returns the gathered matrix
         (wait=True) or a GatheredScores handle (wait=False; only mode "copy" really runs behind the caller)."""
+        with torch.no_grad(), torch.cuda.device(self.device):
+            return self._exchange(L, partials_all, lam, sim, wait)
+
+    def _exchange(self, L, partials_all, lam, sim, wait):
         b = self.turn
         self.turn = (self.turn + 1) % self.depth
         hdl, buf, views = self.hdls[b], self.bufs[b], self.views[b]
@@ -132,12 +158,15 @@ class PeerScoreExchange:
         rows = slice(self.row0, self.row0 + self.sizes[self.rank])
         if self.mode == "fused":
             hdl.barrier(channel=0)
-            with sim._Stage("finalize_bcast"):
-                sim.pmi_finalize_bcast(L, partials_all, self.K_total, lam, list(hdl.buffer_ptrs), self.row0)
+            if L.shape[0] > 0:
+                with sim._Stage("finalize_bcast"):
+                    sim.pmi_finalize_bcast(L, partials_all, self.K_total, lam, list(hdl.buffer_ptrs), self.row0)
             hdl.barrier(channel=1)
             return buf if wait else GatheredScores(buf, None)
-        with sim._Stage("lse_finalize"):
-            local = sim.pmi_finalize(L, partials_all, self.K_total, lam)[0]
+        local = L
+        if L.shape[0] > 0:
+            with sim._Stage("lse_finalize"):
+                local = sim.pmi_finalize(L, partials_all, self.K_total, lam)[0]
         ready = torch.cuda.Event()
         ready.record(main)
         self.comm.wait_event(ready)
@@ -150,7 +179,8 @@ class PeerScoreExchange:
                 st = self.push_streams[i]
                 st.wait_event(start)
                 with torch.cuda.stream(st):
-                    views[p][rows].copy_(local, non_blocking=True)
+                    if local.shape[0] > 0:
+                        views[p][rows].copy_(local, non_blocking=True)
                 self.comm.wait_stream(st)
             hdl.barrier(channel=1)
             done = torch.cuda.Event()
@@ -188,19 +218,30 @@ def pmi_scores_sharded(clip_feats, target_shard, shard_sizes: Sequence[int], top
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     assert len(shard_sizes) == world and shard_sizes[rank] == target_shard.shape[1]
+    # a boundary needs 256-alignment only if neurons follow it (small layers: K < 256 * (world - 1) leaves the last
+    # ranks with empty shards, which skip the compute and contribute no partial blocks)
     for g in range(world - 1):
-        if shard_sizes[g] % LSE_BLOCK != 0:
+        if shard_sizes[g] % LSE_BLOCK != 0 and any(int(x) > 0 for x in shard_sizes[g + 1:]):
             raise RuntimeError("interior shard boundaries must be multiples of %d neurons" % LSE_BLOCK)
     K_total = int(sum(shard_sizes))
-    L = backend.log_sums(clip_feats, target_shard, top_k, a, min_prob, ramp)
-    part = backend.lse_partials(L)
+    C = clip_feats.shape[1]
+    empty = int(shard_sizes[rank]) == 0
+    if empty:
+        dev = getattr(backend, "device", target_shard.device)
+        L = torch.empty((0, C), dtype=torch.float32, device=dev)
+        part = torch.empty((0, 2, C), dtype=torch.float32, device=dev)
+    elif hasattr(backend, "log_sums_and_partials"):
+        L, part = backend.log_sums_and_partials(clip_feats, target_shard, top_k, a, min_prob, ramp)
+    else:
+        L = backend.log_sums(clip_feats, target_shard, top_k, a, min_prob, ramp)
+        part = backend.lse_partials(L)
     nblocks = [(s + LSE_BLOCK - 1) // LSE_BLOCK for s in shard_sizes]
     part_all = _all_gather_var(part, nblocks, group) if world > 1 else part
     if exchange is not None and gather_scores and world > 1:
         if list(exchange.sizes) != [int(x) for x in shard_sizes] or exchange.C != L.shape[1]:
             raise RuntimeError("PeerScoreExchange was built for other shard sizes")
         return exchange.exchange(L, part_all, lam, backend.sim, wait=wait)
-    local = backend.finalize(L, part_all, K_total, lam)
+    local = L if empty else backend.finalize(L, part_all, K_total, lam)
     if not gather_scores or world == 1:
         return local
     stage = getattr(getattr(backend, "sim", None), "_Stage", None)

@@ -48,16 +48,30 @@ def similarity_matrix(image_features, text_features, device="cuda", normalize=Tr
     return P
 
 
+def last_gemm_path():
+    """Which K1 kernel the last similarity_matrix call ran: 'tcgen05' (3xTF32 tensor-core GEMM + stand-alone softmax),
+    'tcgen05_fused_softmax', or 'fp32_ffma' (the exact CUDA-core kernel: forced by tunable gemm_variant = 1, or shapes the
+    tensor path does not take)."""
+    return {1: "tcgen05", 2: "tcgen05_fused_softmax", 3: "fp32_ffma"}.get(int(_lib.lib().mcd_last_gemm_path()), "none")
+
+
 def get_similarity_from_activations(target_save_name, clip_save_name, text_save_name, similarity_fn,
-                                    return_target_feats=True, device="cuda"):
-    """Drop-in for CLIP_og_utils.get_similarity_from_activations (reference CLIP_og_utils.py:153-175):
-    loads the three cached .pt tensors, builds clip_feats on the GPU and calls `similarity_fn`."""
+                                    return_target_feats=True, device="cuda", d_probe=None, top_k=None,
+                                    target_on_device=False):
+    """Drop-in for get_similarity_from_activations of all three reference variants: CLIP_og_utils.py:153-175
+    (no extra arguments; target_feats handed back on the CPU), og_utils.py:478-521 (`d_probe`; target_feats loaded onto
+    `device`) and utils.py:566-612 (`d_probe` and `top_k`, the latter forwarded to `similarity_fn` exactly as
+    utils.py:602 does).  Loads the three cached .pt tensors, builds clip_feats on the GPU (K1) and calls
+    `similarity_fn`.  `d_probe` only chose where the reference ran its matmul; it is accepted and not needed here."""
     image_features = torch.load(clip_save_name, map_location='cpu', weights_only=True)
     text_features = torch.load(text_save_name, map_location='cpu', weights_only=True)
     clip_feats = similarity_matrix(image_features, text_features, device=device)
     del image_features, text_features
-    target_feats = torch.load(target_save_name, map_location='cpu', weights_only=True)
-    similarity = similarity_fn(clip_feats, target_feats, device=device)
+    target_feats = torch.load(target_save_name, map_location=device if target_on_device else 'cpu', weights_only=True)
+    if top_k is not None:
+        similarity = similarity_fn(clip_feats, target_feats, device=device, top_k=top_k)
+    else:
+        similarity = similarity_fn(clip_feats, target_feats, device=device)
     del clip_feats
     if return_target_feats:
         return similarity, target_feats

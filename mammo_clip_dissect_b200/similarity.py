@@ -28,7 +28,8 @@ import torch
 from . import _lib
 
 __all__ = ["soft_wpmi", "wpmi", "cos_similarity", "cos_similarity_cubed", "cos_similarity_cubed_single", "rank_reorder",
-           "soft_wpmi_layers", "wpmi_layers", "top_concepts", "topk_cols", "concept_probabilities", "pmi_scores"]
+           "soft_wpmi_layers", "wpmi_layers", "top_concepts", "topk_cols", "concept_probabilities", "pmi_scores",
+           "pmi_logsums"]
 
 _S_ALIGN = 32  # leading dimension of the probability matrix: rows start on 128-byte boundaries
 
@@ -175,9 +176,10 @@ def _topk_int32(A, k, dev):
     need = lib.mcd_topk_cols_workspace_bytes(N, K, k)
     if need == 0:
         raise RuntimeError("top_k=%d is outside the supported range of the column top-k kernel (<= 512)" % k)
-    ws = _workspace(need, dev)
-    _lib.check(lib.mcd_topk_cols_f32(_ptr(A), _ld(A), N, K, k, None, _ptr(idx32), None, _ptr(ws), ws.numel(),
-                                     _stream(dev)), "mcd_topk_cols_f32")
+    with torch.cuda.device(dev):
+        ws = _workspace(need, dev)
+        _lib.check(lib.mcd_topk_cols_f32(_ptr(A), _ld(A), N, K, k, None, _ptr(idx32), None, _ptr(ws), ws.numel(),
+                                         _stream(dev)), "mcd_topk_cols_f32")
     return idx32
 
 
@@ -208,10 +210,11 @@ def log_sums(S, idx32, weights, min_prob, out=None):
     dev = S.device
     N, C = S.shape
     k, K = idx32.shape
-    if out is None:
-        out = torch.empty((K, C), dtype=torch.float32, device=dev)
-    _lib.check(_lib.lib().mcd_wpmi_accum_f32(_ptr(S), _ld(S), N, C, _ptr(idx32), K, k, _ptr(weights), float(min_prob),
-                                             _ptr(out), _ld(out), _stream(dev)), "mcd_wpmi_accum_f32")
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.empty((K, C), dtype=torch.float32, device=dev)
+        _lib.check(_lib.lib().mcd_wpmi_accum_f32(_ptr(S), _ld(S), N, C, _ptr(idx32), K, k, _ptr(weights), float(min_prob),
+                                                 _ptr(out), _ld(out), _stream(dev)), "mcd_wpmi_accum_f32")
     return out
 
 
@@ -219,9 +222,10 @@ def lse_partials(L):
     """K3b part 1: per-256-neuron-block (max, sum exp) partials [nb, 2, C]."""
     K, C = L.shape
     nb = (K + _lib.LSE_BLOCK - 1) // _lib.LSE_BLOCK
-    part = torch.empty((nb, 2, C), dtype=torch.float32, device=L.device)
-    _lib.check(_lib.lib().mcd_col_lse_partials_f32(_ptr(L), _ld(L), K, C, _ptr(part), _stream(L.device)),
-               "mcd_col_lse_partials_f32")
+    with torch.cuda.device(L.device):
+        part = torch.empty((nb, 2, C), dtype=torch.float32, device=L.device)
+        _lib.check(_lib.lib().mcd_col_lse_partials_f32(_ptr(L), _ld(L), K, C, _ptr(part), _stream(L.device)),
+                   "mcd_col_lse_partials_f32")
     return part
 
 
@@ -230,10 +234,11 @@ def pmi_finalize(L, partials_all, K_total, lam, out=None):
     K, C = L.shape
     if out is None:
         out = L
-    prob_d = torch.empty((C,), dtype=torch.float32, device=L.device)
-    _lib.check(_lib.lib().mcd_pmi_finalize_f32(_ptr(L), _ld(L), K, C, _ptr(partials_all), partials_all.shape[0],
-                                               int(K_total), float(lam), _ptr(prob_d), _ptr(out), _ld(out),
-                                               _stream(L.device)), "mcd_pmi_finalize_f32")
+    with torch.cuda.device(L.device):
+        prob_d = torch.empty((C,), dtype=torch.float32, device=L.device)
+        _lib.check(_lib.lib().mcd_pmi_finalize_f32(_ptr(L), _ld(L), K, C, _ptr(partials_all), partials_all.shape[0],
+                                                   int(K_total), float(lam), _ptr(prob_d), _ptr(out), _ld(out),
+                                                   _stream(L.device)), "mcd_pmi_finalize_f32")
     return out, prob_d
 
 
@@ -245,12 +250,45 @@ def pmi_finalize_bcast(L, partials_all, K_total, lam, dest_ptrs, row_offset):
     K, C = L.shape
     if not L.is_contiguous():
         raise RuntimeError("pmi_finalize_bcast needs contiguous log-sums")
-    prob_d = torch.empty((C,), dtype=torch.float32, device=L.device)
-    arr = (ctypes.c_void_p * len(dest_ptrs))(*[int(p) for p in dest_ptrs])
-    _lib.check(_lib.lib().mcd_pmi_finalize_bcast_f32(_ptr(L), K, C, _ptr(partials_all), partials_all.shape[0],
-                                                     int(K_total), float(lam), _ptr(prob_d), arr, len(dest_ptrs),
-                                                     int(row_offset), _stream(L.device)), "mcd_pmi_finalize_bcast_f32")
+    with torch.cuda.device(L.device):
+        prob_d = torch.empty((C,), dtype=torch.float32, device=L.device)
+        arr = (ctypes.c_void_p * len(dest_ptrs))(*[int(p) for p in dest_ptrs])
+        _lib.check(_lib.lib().mcd_pmi_finalize_bcast_f32(_ptr(L), K, C, _ptr(partials_all), partials_all.shape[0],
+                                                         int(K_total), float(lam), _ptr(prob_d), arr, len(dest_ptrs),
+                                                         int(row_offset), _stream(L.device)), "mcd_pmi_finalize_bcast_f32")
     return prob_d
+
+
+def pmi_logsums(clip_feats, target_feats, top_k, a, device, min_prob, ramp):
+    """(L [K, C], partials [ceil(K/256), 2, C]) of one device's neurons behind one FFI entry point
+    (mcd_pmi_logsums_f32: softmax -> column top-k -> gather / log-sum -> block partials, column chunks pipelined) --
+    what a rank of the neuron-sharded call computes before the partials are exchanged."""
+    dev = _cuda_device(device)
+    with torch.no_grad(), torch.cuda.device(dev):
+        A = _as_f32_matrix(target_feats, dev, "target_feats")
+        P = _as_f32_matrix(clip_feats, dev, "clip_feats")
+        if P.shape[0] != A.shape[0]:
+            raise RuntimeError("clip_feats %s and target_feats %s must share the probe-image axis"
+                               % (tuple(P.shape), tuple(A.shape)))
+        N, C = P.shape
+        K = A.shape[1]
+        top_k = int(top_k)
+        if C < 1 or K < 1:
+            raise RuntimeError("clip_feats / target_feats must be non-empty")
+        if top_k < 1 or top_k > N:
+            raise RuntimeError("selected index k out of range")
+        lib = _lib.lib()
+        need = int(lib.mcd_pmi_scores_workspace_bytes(N, K, C, top_k))
+        if need == 0:
+            raise RuntimeError("top_k=%d is outside the supported range of the column top-k kernel (<= 512)" % top_k)
+        ws = _call_workspace(need, dev)
+        weights = ramp.to(dev) if ramp is not None else None
+        L = torch.empty((K, C), dtype=torch.float32, device=dev)
+        part = torch.empty(((K + _lib.LSE_BLOCK - 1) // _lib.LSE_BLOCK, 2, C), dtype=torch.float32, device=dev)
+        _lib.check(lib.mcd_pmi_logsums_f32(_ptr(P), _ld(P), _ptr(A), _ld(A), N, K, C, top_k, float(a), _ptr(weights),
+                                           float(min_prob), _ptr(L), _ld(L), _ptr(part), _ptr(ws), ws.numel(),
+                                           _stream(dev)), "mcd_pmi_logsums_f32")
+    return L, part
 
 
 def pmi_scores(clip_feats, target_feats, top_k, a, lam, device, min_prob, ramp, return_parts=False):

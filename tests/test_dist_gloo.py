@@ -91,7 +91,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("world,K", [(2, 1024), (2, 700), (3, 1300)])
+@pytest.mark.parametrize("world,K", [(2, 1024), (2, 700), (3, 1300), (3, 300), (2, 100)])   # last two: empty shards
 def test_sharded_equals_unsharded(world, K):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -120,3 +120,4 @@ def test_shard_bounds():
     b = mdist.shard_bounds(1300, 3)
     assert b[0] == 0 and b[-1] == 1300 and all(x % 256 == 0 for x in b[1:-1]) and b == sorted(b)
     assert mdist.shard_bounds(100, 4) == [0, 100, 100, 100, 100]
+    assert mdist.shard_bounds(300, 4) == [0, 256, 300, 300, 300]      # K < 256 * (world - 1): trailing empty shards

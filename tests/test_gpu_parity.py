@@ -182,6 +182,99 @@ def test_topk_pre_threshold_and_exact_redo(sim, kind):
         _lib.set_tunable("topk_pre", 0)
 
 
+def _filter_case(kind, N, K, seed=77):
+    A = torch.randn(N, K, generator=gen(seed))
+    tile = torch.arange(N) // 32
+    if kind == "spikes_on_sampled_rows":
+        A[::32] += 50.0                      # the sample only sees the spikes: threshold far too high -> short lists -> redo
+    elif kind == "overflow":
+        A[(tile % 32 == 5) | (tile % 32 == 7)] += 50.0      # rows no sample stride (32/16/8/4) visits: lists overflow -> redo
+    elif kind == "relu":
+        A = torch.relu(A - 2.5)              # 99.4 % exact zeros
+    elif kind == "const":
+        A = torch.full((N, K), -3.0)
+    elif kind == "nan_cols":
+        A[:, ::3] = float("nan")
+        A[::5, 1] = float("inf")
+    elif kind == "sorted_up":
+        A = torch.sort(A, dim=0).values      # every survivor of a column sits in the last rows: bags fill within a tile
+    elif kind == "sorted_down":
+        A = torch.sort(A, dim=0, descending=True).values
+    elif kind == "round1":
+        A = (A * 10).round() / 10            # ties inside the top k and at its boundary
+    elif kind == "mixed":
+        A[:, : K // 2] = torch.sort(A[:, : K // 2], dim=0).values
+        A[:, 1::4] = 0.5
+    return A
+
+
+@pytest.mark.parametrize("kind", ["randn", "spikes_on_sampled_rows", "overflow", "relu", "const", "nan_cols", "sorted_up",
+                                  "sorted_down", "round1", "mixed"])
+@pytest.mark.parametrize("N,K,k", [(20000, 200, 100), (8192 + 17, 131, 28), (33333, 260, 10), (20000, 96, 256)])
+def test_topk_filter_form(sim, kind, N, K, k):
+    """Long TMA-aligned columns take the filter form (sample threshold -> filter scan -> select, exact redo of flagged
+    column groups).  Same bits as the oracle and as the kept-set scan (tunable topk_filter = 1), values included."""
+    from mammo_clip_dissect_b200 import _lib
+    if K % 4:
+        K += 4 - K % 4                       # TMA needs a 16-byte row pitch (other pitches take the element-copy scan)
+    A = _filter_case(kind, N, K)
+    ref_v, ref_i = orc.topk_cols(A, k)
+    n0 = _lib.launch_count()
+    vals, idx = sim.topk_cols(A, k, device=DEV, want_values=True)
+    assert _lib.launch_count() - n0 == 6     # sample tile maxima, sample select, filter scan, select, redo scan, redo finish
+    assert torch.equal(idx.cpu(), ref_i), kind
+    assert torch.equal(vals.cpu().nan_to_num(7.0), ref_v.nan_to_num(7.0))
+    try:
+        _lib.set_tunable("topk_filter", 1)
+        n0 = _lib.launch_count()
+        assert torch.equal(sim.topk_cols(A, k, device=DEV).cpu(), ref_i)
+        assert _lib.launch_count() - n0 == 5
+    finally:
+        _lib.set_tunable("topk_filter", 0)
+
+
+@pytest.mark.parametrize("stages,chunk_tiles", [(2, 4), (3, 1000000), (12, 7)])
+def test_topk_filter_ring_and_item_shapes(sim, stages, chunk_tiles):
+    from mammo_clip_dissect_b200 import _lib
+    A = _filter_case("mixed", 30011, 388, seed=5)
+    ref = orc.topk_cols(A, 100)[1]
+    try:
+        _lib.set_tunable("filter_stages", stages)
+        _lib.set_tunable("filter_chunk_tiles", chunk_tiles)
+        assert torch.equal(sim.topk_cols(A, 100, device=DEV).cpu(), ref)
+    finally:
+        _lib.set_tunable("filter_stages", 0)
+        _lib.set_tunable("filter_chunk_tiles", 0)
+
+
+@pytest.mark.parametrize("chunks", [-1, 1, 2, 4, 8])
+def test_pipelined_call_equals_the_staged_path(sim, chunks):
+    """mcd_pmi_scores_f32 cuts the neurons into column chunks and runs chunk q's select + K3 + partials on a side stream
+    under the scan of chunk q + 1: same bits as the staged single-stream path, for any chunk count."""
+    from mammo_clip_dissect_b200 import _lib
+    N, K, C = 12000, 2304, 763
+    A = torch.randn(N, K, generator=gen(91)).to(DEV)
+    A[:, 700] = 1.0                                       # a flagged column inside a chunk
+    P = (torch.randn(N, C, generator=gen(92)) * 0.05).to(DEV)
+    staged, raw, idx = sim.pmi_scores(P, A, 100, 10, 1, DEV, 1e-7, sim._reference_ramp(100, 0.998, 0.97).to(DEV), return_parts=True)
+    try:
+        _lib.set_tunable("pipe_chunks", chunks)
+        for _ in range(2):
+            got = sim.soft_wpmi(P, A, device=DEV)
+            assert torch.equal(got, staged)
+        L, part = sim.pmi_logsums(P, A, 100, 10, DEV, 1e-7, sim._reference_ramp(100, 0.998, 0.97).to(DEV))
+        assert torch.equal(L, raw) and torch.equal(part, sim.lse_partials(raw))
+        w = sim.wpmi(P, A, device=DEV)
+    finally:
+        _lib.set_tunable("pipe_chunks", 0)
+    _lib.set_tunable("pipe_chunks", -1)
+    try:
+        assert torch.equal(w, sim.wpmi(P, A, device=DEV))
+    finally:
+        _lib.set_tunable("pipe_chunks", 0)
+
+
+
 def test_topk_errors(sim):
     A = torch.randn(50, 4)
     with pytest.raises(RuntimeError):
@@ -625,6 +718,44 @@ def test_properties_at_scale(sim):
     d = raw - out
     assert (d - d[0:1]).abs().max().item() <= 1e-3
     assert bool(torch.isfinite(out).all())
+
+
+# ------------------------------------------------------------------------------------------------
+# the benched configuration (c4: N = 100000 probe images, the stride-32 sample plan) against the oracle
+# ------------------------------------------------------------------------------------------------
+def test_c4_rows_against_the_oracle(sim):
+    """N = 100000 x K = 4096 (an eighth of the bench's width, the same per-column work and the same K2 plan): the
+    top-k indices of 288 sampled columns -- 32 of them with planted fp32 ties inside the top k and at its boundary --
+    must equal the oracle's bit for bit, their soft-WPMI log-sums (lam = 0) must match the oracle within 1e-5 relative,
+    and log p(d) over all 4096 neurons must match an fp64 logsumexp."""
+    N, K, C, k = 100000, 4096, 763, 100
+    A = torch.randn(N, K, generator=gen(2))
+    P = torch.randn(N, C, generator=gen(0)) * 0.044
+    cols = torch.randperm(K, generator=gen(3))[:288].sort().values
+    tied = cols[:32]
+    for c in tied.tolist():
+        v, r = torch.topk(A[:, c], k)
+        free = torch.tensor([i for i in range(0, 200) if i not in set(r.tolist())][:3])
+        A[free[0], c] = v[49]                 # a tie inside the top k: order by image index decides ranks 50 / 51
+        A[free[1], c] = v[k - 1]              # a tie at the boundary: the lower image index makes the cut
+        A[free[2], c] = v[k - 1]
+    sub = A[:, cols].contiguous()
+    ref_i = orc.topk_cols(sub, k)[1]
+    Ad, Pd = A.to(DEV), P.to(DEV)
+    idx = sim.topk_cols(Ad, k, device=DEV)
+    assert torch.equal(idx[:, cols.to(DEV)].cpu(), ref_i)
+    raw = sim.soft_wpmi(Pd, Ad, lam=0, device=DEV)                 # lam = 0: the rows are the log-sums L
+    ref_L = orc.soft_wpmi_fast(P, sub, top_k=k, lam=0, inds=ref_i)
+    got = raw[cols.to(DEV)].cpu()
+    rel = ((got - ref_L).abs() / ref_L.abs().clamp_min(1e-30)).max().item()
+    assert rel <= 1e-5, rel
+    assert bool((got.argmax(1) == ref_L.argmax(1)).all())
+    # log p(d) over all neurons: block LSE (fp32 blocks, fp64 combine) against fp64 logsumexp of the same L
+    out = sim.soft_wpmi(Pd, Ad, device=DEV)
+    prob_d = (raw - out)[0]
+    truth = (torch.logsumexp(raw.double(), dim=0) - torch.log(torch.tensor(float(K), dtype=torch.float64))).cpu()
+    assert (prob_d.cpu().double() - truth).abs().max().item() <= 1e-5 * truth.abs().max().item()
+    assert bool(((raw - out) - prob_d[None, :]).abs().max().item() <= 1e-3)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -1,0 +1,81 @@
+"""Round-2 timing sweeps on the c4 shape: the filter form of K2 (ring depth, item size) against the kept-set scan, and the
+column-chunk pipeline of the whole call.  usage: python tools/tune_filter.py [--k K] [--quick]"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from mammo_clip_dissect_b200 import _lib, similarity as sim  # noqa: E402
+
+
+def timeit(fn, iters=8, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=100000)
+    ap.add_argument("--k", type=int, default=32768)
+    ap.add_argument("--quick", action="store_true")
+    args = ap.parse_args()
+    dev = torch.device("cuda:0")
+    N, K, C = args.n, args.k, 763
+    g = torch.Generator(device=dev).manual_seed(0)
+    A = torch.randn(N, K, generator=g, device=dev)
+    P = torch.randn(N, C, generator=g, device=dev) * 0.044
+    gb = 4.0 * N * K / 1e9
+
+    def topk():
+        return sim._topk_int32(A, 100, dev)
+
+    def say(label, ms, bytes_gb=gb):
+        print("%-64s %8.3f ms  %7.0f GB/s" % (label, ms, bytes_gb / ms * 1e3), flush=True)
+
+    _lib.set_tunable("topk_filter", 1)
+    say("K2 kept-set scan (round 1)", timeit(topk))
+    _lib.set_tunable("topk_filter", 0)
+    for ns in ([6] if args.quick else [3, 4, 6, 8, 10]):
+        _lib.set_tunable("filter_stages", ns)
+        say("K2 filter form, ring of %d x 16 KB" % ns, timeit(topk))
+    _lib.set_tunable("filter_stages", 0)
+    if not args.quick:
+        for ct in (21, 43, 170, 340):
+            _lib.set_tunable("filter_chunk_tiles", ct)
+            say("K2 filter form, %d tiles per work item" % ct, timeit(topk))
+        _lib.set_tunable("filter_chunk_tiles", 0)
+    ramp = sim._device_ramp(sim._reference_ramp(100, 0.998, 0.97), 100, 0.998, 0.97, dev)
+    S = sim.concept_probabilities(P, 10, dev)
+    idx = topk()
+    L = torch.empty((K, C), device=dev)
+    say("K1b softmax", timeit(lambda: sim.concept_probabilities(P, 10, dev)), 2 * 4.0 * N * 768 / 1e9)
+    say("K3 gather + log-sum", timeit(lambda: sim.log_sums(S, idx, ramp, 1e-7, out=L)), 100 * K * 768 * 4 / 1e9)
+    say("K3b partials + finalize", timeit(lambda: sim.pmi_finalize(L, sim.lse_partials(L), K, 1.0)), 3 * 4.0 * K * C / 1e9)
+    alg = (4.0 * N * K + 4.0 * N * C + 4.0 * K * C) / 1e9
+    for q in ([-1, 1, 4] if args.quick else [-1, 1, 2, 3, 4, 5, 6, 8]):
+        _lib.set_tunable("pipe_chunks", q)
+        for ns in ([0] if args.quick else [0, 4, 8]):
+            _lib.set_tunable("filter_stages", ns)
+            say("soft_wpmi, %d column chunk(s), ring %s" % (q, ns or "default"),
+                timeit(lambda: sim.soft_wpmi(P, A, device=dev)), alg)
+    _lib.set_tunable("pipe_chunks", 0)
+    _lib.set_tunable("filter_stages", 0)
+    _lib.set_tunable("topk_filter", 1)
+    _lib.set_tunable("pipe_chunks", -1)
+    say("soft_wpmi, round-1 kernels (kept-set scan, one stream)", timeit(lambda: sim.soft_wpmi(P, A, device=dev)), alg)
+    _lib.set_tunable("topk_filter", 0)
+    _lib.set_tunable("pipe_chunks", 0)
+
+
+if __name__ == "__main__":
+    main()
