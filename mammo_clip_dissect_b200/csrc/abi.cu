@@ -1,5 +1,7 @@
 // Library-level entry points of include/mcd_b200.h: version, errors, launch accounting, tunables.
 #include <atomic>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -14,6 +16,18 @@ static std::atomic<int> g_num_sms{0};
 
 void count_launch(int n) { g_launches.fetch_add(static_cast<uint64_t>(n), std::memory_order_relaxed); }
 int64_t tunable(int which) { return g_tunables[which].load(std::memory_order_relaxed); }
+
+int debug_sync_check() {
+    static const int on = [] {
+        const char *e = getenv("MCD_DEBUG_SYNC");
+        return (e && e[0] == '1') ? 1 : 0;
+    }();
+    if (!on) return MCD_OK;
+    const cudaError_t err = cudaDeviceSynchronize();
+    if (err == cudaSuccess) return MCD_OK;
+    fprintf(stderr, "[mcd] launch #%llu failed: %s\n", static_cast<unsigned long long>(g_launches.load()), cudaGetErrorString(err));
+    return MCD_ERR_CUDA;
+}
 
 int num_sms() {
     int n = g_num_sms.load(std::memory_order_relaxed);
@@ -60,7 +74,7 @@ int mcd_device_check(void) {
 }
 
 int mcd_set_tunable(const char *name, int64_t value) {
-    static const char *names[] = {"topk_splits", "accum_tile", "topk_variant", "accum_unroll", "topk_cols", "topk_stages", "topk_occ", "gemm_variant", "topk_pre", "topk_small", "topk_filter", "filter_stages", "filter_chunk_tiles", "pipe_chunks"};
+    static const char *names[] = {"topk_splits", "accum_tile", "topk_variant", "accum_unroll", "topk_cols", "topk_stages", "topk_occ", "gemm_variant", "topk_pre", "topk_small", "topk_filter", "filter_stages", "filter_chunk_tiles", "pipe_chunks", "filter_order"};
     constexpr int n_names = sizeof(names) / sizeof(names[0]);
     if (!name) return MCD_ERR_INVALID_ARGUMENT;
     for (int i = 0; i < n_names; ++i)
@@ -140,7 +154,7 @@ PipeRes *pipe_resources() {
 int pipe_bounds(int64_t K, int64_t *bounds) {
     int64_t q = mcd::tunable(mcd::kPipeChunks);
     const int64_t units = (K + MCD_LSE_BLOCK - 1) / MCD_LSE_BLOCK;
-    if (q <= 0) q = K >= 8192 ? 4 : 1;
+    if (q <= 0) q = 1;
     if (q > kMaxPipeChunks) q = kMaxPipeChunks;
     if (q > units) q = units;
     bounds[0] = 0;
@@ -173,8 +187,12 @@ int pmi_logsums(const float *P, int64_t ldp, const float *A, int64_t lda, int64_
     TopkFilterCall call;
     int64_t bounds[kMaxPipeChunks + 1];
     const int nq = pipe_bounds(K, bounds);
-    // tunable pipe_chunks: 0 = automatic, n > 0 = n chunks (1: only the softmax runs beside the scan), -1 = one stream
-    PipeRes *pr = tunable(kPipeChunks) >= 0 ? pipe_resources() : nullptr;
+    // tunable pipe_chunks: 0 (default) / -1 = one stream, stage after stage; n > 0 = n column chunks with a side stream
+    // (1: only the softmax runs beside the sample pass and the scan).  Measured at c4 on B200 (profiles/r2_k2_history.md):
+    // every overlapped variant LOSES to the plain sequence (3.19 ms; 2 chunks 3.46, 4 chunks 3.62) -- K3's CTAs take
+    // resident-warp slots and L2 bandwidth from the scan, which needs >= 9 resident warps per SM to saturate HBM, and
+    // each chunk re-reads the concept-tile slices of S from DRAM -- so the pipeline stays an option, not the default.
+    PipeRes *pr = tunable(kPipeChunks) > 0 ? pipe_resources() : nullptr;
     int rc = pr ? topk_filter_prepare(A, lda, N, K, k, w + l.topk_off, workspace_bytes - l.topk_off, &call) : MCD_ERR_UNSUPPORTED;
     if (rc != MCD_OK && rc != MCD_ERR_UNSUPPORTED) return rc;
     if (rc == MCD_ERR_UNSUPPORTED) {

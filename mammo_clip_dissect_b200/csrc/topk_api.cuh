@@ -23,7 +23,7 @@ struct TopkPlan {
 };
 
 struct TopkFilterCall {
-    CUtensorMap map_filter;             // [32 rows x 128 cols] boxes over A
+    CUtensorMap map_filter;             // [8 rows x 128 cols] boxes over A
     CUtensorMap map_scan;               // [64 rows x 32 cols] boxes (exact redo of flagged column groups)
     TopkPlan plan;
     const float *A;
@@ -44,7 +44,8 @@ int topk_filter_prepare(const float *A, int64_t lda, int64_t N, int64_t K, int64
                         size_t workspace_bytes, TopkFilterCall *c);
 // zero the counters, sample pass -> start threshold per column (all K columns)
 int topk_filter_begin(const TopkFilterCall &c, cudaStream_t st);
-// filter scan of columns [col0, col1) (col0 a multiple of 128); launch_id < 64 selects the launch's item counter
+// filter scan of columns [col0, col1) (col0 a multiple of 4, col1 a multiple of 256 or K); launch_id < 64 selects the
+// launch's item counter
 int topk_filter_scan(const TopkFilterCall &c, int64_t col0, int64_t col1, int launch_id, cudaStream_t st);
 // select the top k of every column in [col0, col1) (col0 a multiple of 32), redo flagged groups exactly, emit [k, K] outputs
 int topk_filter_finish(const TopkFilterCall &c, int64_t col0, int64_t col1, int64_t *idx64, int32_t *idx32, float *vals,

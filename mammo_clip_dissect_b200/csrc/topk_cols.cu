@@ -911,13 +911,18 @@ static bool make_plan(int64_t N, int64_t K, int64_t k64, TopkPlan *p) {
             p->filter = 1;
             p->f_cap = cap;
             int ns = static_cast<int>(tunable(kFilterStages));
-            if (ns < 2 || ns > kFMaxStages) ns = 6;
+            if (ns < 2 || ns > kFMaxStages) ns = 2;         // 18 KB per warp: 12 resident warps per SM, 96 KB in flight (measured best)
             p->f_nstage = ns;
-            const int64_t tiles_total = ceil_div<int64_t>(N, kFRows), nblk = ceil_div<int64_t>(K, kFCols);
+            const int64_t tiles_total = N / kFRows, nblk = ceil_div<int64_t>(K, kFCols);
             int64_t ct = tunable(kFilterChunkTiles);
-            if (ct <= 0) ct = ceil_div<int64_t>(tiles_total * nblk, sms * 64);     // ~64 work items per SM
-            if (ct < 4) ct = 4;
+            if (ct <= 0) {
+                // a work item = one single-warp CTA; ~32 items per resident warp (8 per SM): the tail of the launch and the
+                // pipeline fill / drain of an item stay at a few per cent
+                ct = ceil_div<int64_t>(tiles_total * nblk, sms * 8 * 32);
+                if (ct < 48) ct = 48;
+            }
             if (ct > tiles_total) ct = tiles_total;
+            if (ct < 1) ct = 1;
             p->f_chunk_tiles = static_cast<int>(ct);
             p->f_chunks = static_cast<int>(ceil_div<int64_t>(tiles_total, ct));
             p->f_cnt_bytes = ((size_t(K) + kFMaxLaunches) * 4 + 255) / 256 * 256;
@@ -1068,27 +1073,33 @@ int topk_filter_begin(const TopkFilterCall &c, cudaStream_t st) {
 
 int topk_filter_scan(const TopkFilterCall &c, int64_t col0, int64_t col1, int launch_id, cudaStream_t st) {
     const TopkPlan &p = c.plan;
-    if (col0 % kFCols != 0 || col1 <= col0 || col1 > c.K || launch_id < 0 || launch_id >= kFMaxLaunches)
+    if (col0 % 4 != 0 || col1 <= col0 || col1 > c.K || launch_id < 0 || launch_id >= kFMaxLaunches)
         return MCD_ERR_INVALID_ARGUMENT;
     FilterArgs a;
     a.N = c.N;
     a.K = c.K;
-    a.col_block0 = static_cast<int>(col0 / kFCols);
-    a.n_col_blocks = static_cast<int>(ceil_div<int64_t>(col1 - col0, kFCols));
+    a.col_begin = col0;
+    a.col_end = col1;
     a.chunk_tiles = p.f_chunk_tiles;
-    a.n_chunks = p.f_chunks;
     a.nstage = p.f_nstage;
     a.cap = p.f_cap;
     a.tau = c.tau;
     a.cnt = c.cnt;
     a.lists = c.lists;
-    a.item_ctr = c.cnt + c.K + launch_id;
+    (void)launch_id;
     const size_t smem = filter_smem_bytes(p.f_nstage);
     if (cudaFuncSetAttribute(filter_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
         return MCD_ERR_CUDA;
-    const int64_t items = int64_t(a.n_col_blocks) * a.n_chunks;
-    const unsigned grid = static_cast<unsigned>(items < num_sms() ? items : num_sms());
-    filter_scan_kernel<<<grid, kFThreads, smem, st>>>(c.map_filter, a);
+    if (c.N >= kFRows) {
+        // blockIdx.x = 128-column block (fastest: neighbours in a wave read neighbouring pieces of the same rows),
+        // blockIdx.y = row chunk
+        dim3 grid(static_cast<unsigned>(ceil_div<int64_t>(col1 - col0, kFCols)), static_cast<unsigned>(p.f_chunks));
+        filter_scan_kernel<<<grid, kFThreads, smem, st>>>(c.map_filter, a);
+    }
+    int rc = check_launch();
+    if (rc != MCD_OK || c.N % kFRows == 0) return rc;
+    filter_tail_rows_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(col1 - col0, 256)), 256, 0, st>>>(
+        c.A, c.lda, c.N / kFRows * kFRows, c.N, col0, col1, c.tau, c.cnt, c.lists, p.f_cap);
     return check_launch();
 }
 

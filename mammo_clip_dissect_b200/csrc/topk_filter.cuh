@@ -8,18 +8,20 @@
 // A column whose list comes up short of k, or overflows its capacity, is flagged and redone exactly by
 // topk_scan_kernel (only_flagged), so the result is exact whatever the data.
 //
-//   filter_scan_kernel   persistent CTA per SM: one producer lane streams [32 rows x 128 columns] boxes of A (16 KB,
-//                        512-byte row pieces) into a shared-memory ring with TMA (cp.async.bulk.tensor.2d, mbarrier
-//                        completion, L2 evict-first), 8 consumer warps take WHOLE tiles off the ring by ticket (a
-//                        shared-memory counter), so no warp ever waits for another warp: the only synchronisation is
-//                        the per-stage full / empty mbarrier pair.  A lane owns 4 adjacent columns of the tile
-//                        (thresholds in registers), compares 4 rows x 4 columns per step and appends passing elements
-//                        with predicated stores to its lane-private bag in shared memory (no atomics, no votes, no
-//                        divergence).  A bag is emptied when it could overflow and whenever the warp moves to another
-//                        column block: one global atomic per entry reserves the slot in the column's list, 4 in flight
-//                        per lane.  Work items are (128-column block, row chunk) pairs handed out by a global counter,
-//                        ~64 items per SM, so the tail of the launch is ~1.5 % and a launch over any column range
-//                        (one pipeline chunk, one GPU's shard) fills the machine.
+//   filter_scan_kernel   one WARP per CTA and per work item: 128 adjacent columns x a chunk of ~700 rows.  The warp feeds
+//                        itself: [8 rows x 128 columns] tiles (4 KB, 512-byte row pieces) arrive in a private 4-stage
+//                        shared-memory ring by TMA (cp.async.bulk.tensor.2d, mbarrier completion, L2 evict-first), and
+//                        lane 0 re-arms a stage as soon as the warp holds its 8 rows in registers (8 x LDS.128 per
+//                        lane) -- before any filtering.  8 such warps are resident per SM (128 KB in flight) and none
+//                        ever waits for another, so a warp that is busy emptying its bag only pauses its own 1/8 of the
+//                        SM's stream.  CTAs are dispatched in blockIdx order = adjacent column blocks of the same row
+//                        chunk, so the warps that run at the same time read neighbouring 512-byte pieces of the same
+//                        rows (DRAM pages are streamed contiguously).  A lane owns 4 adjacent columns (thresholds in
+//                        registers).  Per row: four compares OR-ed into one predicate and a predicated append of the
+//                        row's 4 values + the row index to the lane-private bag (no vote, no branch, no atomics).  The
+//                        bag has two halves: emptying one only ISSUES four atomics (one per column, reserving the
+//                        list slots) and switches to the other half; the entries are placed when that half is emptied
+//                        in turn, long after the atomics have returned -- nobody waits for an L2 round trip.
 //   topk_select_kernel   warp per column: the k-th largest (key, ~row) word of the list by range-adaptive 32-bin
 //                        histogram rounds (each round narrows the 64-bit key range 32-fold; ~2-3 rounds until <= 32
 //                        candidates remain, then a 32-lane bitonic sort), the k words >= it are compacted and sorted
@@ -28,32 +30,33 @@
 
 namespace mcd {
 
-constexpr int kFCols = 128;                          // columns per block = TMA box width (512 bytes)
-constexpr int kFRows = 32;                           // rows per tile
-constexpr int kFConsumers = 8;                       // consumer warps per CTA (+ 1 producer warp)
-constexpr int kFThreads = 32 * (kFConsumers + 1);
-constexpr int kFBagCap = 32;                         // slots of a lane-private bag
-constexpr int kFBagStep = 16;                        // a 4-row step appends at most 16 entries per lane
-constexpr int kFMaxStages = 12;
+constexpr int kFCols = 128;                          // columns per work item = TMA box width (a lane owns 4)
+constexpr int kFRows = 8;                            // rows per tile
+constexpr int kFThreads = 32;                        // one warp per CTA
+constexpr int kFBagCap = 8;                          // entries of one half of a lane-private bag (an entry = 4 values of one row)
+constexpr int kFBagStep = 4;                         // 4 rows append at most 4 entries per lane
+constexpr int kFMaxStages = 8;
 constexpr uint32_t kFTileBytes = kFCols * kFRows * 4;
-constexpr uint32_t kFBagSlotBytes = 32 * 8;          // bag[slot][lane] of uint2
-constexpr int kFMaxLaunches = 64;                    // item counters per call (one per scan launch / pipeline chunk)
-
-struct FilterMeta {
-    int col0, row0, nvalid, pad;                     // col0 < 0: no more tiles
-};
+constexpr uint32_t kFBagValBytes = 32 * 16, kFBagRowBytes = 32 * 4;      // bag slot strides: float4 / row per lane
+constexpr int kFMaxLaunches = 64;                    // (spare counters behind the survivor counts)
 
 // behind the ring (nstage tiles) in dynamic shared memory
 struct FilterTail {
-    uint2 bag[kFConsumers][kFBagCap][32];
-    FilterMeta meta[kFMaxStages];
-    uint64_t full[kFMaxStages], empty[kFMaxStages];
-    int next;                                        // ticket counter: the next tile to be taken by a consumer warp
+    float4 bagv[2][kFBagCap][32];                    // two halves: the row's 4 values of a lane with a passing element
+    uint32_t bagr[2][kFBagCap][32];                  // ... and the row
+    uint64_t full[kFMaxStages];
 };
 __host__ __device__ inline size_t filter_smem_bytes(int nstage) { return size_t(nstage) * kFTileBytes + sizeof(FilterTail); }
 
+__device__ __forceinline__ uint64_t global_timer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// a lost arrival must not hang the GPU: after 2 s of waiting the kernel traps (the call then fails with a CUDA error)
 __device__ __forceinline__ void mbar_wait_bounded(uint32_t bar_addr, uint32_t parity) {
     uint32_t ok, spins = 0;
+    uint64_t t0 = 0;
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -62,159 +65,188 @@ __device__ __forceinline__ void mbar_wait_bounded(uint32_t bar_addr, uint32_t pa
             : "=r"(ok)
             : "r"(bar_addr), "r"(parity)
             : "memory");
-        if (!ok && ++spins > (1u << 24)) __trap();   // a lost arrival must not hang the GPU
+        if (!ok && (++spins & 255u) == 0u) {
+            const uint64_t now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 2000000000ull) __trap();
+        }
     } while (!ok);
 }
-__device__ __forceinline__ void mbar_arrive_addr(uint32_t bar_addr) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
 struct FilterArgs {
     int64_t N, K;
-    int col_block0, n_col_blocks;        // this launch covers column blocks [col_block0, col_block0 + n_col_blocks)
-    int chunk_tiles, n_chunks;           // a work item = chunk_tiles consecutive tiles of one column block
+    int64_t col_begin, col_end;          // this launch covers columns [col_begin, col_end): blockIdx.x counts 128-column blocks
+    int chunk_tiles;                     // blockIdx.y counts row chunks of chunk_tiles whole 8-row tiles
     int nstage, cap;
     const float *tau;                    // [K] start thresholds
     int *cnt;                            // [K] survivors per column (may exceed cap: the excess is dropped and the column flagged)
     unsigned long long *lists;           // [K][cap] survivor words (ordered key << 32 | ~row)
-    int *item_ctr;                       // work-item counter of this launch (zero on entry)
 };
 
-__global__ void __launch_bounds__(kFThreads, 1)
+__global__ void __launch_bounds__(kFThreads)
 filter_scan_kernel(const __grid_constant__ CUtensorMap tmap, const FilterArgs a) {
     extern __shared__ __align__(1024) unsigned char fsm[];
     FilterTail &t = *reinterpret_cast<FilterTail *>(fsm + size_t(a.nstage) * kFTileBytes);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t ring_addr = smem_u32(fsm);
-    const uint32_t full_addr = smem_u32(&t.full[0]), empty_addr = smem_u32(&t.empty[0]);
+    const int lane = threadIdx.x;
+    const uint32_t ring_addr = smem_u32(fsm), full_addr = smem_u32(&t.full[0]);
     const int nstage = a.nstage;
+    const int64_t c0 = a.col_begin + int64_t(blockIdx.x) * kFCols;
+    const int64_t tiles_total = a.N / kFRows;        // whole tiles; filter_tail_rows_kernel takes the last N % 8 rows
+    const int64_t tile0 = int64_t(blockIdx.y) * a.chunk_tiles;
+    const int ntile = static_cast<int>(min(int64_t(a.chunk_tiles), tiles_total - tile0));
+    if (ntile <= 0) return;
+    const uint64_t policy = l2_policy_evict_first();
+    const int tx = static_cast<int>(c0), ty0 = static_cast<int>(tile0 * kFRows);
 
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < nstage; ++i) {
-            mbar_init(&t.full[i], 1);
-            mbar_init(&t.empty[i], 1);
-        }
-        t.next = 0;
+    if (lane == 0) {
+        for (int i = 0; i < nstage; ++i) mbar_init(&t.full[i], 1);
         fence_mbar_init();
     }
-    __syncthreads();
-
-    if (warp == kFConsumers) {
-        // ---- producer: one lane turns work items into TMA tile loads ------------------------------------------------
-        if (lane != 0) return;
-        const uint64_t policy = l2_policy_evict_first();
-        const int n_items = a.n_col_blocks * a.n_chunks;
-        const int64_t tiles_total = (a.N + kFRows - 1) / kFRows;
-        int stage = 0, use = 0;
-        auto next_stage = [&]() {
-            if (use > 0) mbar_wait_bounded(empty_addr + stage * 8, (use - 1) & 1);
-        };
-        auto advance = [&]() {
-            if (++stage == nstage) {
-                stage = 0;
-                ++use;
-            }
-        };
-        for (;;) {
-            const int item = atomicAdd(a.item_ctr, 1);
-            if (item >= n_items) break;
-            // column-block-major order: the blocks of a launch complete roughly in order
-            const int b = item / a.n_chunks, r = item - b * a.n_chunks;
-            const int col0 = (a.col_block0 + b) * kFCols;
-            const int64_t tile0 = int64_t(r) * a.chunk_tiles;
-            const int ntile = static_cast<int>(min(int64_t(a.chunk_tiles), tiles_total - tile0));
-            for (int i = 0; i < ntile; ++i) {
-                next_stage();
-                const int64_t row0 = (tile0 + i) * kFRows;
-                t.meta[stage] = FilterMeta{col0, static_cast<int>(row0), static_cast<int>(min(int64_t(kFRows), a.N - row0)), 0};
-                mbar_arrive_expect_tx_addr(full_addr + stage * 8, kFTileBytes);
-                tma_tile_g2s(ring_addr + stage * kFTileBytes, &tmap, col0, static_cast<int>(row0), full_addr + stage * 8, policy);
-                advance();
-            }
+    __syncwarp();
+    // prologue: start the stream before touching anything else
+    if (lane == 0) {
+        for (int i = 0; i < nstage && i < ntile; ++i) {
+            mbar_arrive_expect_tx_addr(full_addr + i * 8, kFTileBytes);
+            tma_tile_g2s(ring_addr + i * kFTileBytes, &tmap, tx, ty0 + i * kFRows, full_addr + i * 8, policy);
         }
-        // one end marker per consumer warp
-        for (int c = 0; c < kFConsumers; ++c) {
-            next_stage();
-            t.meta[stage] = FilterMeta{-1, 0, 0, 0};
-            mbar_arrive_addr(full_addr + stage * 8);
-            advance();
-        }
-        return;
     }
+    // this lane's 4 columns and their thresholds (columns outside the launch's range never pass)
+    const int64_t cur_col = c0 + lane * 4;
+    float4 tau4;
+    tau4.x = cur_col + 0 < a.col_end ? __ldg(a.tau + cur_col + 0) : INFINITY;
+    tau4.y = cur_col + 1 < a.col_end ? __ldg(a.tau + cur_col + 1) : INFINITY;
+    tau4.z = cur_col + 2 < a.col_end ? __ldg(a.tau + cur_col + 2) : INFINITY;
+    tau4.w = cur_col + 3 < a.col_end ? __ldg(a.tau + cur_col + 3) : INFINITY;
 
-    // ---- consumers: whole tiles by ticket ----------------------------------------------------------------------------
-    const uint32_t bag_base = smem_u32(&t.bag[warp][0][lane]);
-    const uint32_t bag_limit = bag_base + uint32_t(kFBagCap - kFBagStep) * kFBagSlotBytes;   // beyond: a step may overflow
-    uint32_t bp = bag_base;
-    int cur_col0 = -1;
-    float4 tau4 = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+    const uint32_t bagv0 = smem_u32(&t.bagv[0][0][lane]), bagr0 = smem_u32(&t.bagr[0][0][lane]);
+    constexpr uint32_t kHalfV = kFBagCap * kFBagValBytes, kHalfR = kFBagCap * kFBagRowBytes;
+    int half = 0;
+    uint32_t pv = bagv0, pr = bagr0;
     const int cap = a.cap;
+    // pending half: entries counted, slots reserved (o0..o3 = first slot per column), not yet placed
+    int pend_c = 0, pend_mx = 0, pend_half = 0, o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+    uint32_t half_limit = bagr0 + uint32_t(kFBagCap - kFBagStep) * kFBagRowBytes;
 
-    // empty the lane-private bag into the survivor lists of the lane's 4 columns: one atomic per entry reserves the slot
-    auto flush = [&]() {
-        const int c = static_cast<int>((bp - bag_base) / kFBagSlotBytes);
-        const int mx = __reduce_max_sync(0xffffffffu, c);
-        for (int i = 0; i < mx; i += 4) {
-            uint2 e[4];
-            int pos[4], col[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (i + u < c) {
-                    e[u] = t.bag[warp][i + u][lane];
-                    col[u] = cur_col0 + lane * 4 + int(e[u].y & 3u);
-                    pos[u] = atomicAdd(a.cnt + col[u], 1);
-                }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (i + u < c && pos[u] < cap)
-                    a.lists[int64_t(col[u]) * cap + pos[u]] = pack_key(ordered_key(__uint_as_float(e[u].x)), ~(e[u].y >> 2));
+    auto place = [&]() {
+        unsigned long long *list = a.lists + cur_col * cap;
+#pragma unroll 1
+        for (int i = 0; i < pend_mx; ++i) {
+            if (i < pend_c) {
+                const float4 v = t.bagv[pend_half][i][lane];
+                const uint32_t nrow = ~t.bagr[pend_half][i][lane];
+                if (!(v.x <= tau4.x)) { if (o0 < cap) list[o0] = pack_key(ordered_key(v.x), nrow); ++o0; }
+                if (!(v.y <= tau4.y)) { if (o1 < cap) list[int64_t(cap) + o1] = pack_key(ordered_key(v.y), nrow); ++o1; }
+                if (!(v.z <= tau4.z)) { if (o2 < cap) list[int64_t(cap) * 2 + o2] = pack_key(ordered_key(v.z), nrow); ++o2; }
+                if (!(v.w <= tau4.w)) { if (o3 < cap) list[int64_t(cap) * 3 + o3] = pack_key(ordered_key(v.w), nrow); ++o3; }
+            }
         }
-        bp = bag_base;
+        pend_mx = 0;
     };
-
-    for (;;) {
-        int ticket = 0;
-        if (lane == 0) ticket = atomicAdd(&t.next, 1);
-        ticket = __shfl_sync(0xffffffffu, ticket, 0);
-        const int stage = ticket % nstage;
-        mbar_wait_bounded(full_addr + stage * 8, uint32_t(ticket / nstage) & 1u);
-        const FilterMeta m = t.meta[stage];
-        if (m.col0 < 0) break;
-        if (m.col0 != cur_col0) {
-            if (cur_col0 >= 0) flush();              // bag entries name their column relative to the block
-            cur_col0 = m.col0;
-            const int64_t c = int64_t(m.col0) + lane * 4;
-            tau4.x = c + 0 < a.K ? a.tau[c + 0] : INFINITY;      // columns past K (zero-filled by TMA) never pass
-            tau4.y = c + 1 < a.K ? a.tau[c + 1] : INFINITY;
-            tau4.z = c + 2 < a.K ? a.tau[c + 2] : INFINITY;
-            tau4.w = c + 3 < a.K ? a.tau[c + 3] : INFINITY;
+    auto flush_issue = [&]() {
+        if (pend_mx) place();
+        const int c = static_cast<int>((pr - (bagr0 + half * kHalfR)) / kFBagRowBytes);
+        const int mx = __reduce_max_sync(0xffffffffu, c);
+        if (mx == 0) return;
+        int n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+#pragma unroll 1
+        for (int i = 0; i < mx; ++i) {
+            if (i < c) {
+                const float4 v = t.bagv[half][i][lane];
+                n0 += !(v.x <= tau4.x);
+                n1 += !(v.y <= tau4.y);
+                n2 += !(v.z <= tau4.z);
+                n3 += !(v.w <= tau4.w);
+            }
         }
+        int *cnt = a.cnt + cur_col;
+        if (n0) o0 = atomicAdd(cnt + 0, n0);
+        if (n1) o1 = atomicAdd(cnt + 1, n1);
+        if (n2) o2 = atomicAdd(cnt + 2, n2);
+        if (n3) o3 = atomicAdd(cnt + 3, n3);
+        pend_c = c;
+        pend_mx = mx;
+        pend_half = half;
+        half ^= 1;
+        pv = bagv0 + half * kHalfV;
+        pr = bagr0 + half * kHalfR;
+        half_limit = pr + uint32_t(kFBagCap - kFBagStep) * kFBagRowBytes;
+    };
+    // One row of the lane's slice: four compares OR-ed into one predicate, then the predicated append.  Written as one
+    // asm block so that the predicate is consumed at once (left to itself the compiler hoists all 32 compares of a
+    // tile in front of the appends and shuffles the predicates through a general register).
+    auto append = [&](const float4 &v, uint32_t row0, int i) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t.reg .b32 r;\n\t"
+            "setp.gtu.f32 p, %2, %6;\n\t"
+            "setp.gtu.or.f32 p, %3, %7, p;\n\t"
+            "setp.gtu.or.f32 p, %4, %8, p;\n\t"
+            "setp.gtu.or.f32 p, %5, %9, p;\n\t"
+            "@p add.u32 r, %10, %11;\n\t"
+            "@p st.shared.v4.f32 [%0], {%2,%3,%4,%5};\n\t"
+            "@p st.shared.u32 [%1], r;\n\t"
+            "@p add.u32 %0, %0, 512;\n\t"
+            "@p add.u32 %1, %1, 128;\n\t}"
+            : "+r"(pv), "+r"(pr)
+            : "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "f"(tau4.x), "f"(tau4.y), "f"(tau4.z), "f"(tau4.w), "r"(row0), "r"(i)
+            : "memory");
+    };
+    static_assert(kFBagValBytes == 512 && kFBagRowBytes == 128, "the append block hard-codes the bag strides");
+
+    int stage = 0, use = 0;
+    uint32_t row0 = static_cast<uint32_t>(ty0);
+#pragma unroll 1
+    for (int tl = 0; tl < ntile; ++tl, row0 += kFRows) {
+        mbar_wait_bounded(full_addr + stage * 8, uint32_t(use) & 1u);
         const uint32_t tile = ring_addr + uint32_t(stage) * kFTileBytes + uint32_t(lane) * 16u;
-        const uint32_t rowcode = uint32_t(m.row0) << 2;          // entry word 1: row << 2 | column within the lane
-        const bool whole = m.nvalid == kFRows;
+        float4 v[kFRows];
 #pragma unroll
-        for (int s = 0; s < kFRows / 4; ++s) {
-            float4 v[4];
+        for (int i = 0; i < kFRows; ++i) v[i] = lds_v4(tile + uint32_t(i) * (kFCols * 4));
+        __syncwarp();                                // every lane has the tile's rows in registers
+        if (lane == 0 && tl + nstage < ntile) {
+            fence_proxy_async();                     // generic-proxy reads before the async-proxy refill
+            mbar_arrive_expect_tx_addr(full_addr + stage * 8, kFTileBytes);
+            tma_tile_g2s(ring_addr + uint32_t(stage) * kFTileBytes, &tmap, tx, static_cast<int>(row0) + nstage * kFRows,
+                         full_addr + stage * 8, policy);
+        }
+        if (++stage == nstage) {
+            stage = 0;
+            ++use;
+        }
+#pragma unroll 1
+        for (int ph = 0; ph < 2; ++ph) {
+            if (ph == 0) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = lds_v4(tile + uint32_t(4 * s + i) * (kFCols * 4));
-            if (s == kFRows / 4 - 1) {
-                // the whole tile is in registers: hand the stage back before the last step's appends
-                __syncwarp();
-                if (lane == 0) mbar_arrive_addr(empty_addr + stage * 8);
+                for (int i = 0; i < 4; ++i) append(v[i], row0, i);
+            } else {
+#pragma unroll
+                for (int i = 4; i < 8; ++i) append(v[i], row0, i);
             }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const uint32_t rc = rowcode + (uint32_t(4 * s + i) << 2);
-                const bool ok = whole || (4 * s + i) < m.nvalid;           // rows past N are zero-filled, not data
-                if (ok && !(v[i].x <= tau4.x)) { sts_v2(bp, __float_as_uint(v[i].x), rc); bp += kFBagSlotBytes; }
-                if (ok && !(v[i].y <= tau4.y)) { sts_v2(bp, __float_as_uint(v[i].y), rc | 1u); bp += kFBagSlotBytes; }
-                if (ok && !(v[i].z <= tau4.z)) { sts_v2(bp, __float_as_uint(v[i].z), rc | 2u); bp += kFBagSlotBytes; }
-                if (ok && !(v[i].w <= tau4.w)) { sts_v2(bp, __float_as_uint(v[i].w), rc | 3u); bp += kFBagSlotBytes; }
-            }
-            if (__any_sync(0xffffffffu, bp > bag_limit)) flush();
+            // 4 rows add at most 4 entries per lane: switch halves when a lane has fewer than 4 free slots left
+            if (__any_sync(0xffffffffu, pr > half_limit)) flush_issue();
         }
     }
-    if (cur_col0 >= 0) flush();
+#pragma unroll 1
+    for (int rep = 0; rep < 2; ++rep) flush_issue();       // the second call places what the first one reserved
+}
+
+// The last N % 8 rows of the matrix (the scan streams whole 8-row tiles only): thread per column.
+__global__ void __launch_bounds__(256)
+filter_tail_rows_kernel(const float *__restrict__ A, int64_t lda, int64_t row_begin, int64_t N, int64_t col_begin,
+                        int64_t col_end, const float *__restrict__ tau, int *__restrict__ cnt,
+                        unsigned long long *__restrict__ lists, int cap) {
+    const int64_t col = col_begin + int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (col >= col_end) return;
+    const float th = tau[col];
+    for (int64_t r = row_begin; r < N; ++r) {
+        const float v = A[r * lda + col];
+        if (!(v <= th)) {
+            const int pos = atomicAdd(cnt + col, 1);
+            if (pos < cap) lists[col * cap + pos] = pack_key(ordered_key(v), ~static_cast<uint32_t>(r));
+        }
+    }
 }
 
 // ---- select ---------------------------------------------------------------------------------------------------------

@@ -210,7 +210,7 @@ def _filter_case(kind, N, K, seed=77):
 
 @pytest.mark.parametrize("kind", ["randn", "spikes_on_sampled_rows", "overflow", "relu", "const", "nan_cols", "sorted_up",
                                   "sorted_down", "round1", "mixed"])
-@pytest.mark.parametrize("N,K,k", [(20000, 200, 100), (8192 + 17, 131, 28), (33333, 260, 10), (20000, 96, 256)])
+@pytest.mark.parametrize("N,K,k", [(20000, 200, 100), (17017, 131, 28), (33333, 260, 10), (60000, 100, 256)])
 def test_topk_filter_form(sim, kind, N, K, k):
     """Long TMA-aligned columns take the filter form (sample threshold -> filter scan -> select, exact redo of flagged
     column groups).  Same bits as the oracle and as the kept-set scan (tunable topk_filter = 1), values included."""
@@ -221,7 +221,8 @@ def test_topk_filter_form(sim, kind, N, K, k):
     ref_v, ref_i = orc.topk_cols(A, k)
     n0 = _lib.launch_count()
     vals, idx = sim.topk_cols(A, k, device=DEV, want_values=True)
-    assert _lib.launch_count() - n0 == 6     # sample tile maxima, sample select, filter scan, select, redo scan, redo finish
+    # sample tile maxima, sample select, filter scan (+ the last N % 8 rows), select, redo scan, redo finish
+    assert _lib.launch_count() - n0 == 6 + (N % 8 != 0)
     assert torch.equal(idx.cpu(), ref_i), kind
     assert torch.equal(vals.cpu().nan_to_num(7.0), ref_v.nan_to_num(7.0))
     try:
@@ -233,7 +234,7 @@ def test_topk_filter_form(sim, kind, N, K, k):
         _lib.set_tunable("topk_filter", 0)
 
 
-@pytest.mark.parametrize("stages,chunk_tiles", [(2, 4), (3, 1000000), (12, 7)])
+@pytest.mark.parametrize("stages,chunk_tiles", [(2, 1), (3, 1000000), (4, 7)])
 def test_topk_filter_ring_and_item_shapes(sim, stages, chunk_tiles):
     from mammo_clip_dissect_b200 import _lib
     A = _filter_case("mixed", 30011, 388, seed=5)

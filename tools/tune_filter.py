@@ -42,15 +42,20 @@ def main():
     def say(label, ms, bytes_gb=gb):
         print("%-64s %8.3f ms  %7.0f GB/s" % (label, ms, bytes_gb / ms * 1e3), flush=True)
 
+    Z = torch.zeros_like(A[:, : min(K, 8192)])
+    Z[:200] = torch.arange(200, 0, -1, device=dev, dtype=torch.float32)[:, None]      # nothing passes after the first rows
+    zb = 4.0 * N * Z.shape[1] / 1e9
+    say("K2 filter form, nothing to append (streaming floor, %d cols)" % Z.shape[1], timeit(lambda: sim._topk_int32(Z, 100, dev)), zb)
+    del Z
     _lib.set_tunable("topk_filter", 1)
     say("K2 kept-set scan (round 1)", timeit(topk))
     _lib.set_tunable("topk_filter", 0)
-    for ns in ([6] if args.quick else [3, 4, 6, 8, 10]):
+    for ns in ([4] if args.quick else [2, 3, 4, 5, 6]):
         _lib.set_tunable("filter_stages", ns)
-        say("K2 filter form, ring of %d x 16 KB" % ns, timeit(topk))
+        say("K2 filter form, per-warp ring of %d x 4 KB" % ns, timeit(topk))
     _lib.set_tunable("filter_stages", 0)
     if not args.quick:
-        for ct in (21, 43, 170, 340):
+        for ct in (43, 85, 170, 340):
             _lib.set_tunable("filter_chunk_tiles", ct)
             say("K2 filter form, %d tiles per work item" % ct, timeit(topk))
         _lib.set_tunable("filter_chunk_tiles", 0)
@@ -64,7 +69,7 @@ def main():
     alg = (4.0 * N * K + 4.0 * N * C + 4.0 * K * C) / 1e9
     for q in ([-1, 1, 4] if args.quick else [-1, 1, 2, 3, 4, 5, 6, 8]):
         _lib.set_tunable("pipe_chunks", q)
-        for ns in ([0] if args.quick else [0, 4, 8]):
+        for ns in ([0] if args.quick else [0, 3]):
             _lib.set_tunable("filter_stages", ns)
             say("soft_wpmi, %d column chunk(s), ring %s" % (q, ns or "default"),
                 timeit(lambda: sim.soft_wpmi(P, A, device=dev)), alg)
