@@ -158,6 +158,13 @@ int mcd_pool_nchw(const void *x, mcd_dtype_t dtype, int64_t B, int64_t C, int64_
                   mcd_pool_t mode, void *out, void *workspace, size_t workspace_bytes,
                   mcd_stream_t stream);
 
+/* the same with the result row of image b at out[b * out_ld + c] (out_ld >= C elements), as `dtype` or as fp32
+ * (out_dtype) -- the hook writes straight into the [n_images, sum K_l] activation matrix -- and, with channels_last != 0,
+ * for activations stored in channels-last order ([B, H, W, C] in memory) without repacking them.  Same workspace. */
+int mcd_pool_nchw_to(const void *x, mcd_dtype_t dtype, int64_t B, int64_t C, int64_t H, int64_t W,
+                     int channels_last, mcd_pool_t mode, void *out, mcd_dtype_t out_dtype, int64_t out_ld,
+                     void *workspace, size_t workspace_bytes, mcd_stream_t stream);
+
 /* ---- cosine similarities (similarity.py:7-47), next rows of the scope table -------------
  *      column statistics of X [N,M]: cubed: mean[m] and norm[m] = max(||(x-mean)^3||_2, min_norm);
  *      plain: norm[m] = ||x||_2 (mean_out may be NULL). */

@@ -45,6 +45,7 @@ SIGNATURES = {
     "mcd_row_topk_f32": (_i32, [_p, _i64, _i64, _i64, _i64, _p, _p, _p]),
     "mcd_pool_nchw_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64]),
     "mcd_pool_nchw": (_i32, [_p, _i32, _i64, _i64, _i64, _i64, _i32, _p, _p, _sz, _p]),
+    "mcd_pool_nchw_to": (_i32, [_p, _i32, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i32, _i64, _p, _sz, _p]),
     "mcd_col_stats_f32": (_i32, [_p, _i64, _i64, _i64, _i32, _f32, _p, _p, _p]),
     "mcd_rank_reorder_f32": (_i32, [_p, _i64, _i64, _i64, _p, _p, _i64, _i64, _p, _f32, _f32, _p, _p, _i64, _p]),
     "mcd_cos_matmul_f32": (_i32, [_p, _i64, _p, _p, _p, _i64, _p, _p, _i64, _i64, _i64, _i32, _p, _i64, _p]),

@@ -30,8 +30,13 @@ def _workspace(device, nbytes):
     return buf
 
 
-def pool_nchw(x: torch.Tensor, mode: str) -> torch.Tensor:
-    """[B,C,H,W] CUDA tensor -> [B,C] spatial mean ('avg') or max ('max'), same dtype."""
+def pool_nchw(x: torch.Tensor, mode: str, out: torch.Tensor = None) -> torch.Tensor:
+    """[B,C,H,W] CUDA tensor -> [B,C] spatial mean ('avg') or max ('max').
+
+    out=None: a new [B,C] tensor of x's dtype (what the reference's hook appends).  Otherwise `out` is a [B,C] view with
+    unit column stride and any row stride, of x's dtype or fp32 -- e.g. rows of the stacked activation matrix --
+    and the kernel writes straight into it (mcd_pool_nchw_to).  Contiguous and channels-last activations are pooled
+    in place; other layouts are repacked once."""
     if x.dim() != 4:
         raise RuntimeError("pool_nchw expects a 4-D tensor")
     if not x.is_cuda:
@@ -42,21 +47,29 @@ def pool_nchw(x: torch.Tensor, mode: str) -> torch.Tensor:
     if B * C == 0 or H * W == 0:
         raise RuntimeError("pool_nchw: empty activation %s" % (tuple(x.shape),))
     x = x.detach()
+    channels_last = 0
     if not x.is_contiguous():
-        x = x.contiguous()          # channels_last / sliced activations: one repack, then the NCHW kernel
+        if x.is_contiguous(memory_format=torch.channels_last):
+            channels_last = 1           # memory order [B, H, W, C]: pooled in place by the channels-last kernel
+        else:
+            x = x.contiguous()          # sliced / permuted activations: one repack, then the NCHW kernel
     lib = _lib.lib()
-    out = torch.empty((B, C), dtype=x.dtype, device=x.device)
-    need = int(lib.mcd_pool_nchw_workspace_bytes(B, C, H, W))
-    ws = _workspace(x.device, need) if need else None      # only planes split across CTAs need partials
-    args = (ctypes.c_void_p(x.data_ptr()), _DTYPES[x.dtype], B, C, H, W,
-            _lib.POOL_MEAN if mode == "avg" else _lib.POOL_MAX, ctypes.c_void_p(out.data_ptr()),
-            ctypes.c_void_p(ws.data_ptr() if ws is not None else 0), need)
-    if x.device.index == torch.cuda.current_device():
-        code = lib.mcd_pool_nchw(*args, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    if out is None:
+        out = torch.empty((B, C), dtype=x.dtype, device=x.device)
     else:
-        with torch.cuda.device(x.device):
-            code = lib.mcd_pool_nchw(*args, ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
-    _lib.check(code, "mcd_pool_nchw")
+        if tuple(out.shape) != (B, C) or out.device != x.device or out.dtype not in (x.dtype, torch.float32) or \
+                (C > 1 and out.stride(1) != 1) or (B > 1 and out.stride(0) < C):
+            raise RuntimeError("pool_nchw: out must be a [%d, %d] view on %s with unit column stride, dtype %s or float32"
+                               % (B, C, x.device, x.dtype))
+    out_ld = out.stride(0) if B > 1 else max(C, 1)
+    need = int(lib.mcd_pool_nchw_workspace_bytes(B, C, H, W))
+    with torch.cuda.device(x.device):
+        ws = _workspace(x.device, need) if need else None      # only planes split across CTAs need partials
+        code = lib.mcd_pool_nchw_to(ctypes.c_void_p(x.data_ptr()), _DTYPES[x.dtype], B, C, H, W, channels_last,
+                                    _lib.POOL_MEAN if mode == "avg" else _lib.POOL_MAX, ctypes.c_void_p(out.data_ptr()),
+                                    _DTYPES[out.dtype], out_ld, ctypes.c_void_p(ws.data_ptr() if ws is not None else 0),
+                                    need, ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+    _lib.check(code, "mcd_pool_nchw_to")
     return out
 
 
@@ -126,19 +139,20 @@ class ActivationStack:
             if mode == "avg" and type(output) is tuple:
                 output = output[0]
             ndim = len(output.shape)
-            if ndim == 4:
-                pooled = pool_nchw(output, mode)
-            elif ndim == 3:
-                pooled = output[:, 0]
-            elif ndim == 2:
-                pooled = output
-            else:
+            if ndim not in (2, 3, 4):
                 return
-            B = pooled.shape[0]
+            B = output.shape[0]
+            width = output.shape[1] if ndim != 3 else output.shape[2]
             r = self.rows[l]
-            if pooled.shape[1] != hi - lo or r + B > self.matrix.shape[0]:
+            if width != hi - lo or r + B > self.matrix.shape[0]:
                 raise RuntimeError("ActivationStack: layer %d produced [%d, %d], expected width %d and at most %d more rows"
-                                   % (l, B, pooled.shape[1], hi - lo, self.matrix.shape[0] - r))
-            self.matrix[r:r + B, lo:hi].copy_(pooled.detach())
+                                   % (l, B, width, hi - lo, self.matrix.shape[0] - r))
+            dst = self.matrix[r:r + B, lo:hi]
+            if ndim == 4:
+                pool_nchw(output, mode, out=dst)        # K4 writes the rows of the stacked matrix itself
+            elif ndim == 3:
+                dst.copy_(output.detach()[:, 0])        # ViT: CLS token
+            else:
+                dst.copy_(output.detach())              # FC layers
             self.rows[l] = r + B
         return hook

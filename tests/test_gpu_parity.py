@@ -692,6 +692,35 @@ def test_pooling_nan_propagates(sim):
     assert torch.isnan(got[0, 1]) and torch.equal(torch.isnan(got), torch.isnan(x.amax(dim=[2, 3])))
 
 
+@pytest.mark.parametrize("shape", [(4, 24, 190, 114), (3, 40, 95, 57), (5, 128, 48, 29), (2, 304, 12, 9), (1, 7, 33, 5),
+                                   (6, 20, 3, 3)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("mode", ["avg", "max"])
+def test_pooling_channels_last_and_strided_output(sim, shape, dtype, mode):
+    """Channels-last activations are pooled in place (no repack), and the result may be written straight into rows of a
+    wider fp32 matrix (hooks.ActivationStack): same values as the NCHW kernel / torch."""
+    from mammo_clip_dissect_b200.hooks import pool_nchw
+    B, C, H, W = shape
+    x = (torch.randn(shape, generator=gen(B * C + H)) * 2 + 0.5).to(dtype).to(DEV)
+    ref = x.float().mean(dim=[2, 3]) if mode == "avg" else x.float().amax(dim=[2, 3])
+    tol = 1e-5 * x.float().abs().mean().item() if mode == "avg" else 0.0
+    xl = x.contiguous(memory_format=torch.channels_last)
+    assert not xl.is_contiguous() or C == 1 or H * W == 1
+    big = torch.full((B + 2, C + 11), -7.0, dtype=torch.float32, device=DEV)
+    for src in (x, xl):
+        got = pool_nchw(src, mode)
+        assert got.dtype == dtype and tuple(got.shape) == (B, C)
+        lim = tol if dtype == torch.float32 else tol + 2 ** -7 * ref.abs().max().item()
+        assert (got.float() - ref).abs().max().item() <= lim
+        big.fill_(-7.0)
+        view = big[1:1 + B, 5:5 + C]
+        assert pool_nchw(src, mode, out=view) is view
+        assert (view - ref).abs().max().item() <= tol                     # fp32 output: no rounding to the input dtype
+        assert bool((big[0] == -7).all() and (big[-1] == -7).all() and (big[:, :5] == -7).all() and (big[:, 5 + C:] == -7).all())
+    with pytest.raises(RuntimeError):
+        pool_nchw(x, mode, out=big[:B, :C].t().t()[:, ::1].to(torch.float64))
+
+
 # ------------------------------------------------------------------------------------------------
 # size-independent properties at a larger shape (the oracle would take minutes here)
 # ------------------------------------------------------------------------------------------------

@@ -1,0 +1,111 @@
+"""The UNMODIFIED reference driver end to end, on the GPU box (SURVEY.md section 4's acceptance test):
+
+    run A   python baseline/_ref/concept_vit/describe_clip_neurons.py ... --device cpu
+            -- the reference's own similarity.py / CLIP_og_utils.py, stock torch, on the CPU;
+    run B   the same file through mammo_clip_dissect_b200.shim.run_reference_driver ... --device cuda
+            -- `similarity.*`, the forward hook and get_similarity_from_activations resolved to the sm_100a kernels,
+            activations recomputed on the GPU (hooks fire inside the forward: K4 in situ);
+    run C   as B, but on run A's cached activation files (the hooks are skipped), which isolates K1 + scoring.
+
+descriptions.csv of C must name the same concept for every neuron (wherever the fp64 top-1/top-2 gap exceeds the fp32
+noise band) with the similarity within 1e-5 * max|L|; B may additionally differ where GPU and CPU convolutions round
+differently, so it is held to >= 98 % identical descriptions.  `clip` and `data_utils` are stubbed (no network, no
+datasets); baseline/_ref is produced by tools/stage_reference.py and travels with the gpurun snapshot."""
+import glob
+import os
+import subprocess
+import sys
+import textwrap
+
+import pandas as pd
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "baseline", "_ref", "concept_vit")
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not os.path.exists(os.path.join(REF, "describe_clip_neurons.py")),
+                                 reason="reference not staged (python tools/stage_reference.py)")]
+
+STUB_CLIP = """
+import torch
+class _M(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(11)
+        self.img = torch.nn.Linear(3 * 16 * 16, 64)
+        self.txt = torch.nn.Embedding(997, 64)
+    def encode_image(self, x):
+        return self.img(x.flatten(1))
+    def encode_text(self, t):
+        return self.txt(t[:, 0]) + 0.5 * self.txt(t[:, 1])
+def load(name, device="cpu"):
+    return _M().to(device).eval(), None
+def tokenize(words):
+    return torch.tensor([[sum(map(ord, w)) % 997, (7 * len(w) + ord(w[0])) % 997] for w in words])
+"""
+STUB_DATA = """
+import torch
+class _T(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        torch.manual_seed(12)
+        self.layer1 = torch.nn.Conv2d(3, 24, 3, padding=1)
+        self.layer2 = torch.nn.Conv2d(24, 40, 3, stride=2, padding=1)
+        self.fc = torch.nn.Linear(40 * 8 * 8, 30)
+    def forward(self, x):
+        return self.fc(torch.relu(self.layer2(torch.relu(self.layer1(x)))).flatten(1))
+def get_target_model(name, device):
+    return _T().to(device).eval(), None
+def get_data(name, preprocess=None):
+    g = torch.Generator().manual_seed(0)
+    return [(torch.randn(3, 16, 16, generator=g), 0) for _ in range(700)]
+"""
+
+
+def _run(tmp_path, tag, device, shim, act_dir):
+    stubs = tmp_path / "stubs"
+    if not stubs.exists():
+        stubs.mkdir()
+        (stubs / "clip.py").write_text(textwrap.dedent(STUB_CLIP))
+        (stubs / "data_utils.py").write_text(textwrap.dedent(STUB_DATA))
+        words = open(os.path.join(ROOT, "baseline", "_ref", "Concepts", "Specific_concepts_sorted.txt")).read().split("\n")
+        (tmp_path / "concepts.txt").write_text("\n".join(w for w in words if w != ""))
+    res = tmp_path / ("res_" + tag)
+    args = ["--target_layers", "layer1,layer2,fc", "--d_probe", "broden", "--concept_set", str(tmp_path / "concepts.txt"),
+            "--device", device, "--batch_size", "100", "--activation_dir", str(act_dir), "--result_dir", str(res),
+            "--similarity_fn", "soft_wpmi"]
+    env = dict(os.environ)
+    script = os.path.join(REF, "describe_clip_neurons.py")
+    if shim:
+        env.update(MCD_EXTRA_PATH=str(stubs), MCD_REFERENCE_DIR=REF, PYTHONPATH=ROOT)
+        cmd = [sys.executable, "-m", "mammo_clip_dissect_b200.shim.run_reference_driver", script] + args
+    else:
+        env.update(PYTHONPATH=str(stubs))          # sys.path[0] is the script's directory: the reference's own modules
+        cmd = [sys.executable, script] + args
+    r = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    files = glob.glob(str(res / "*" / "descriptions.csv"))
+    assert len(files) == 1, files
+    return pd.read_csv(files[0])
+
+
+def test_unmodified_driver_reference_cpu_vs_b200(tmp_path):
+    assert torch.cuda.is_available()
+    a = _run(tmp_path, "ref_cpu", "cpu", shim=False, act_dir=tmp_path / "act_ref")
+    c = _run(tmp_path, "ours_on_ref_activations", "cuda", shim=True, act_dir=tmp_path / "act_ref")
+    b = _run(tmp_path, "ours_gpu", "cuda", shim=True, act_dir=tmp_path / "act_gpu")
+    assert len(a) == 24 + 40 + 30 and list(a.columns) == list(c.columns) == list(b.columns)
+    for name, got, min_same in (("scoring on the reference's activations", c, 0.99), ("hooks + scoring on the GPU", b, 0.98)):
+        assert list(got["layer"]) == list(a["layer"]) and list(got["unit"]) == list(a["unit"])
+        same = (got["description"] == a["description"]).mean()
+        assert same >= min_same, (name, same)
+        # |L| is a few hundred here: 1e-5 * max|L| in absolute terms, as everywhere in the parity tests
+        m = got["description"] == a["description"]
+        err = (got["similarity"][m] - a["similarity"][m]).abs().max()
+        assert err <= 1e-2, (name, err)
+    # the cached-activation run must also pick the same most-activating images (stock torch.topk in both runs)
+    assert list(c["images"]) == list(a["images"])
+    print("descriptions identical: scoring-only %.4f, hooks+scoring %.4f" %
+          ((c["description"] == a["description"]).mean(), (b["description"] == a["description"]).mean()))
