@@ -201,7 +201,7 @@ int pmi_logsums(const float *P, int64_t ldp, const float *A, int64_t lda, int64_
         if (rc != MCD_OK) return rc;
         rc = mcd_topk_cols_f32(A, lda, N, K, k, nullptr, idx, nullptr, w + l.topk_off, workspace_bytes - l.topk_off, stream);
         if (rc != MCD_OK) return rc;
-        rc = mcd_wpmi_accum_f32(S, l.lds, N, C, idx, K, k, p, min_prob, L, ldl, stream);
+        rc = mcd_wpmi_accum_prob_f32(S, l.lds, N, C, idx, K, k, p, min_prob, L, ldl, stream);      // S is our own softmax
         if (rc != MCD_OK) return rc;
         return mcd_col_lse_partials_f32(L, ldl, K, C, part, stream);
     }
@@ -219,7 +219,7 @@ int pmi_logsums(const float *P, int64_t ldp, const float *A, int64_t lda, int64_
             return MCD_ERR_CUDA;
         rc = topk_filter_finish(call, c0, c1, nullptr, idx, nullptr, side);
         if (rc != MCD_OK) return rc;
-        rc = wpmi_accum_range(S, l.lds, N, C, idx + c0, K, c1 - c0, k, p, min_prob, L + c0 * ldl, ldl, side);
+        rc = wpmi_accum_range(S, l.lds, N, C, idx + c0, K, c1 - c0, k, p, min_prob, L + c0 * ldl, ldl, side, true);
         if (rc != MCD_OK) return rc;
         rc = mcd_col_lse_partials_f32(L + c0 * ldl, ldl, c1 - c0, C, part + (c0 / MCD_LSE_BLOCK) * 2 * C, side);
         if (rc != MCD_OK) return rc;

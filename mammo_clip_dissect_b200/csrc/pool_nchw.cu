@@ -315,10 +315,13 @@ static int pool_dispatch(const void *x, int64_t B, int64_t C, int64_t hw, int ch
 
 extern "C" size_t mcd_pool_nchw_workspace_bytes(int64_t B, int64_t C, int64_t H, int64_t W) {
     if (B < 1 || C < 1 || H < 1 || W < 1) return 0;
-    // enough for either memory order (the channels-last split count never exceeds 64)
+    // enough for either memory order: the channels-last kernel splits H*W the most when its channel tiles are the fewest
+    // (8 channels per 16-byte load)
     const int s = mcd::pool_splits(B * C, H * W);
     const size_t nchw = s > 1 ? size_t(B * C) * s * sizeof(float) : 0;
-    const size_t nhwc = size_t(B * C) * 64 * sizeof(float);
+    const int tiles_min = static_cast<int>(mcd::ceil_div<int64_t>(mcd::ceil_div<int64_t>(C, 8), 32));
+    const int sl = mcd::nhwc_splits(B, C, H * W, tiles_min);
+    const size_t nhwc = sl > 1 ? size_t(B * C) * sl * sizeof(float) : 0;
     return nchw > nhwc ? nchw : nhwc;
 }
 

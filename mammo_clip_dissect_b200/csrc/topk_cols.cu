@@ -1110,9 +1110,18 @@ int topk_filter_finish(const TopkFilterCall &c, int64_t col0, int64_t col1, int6
     const unsigned sgrid = static_cast<unsigned>(ceil_div<int64_t>(col1 - col0, kSelWarps));
     int kpad = 32;
     while (kpad < c.k) kpad <<= 1;
-#define MCD_SELECT(PER)                                                                                               \
-    topk_select_kernel<PER><<<sgrid, kSelWarps * 32, 0, st>>>(c.lists, c.cnt, p.f_cap, c.k, col0, col1, c.K, c.A, c.lda, \
-                                                             idx64, idx32, vals, c.flags)
+    // two launches split the columns: lists that fit the registers (the usual case), and -- only if the capacity allows
+    // longer ones at all -- the rest
+#define MCD_SELECT(PER)                                                                                                      \
+    do {                                                                                                                     \
+        topk_select_kernel<PER, true><<<sgrid, kSelWarps * 32, 0, st>>>(c.lists, c.cnt, p.f_cap, c.k, col0, col1, c.K, c.A,  \
+                                                                        c.lda, idx64, idx32, vals, c.flags);                \
+        if (p.f_cap > 32 * kSelRegWords) {                                                                                   \
+            count_launch(1);                                                                                                 \
+            topk_select_kernel<PER, false><<<sgrid, kSelWarps * 32, 0, st>>>(c.lists, c.cnt, p.f_cap, c.k, col0, col1, c.K,  \
+                                                                             c.A, c.lda, idx64, idx32, vals, c.flags);      \
+        }                                                                                                                    \
+    } while (0)
     switch (kpad) {
         case 32: MCD_SELECT(1); break;
         case 64: MCD_SELECT(2); break;

@@ -306,7 +306,7 @@ __device__ __forceinline__ void bitonic_desc_regs(unsigned long long (&v)[PER], 
     }
 }
 
-constexpr int kSelWarps = 8;
+constexpr int kSelWarps = 4;
 
 struct SelSmem {
     uint32_t hist[kSelWarps][32];
@@ -314,13 +314,18 @@ struct SelSmem {
     int count[kSelWarps];
 };
 
-// flags[col] = k when the column was resolved here, 0 when it has to be redone exactly (list short of k or overflowed)
-template <int PER>
+// flags[col] = k when the column was resolved here, 0 when it has to be redone exactly (list short of k or overflowed).
+// A list of up to 32 * T words is read ONCE (coalesced) and kept in registers, T words per lane -- the usual case: ~576
+// words at c4 --; longer lists are re-read from L2 in every pass (REG = false).
+constexpr int kSelRegWords = 32;
+
+template <int PER, bool REG>
 __global__ void __launch_bounds__(kSelWarps * 32)
 topk_select_kernel(const unsigned long long *__restrict__ lists, const int *__restrict__ cnt, int cap, int k,
                    int64_t col_first, int64_t col_end, int64_t K, const float *__restrict__ A, int64_t lda,
                    int64_t *__restrict__ idx64, int32_t *__restrict__ idx32, float *__restrict__ vals,
                    int *__restrict__ flags) {
+    constexpr int T = kSelRegWords;
     __shared__ SelSmem sm;
     __shared__ unsigned long long sortbuf[kSelWarps][32 * PER];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -328,17 +333,37 @@ topk_select_kernel(const unsigned long long *__restrict__ lists, const int *__re
     if (col >= col_end) return;
     const int n = cnt[col];
     if (n < k || n > cap) {
-        if (lane == 0) flags[col] = 0;
+        if (lane == 0 && REG) flags[col] = 0;
         return;
     }
+    // the two instantiations split the columns between them: REG takes the lists that fit the registers
+    if (REG != (n <= 32 * T)) return;
     if (lane == 0) flags[col] = k;
     const unsigned long long *ent = lists + col * cap;
-    unsigned long long lo = ~0ull, hi = 0ull;
-    for (int i = lane; i < n; i += 32) {
-        const unsigned long long e = ent[i];
-        lo = e < lo ? e : lo;
-        hi = e > hi ? e : hi;
+    const int tn = (n + 31) >> 5;                            // words per lane (rounded up)
+    unsigned long long e[T];
+    if (REG) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const int i = t * 32 + lane;
+            e[t] = (t < tn && i < n) ? ent[i] : 0ull;        // 0 sorts below every real word
+        }
     }
+    // visit every word of the list: from the registers, or from L2 again
+    auto for_each = [&](auto &&fn) {
+        if (REG) {
+#pragma unroll
+            for (int t = 0; t < T; ++t)
+                if (t < tn && e[t] != 0ull) fn(e[t]);
+        } else {
+            for (int i = lane; i < n; i += 32) fn(ent[i]);
+        }
+    };
+    unsigned long long lo = ~0ull, hi = 0ull;
+    for_each([&](unsigned long long w) {
+        lo = w < lo ? w : lo;
+        hi = w > hi ? w : hi;
+    });
     lo = warp_min_u64(lo);
     hi = warp_max_u64(hi);
     // invariant: the need-th largest of the m words inside [lo, hi] is the k-th largest of the list
@@ -349,10 +374,9 @@ topk_select_kernel(const unsigned long long *__restrict__ lists, const int *__re
         const int shift = bits > 5 ? bits - 5 : 0;            // (range >> shift) < 32
         sm.hist[warp][lane] = 0u;
         __syncwarp();
-        for (int i = lane; i < n; i += 32) {
-            const unsigned long long e = ent[i];
-            if (e >= lo && e <= hi) atomicAdd(&sm.hist[warp][(e - lo) >> shift], 1u);
-        }
+        for_each([&](unsigned long long w) {
+            if (w >= lo && w <= hi) atomicAdd(&sm.hist[warp][(w - lo) >> shift], 1u);
+        });
         __syncwarp();
         const uint32_t h = sm.hist[warp][lane];
         uint32_t incl = h;                                    // words in bins >= lane
@@ -376,10 +400,9 @@ topk_select_kernel(const unsigned long long *__restrict__ lists, const int *__re
     // the <= 32 words left: sort them across the lanes and read off the need-th largest
     if (lane == 0) sm.count[warp] = 0;
     __syncwarp();
-    for (int i = lane; i < n; i += 32) {
-        const unsigned long long e = ent[i];
-        if (e >= lo && e <= hi) sm.small[warp][atomicAdd(&sm.count[warp], 1)] = e;
-    }
+    for_each([&](unsigned long long w) {
+        if (w >= lo && w <= hi) sm.small[warp][atomicAdd(&sm.count[warp], 1)] = w;
+    });
     __syncwarp();
     unsigned long long x[1] = {lane < m ? sm.small[warp][lane] : 0ull};
     bitonic_desc_regs<1>(x, lane);
@@ -389,20 +412,19 @@ topk_select_kernel(const unsigned long long *__restrict__ lists, const int *__re
     if (lane == 0) sm.count[warp] = 0;
     for (int i = lane; i < 32 * PER; i += 32) sortbuf[warp][i] = 0ull;      // 0 sorts below every real word
     __syncwarp();
-    for (int i = lane; i < n; i += 32) {
-        const unsigned long long e = ent[i];
-        if (e >= kth) sortbuf[warp][atomicAdd(&sm.count[warp], 1)] = e;
-    }
+    for_each([&](unsigned long long w) {
+        if (w >= kth) sortbuf[warp][atomicAdd(&sm.count[warp], 1)] = w;
+    });
     __syncwarp();
     unsigned long long v[PER];
 #pragma unroll
-    for (int e = 0; e < PER; ++e) v[e] = sortbuf[warp][lane * PER + e];
+    for (int q = 0; q < PER; ++q) v[q] = sortbuf[warp][lane * PER + q];
     bitonic_desc_regs<PER>(v, lane);
 #pragma unroll
-    for (int e = 0; e < PER; ++e) {
-        const int r = lane * PER + e;
+    for (int q = 0; q < PER; ++q) {
+        const int r = lane * PER + q;
         if (r < k) {
-            const uint32_t row = ~static_cast<uint32_t>(v[e]);
+            const uint32_t row = ~static_cast<uint32_t>(v[q]);
             const int64_t o = int64_t(r) * K + col;
             if (idx64) idx64[o] = static_cast<int64_t>(row);
             if (idx32) idx32[o] = static_cast<int32_t>(row);

@@ -17,7 +17,11 @@ Differences from the reference, all supersets or stated rules:
     (torch.topk leaves both tie order and tie membership unspecified);
   * ``top_k`` is accepted and ignored by the cos functions (the reference's utils.py:602 passes it
     to every similarity function and its cos functions raise TypeError on it);
-  * nothing is printed, no tqdm bar, no empty_cache() calls.
+  * nothing is printed, no tqdm bar, no empty_cache() calls;
+  * numerics of the log-sums: the term 1 + p(s - 1) + eps is one FMA and the terms of 4 consecutive ranks are multiplied
+    before one MUFU lg2 (S is this module's own softmax, entries in [0, 1]): ~5e-8 relative on L against the reference's
+    fp32 operation order, the same size as the reference's own distance from its fp64 run (stated tolerance 1e-5; DESIGN.md
+    section 3).  `log_sums(..., probabilities=False)` / `mcd_wpmi_accum_f32` evaluate in the reference's order.
 """
 from __future__ import annotations
 
@@ -205,16 +209,19 @@ def _device_ramp(ramp, top_k, p_start, p_end, dev):
     return t
 
 
-def log_sums(S, idx32, weights, min_prob, out=None):
-    """K3: L[j,c] = sum_r log(1 + w_r (S[idx[r,j],c]-1) + eps)  (weights=None: sum_r log(S+eps))."""
+def log_sums(S, idx32, weights, min_prob, out=None, probabilities=True):
+    """K3: L[j,c] = sum_r log(1 + w_r (S[idx[r,j],c]-1) + eps)  (weights=None: sum_r log(S+eps)).
+    probabilities=True (S is a softmax output, entries in [0, 1]): grouped-log evaluation (mcd_wpmi_accum_prob_f32);
+    False: any S, the reference's operation order per term (mcd_wpmi_accum_f32)."""
     dev = S.device
     N, C = S.shape
     k, K = idx32.shape
     with torch.cuda.device(dev):
         if out is None:
             out = torch.empty((K, C), dtype=torch.float32, device=dev)
-        _lib.check(_lib.lib().mcd_wpmi_accum_f32(_ptr(S), _ld(S), N, C, _ptr(idx32), K, k, _ptr(weights), float(min_prob),
-                                                 _ptr(out), _ld(out), _stream(dev)), "mcd_wpmi_accum_f32")
+        fn = _lib.lib().mcd_wpmi_accum_prob_f32 if probabilities else _lib.lib().mcd_wpmi_accum_f32
+        _lib.check(fn(_ptr(S), _ld(S), N, C, _ptr(idx32), K, k, _ptr(weights), float(min_prob), _ptr(out), _ld(out),
+                      _stream(dev)), "mcd_wpmi_accum_f32")
     return out
 
 

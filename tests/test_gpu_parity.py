@@ -222,7 +222,8 @@ def test_topk_filter_form(sim, kind, N, K, k):
     n0 = _lib.launch_count()
     vals, idx = sim.topk_cols(A, k, device=DEV, want_values=True)
     # sample tile maxima, sample select, filter scan (+ the last N % 8 rows), select, redo scan, redo finish
-    assert _lib.launch_count() - n0 == 6 + (N % 8 != 0)
+    # (+ a second select launch for lists that do not fit the registers when the list capacity allows such lists)
+    assert 6 + (N % 8 != 0) <= _lib.launch_count() - n0 <= 7 + (N % 8 != 0)
     assert torch.equal(idx.cpu(), ref_i), kind
     assert torch.equal(vals.cpu().nan_to_num(7.0), ref_v.nan_to_num(7.0))
     try:
@@ -412,6 +413,25 @@ def test_accumulate_grouped_logs_and_fallbacks(sim, k, case):
         assert torch.equal(out.isnan(), ref.isnan())
     fin = ~ref.isnan()
     assert ((out[fin] - ref[fin]).abs() <= 1e-5 * ref[fin].abs() + 1e-6).all()
+
+
+def test_accumulate_plain_entry_keeps_the_reference_order_for_any_matrix(sim):
+    """mcd_wpmi_accum_f32 (no promise about S) evaluates every term in the reference's order: entries outside [0, 1] --
+    where the grouped evaluation could turn two negative terms into a positive product -- give the reference's NaN / -inf
+    pattern and values."""
+    S = torch.randn(300, 77, generator=gen(35)) * 0.6          # not a probability matrix: negative entries, entries > 1
+    k = 8
+    idx = torch.stack([torch.randperm(300, generator=gen(36 + j))[:k] for j in range(21)], dim=1)
+    w = orc.p_ramp(k, 0.998, 0.97)
+    for weights in (w, None):
+        ref = orc.log_sums_chunked(S, idx, weights, 1e-7)
+        assert ref.isnan().any()
+        out = sim.log_sums(S.to(DEV), idx.to(DEV).int(), None if weights is None else weights.to(DEV), 1e-7,
+                           probabilities=False).cpu()
+        assert torch.equal(out.isnan(), ref.isnan())
+        fin = torch.isfinite(ref)
+        assert torch.equal(torch.isinf(out), torch.isinf(ref))
+        assert ((out[fin] - ref[fin]).abs() <= 1e-5 * ref[fin].abs() + 1e-5).all()
 
 
 def test_tied_activations_use_the_stated_rule(sim):
