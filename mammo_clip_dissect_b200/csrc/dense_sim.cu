@@ -176,6 +176,45 @@ extern "C" int mcd_cos_matmul_f32(const float *A, int64_t lda, const float *mean
     return check_launch();
 }
 
+namespace mcd {
+size_t cos_matmul_tc_workspace(int64_t N, int64_t K, int64_t C);                                  // gemm_tf32x3.cu
+int cos_matmul_tc(const float *A, int64_t lda, const float *meanA, const float *normA, const float *P, int64_t ldp,
+                  const float *meanP, const float *normP, int64_t N, int64_t K, int64_t C, int cubed, float *out,
+                  int64_t ldo, void *ws, size_t ws_bytes, cudaStream_t st);
+static int g_last_cos_path = 0;
+}  // namespace mcd
+
+extern "C" int mcd_last_cos_path(void) { return mcd::g_last_cos_path; }
+
+extern "C" size_t mcd_cos_matmul_workspace_bytes(int64_t N, int64_t K, int64_t C) {
+    if (N < 1 || K < 1 || C < 1) return 0;
+    return mcd::cos_matmul_tc_workspace(N, K, C);
+}
+
+// tensor-core form (tcgen05 kind::tf32, 3-term split, periodic accumulator flush); falls back to the exact CUDA-core
+// kernel only when the tensor-map encoder is unavailable or tunable gemm_variant = 1 asks for it (mcd_last_cos_path tells)
+extern "C" int mcd_cos_matmul_tc_f32(const float *A, int64_t lda, const float *meanA, const float *normA, const float *P,
+                                     int64_t ldp, const float *meanP, const float *normP, int64_t N, int64_t K, int64_t C,
+                                     int cubed, float *out, int64_t ldo, void *workspace, size_t workspace_bytes,
+                                     mcd_stream_t stream) {
+    using namespace mcd;
+    if (!A || !P || !normA || !normP || !out || N < 1 || K < 1 || C < 1 || lda < K || ldp < C || ldo < C)
+        return MCD_ERR_INVALID_ARGUMENT;
+    if (cubed && (!meanA || !meanP)) return MCD_ERR_INVALID_ARGUMENT;
+    int rc = MCD_ERR_UNSUPPORTED;
+    if (tunable(kGemmVariant) != 1) {
+        if (!workspace || workspace_bytes < cos_matmul_tc_workspace(N, K, C)) return MCD_ERR_WORKSPACE;
+        rc = cos_matmul_tc(A, lda, meanA, normA, P, ldp, meanP, normP, N, K, C, cubed, out, ldo, workspace, workspace_bytes,
+                           static_cast<cudaStream_t>(stream));
+        if (rc == MCD_OK) g_last_cos_path = 1;
+    }
+    if (rc == MCD_ERR_UNSUPPORTED) {
+        rc = mcd_cos_matmul_f32(A, lda, meanA, normA, P, ldp, meanP, normP, N, K, C, cubed, out, ldo, stream);
+        if (rc == MCD_OK) g_last_cos_path = 3;
+    }
+    return rc;
+}
+
 // fp32 CUDA-core form of K1 (exact-fp32 reference semantics).  workspace: (N + C) floats of norms.
 namespace mcd {
 int sim_matrix_fp32(const float *I, int64_t ldi, const float *T, int64_t ldt, int64_t N, int64_t C, int64_t D,

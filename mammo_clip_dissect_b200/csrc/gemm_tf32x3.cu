@@ -384,6 +384,184 @@ gemm_tf32x3_band_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid
     }
 }
 
+// ---- cos / cos^3 similarities on the tensor cores (reference concept_vit/similarity.py:7-47) ---------------------------
+// out[j, c] = sum_i f(A[i, j]) * f(P[i, c]): the contraction runs over the N probe images, the slow axis of both
+// row-major inputs.  prepare_cols_kernel applies f (centre, cube, divide by the clipped norm -- the reference's fp32
+// operation sequence -- or divide by the norm), splits the result into hi + lo and writes it TRANSPOSED ([columns, images],
+// zero-padded to the tile grid), which makes both operands K-major for the same UMMA descriptors as K1.
+// gemm_tf32x3_long_kernel is K1's kernel for a long contraction: the tensor core's fp32 accumulation truncates, so an
+// accumulator is only trusted for kFlushBlocks k-blocks (48 MMAs, the same depth as K1 at D = 512); the k-blocks of a
+// group alternate between the two accumulators of a TMEM set, and while the MMA warp fills the other set the four
+// epilogue warps add the finished set into fp32 registers with round-to-nearest adds (a thread owns one output row:
+// 128 running sums).  The error therefore no longer grows with N.
+enum { kPrepCos = 1, kPrepCos3 = 2 };
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+prepare_cols_kernel(const float *__restrict__ X, int64_t ldx, int64_t N, int64_t M, const float *__restrict__ mean,
+                    const float *__restrict__ norm, float *__restrict__ Thi, float *__restrict__ Tlo, int64_t Npad) {
+    __shared__ float s_hi[32][33], s_lo[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t m0 = int64_t(blockIdx.x) * 32, i0 = int64_t(blockIdx.y) * 32;
+    const int64_t m = m0 + tx;
+    const float mu = (MODE == kPrepCos3 && m < M) ? mean[m] : 0.f;
+    const float nr = m < M ? norm[m] : 1.f;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t i = i0 + r;
+        float v = 0.f;
+        if (m < M && i < N) {
+            const float x = X[i * ldx + m];
+            if (MODE == kPrepCos3) {
+                const float d = __fsub_rn(x, mu);
+                v = __fdiv_rn(__fmul_rn(__fmul_rn(d, d), d), nr);
+            } else {
+                v = __fdiv_rn(x, nr);
+            }
+        }
+        const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+        s_hi[r][tx] = h;
+        s_lo[r][tx] = __fsub_rn(v, h);           // exact (NaN / inf stay NaN / inf in hi; lo becomes NaN: propagates)
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t o = (m0 + r) * Npad + i0 + tx;
+        Thi[o] = s_hi[tx][r];
+        Tlo[o] = s_lo[tx][r];
+    }
+}
+
+constexpr int kFlushBlocks = 8;                          // k-blocks per accumulator group (2 accumulators x 4 k-blocks)
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+gemm_tf32x3_long_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
+                        const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
+                        int64_t M, int64_t Nn, int num_kb, float *__restrict__ Cout, int64_t ldc) {
+    extern __shared__ unsigned char smem_dyn[];
+    const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
+    unsigned char *aligned = smem_dyn + (base - smem_u32(smem_dyn));
+    uint64_t *full = reinterpret_cast<uint64_t *>(aligned + size_t(kGemmStages) * kStageBytes);
+    uint64_t *empty = full + kGemmStages;
+    uint64_t *tmem_full = empty + kGemmStages;           // [2]: one per TMEM set
+    uint64_t *tmem_empty = tmem_full + 2;                // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+    const int ngroups = (num_kb + kFlushBlocks - 1) / kFlushBlocks;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kGemmStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tmem_full[s], 1);
+            mbar_init(&tmem_empty[s], 4);        // one arrival per epilogue warp
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) {     // TMEM: 2 sets x 2 accumulators x 128 fp32 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % kGemmStages, use = kb / kGemmStages;
+                if (use > 0) mbar_wait_bounded(&empty[s], (use - 1) & 1);
+                mbar_arrive_expect_tx(&full[s], kStageBytes);
+                const uint32_t st = base + s * kStageBytes;
+                const int kx = kb * kBK;
+                tma_load_2d(st, &mapAhi, kx, m_tile * kBM, &full[s]);
+                tma_load_2d(st + kATileBytes, &mapAlo, kx, m_tile * kBM, &full[s]);
+                tma_load_2d(st + 2 * kATileBytes, &mapBhi, kx, n_tile * kBN, &full[s]);
+                tma_load_2d(st + 2 * kATileBytes + kBTileBytes, &mapBlo, kx, n_tile * kBN, &full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int g = kb / kFlushBlocks, in_g = kb - g * kFlushBlocks, set = g & 1;
+                if (in_g == 0 && g >= 2) {                   // the epilogue has drained this set's previous group
+                    mbar_wait_bounded(&tmem_empty[set], ((g >> 1) - 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                }
+                const int s = kb % kGemmStages, use = kb / kGemmStages;
+                mbar_wait_bounded(&full[s], use & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t st = base + s * kStageBytes;
+                const uint64_t ahi = umma_desc_k128(st), alo = umma_desc_k128(st + kATileBytes);
+                const uint64_t bhi = umma_desc_k128(st + 2 * kATileBytes), blo = umma_desc_k128(st + 2 * kATileBytes + kBTileBytes);
+                const uint32_t acc = tmem_base + uint32_t(set * 2 + (in_g & 1)) * kBN;
+                for (int kk = 0; kk < kBK / 8; ++kk) {
+                    const uint64_t adv = uint64_t((kk * 32) >> 4);
+                    umma_tf32(acc, ahi + adv, bhi + adv, in_g >= 2 || kk > 0);      // first use of the accumulator in its group: overwrite
+                    umma_tf32(acc, ahi + adv, blo + adv, true);
+                    umma_tf32(acc, alo + adv, bhi + adv, true);
+                }
+                umma_commit(&empty[s]);
+                if (in_g == kFlushBlocks - 1 || kb == num_kb - 1) umma_commit(&tmem_full[set]);
+            }
+        }
+    } else {
+        const int quarter = warp & 3;
+        float sum[kBN];
+#pragma unroll
+        for (int i = 0; i < kBN; ++i) sum[i] = 0.f;
+#pragma unroll 1
+        for (int g = 0; g < ngroups; ++g) {
+            const int set = g & 1;
+            mbar_wait_bounded(&tmem_full[set], (g >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const bool two = num_kb - g * kFlushBlocks >= 2;                         // the group used both accumulators
+            const uint32_t t0 = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(set * 2) * kBN;
+#pragma unroll
+            for (int c = 0; c < kBN; c += 32) {
+                float v[32];
+                tmem_ld_32x32(t0 + uint32_t(c), v);
+                if (two) {
+                    float w[32];
+                    tmem_ld_32x32(t0 + uint32_t(kBN + c), w);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __fadd_rn(v[i], w[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 32; ++i) sum[c + i] = __fadd_rn(sum[c + i], v[i]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[set]);
+        }
+        const int64_t row = int64_t(m_tile) * kBM + quarter * 32 + lane;
+        const int64_t col0 = int64_t(n_tile) * kBN;
+        if (row < M) {
+            float *dst = Cout + row * ldc + col0;
+            const bool vec_ok = (ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(Cout) % 16 == 0) && col0 + kBN <= Nn;
+            if (vec_ok) {
+#pragma unroll
+                for (int i = 0; i < kBN; i += 4) *reinterpret_cast<float4 *>(dst + i) = make_float4(sum[i], sum[i + 1], sum[i + 2], sum[i + 3]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < kBN; ++i)
+                    if (col0 + i < Nn) dst[i] = sum[i];
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    }
+}
+
 // ---- host ---------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn2)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -450,6 +628,55 @@ int sim_matrix_tc(const float *I, int64_t ldi, const float *T, int64_t ldt, int6
     dim3 grid(static_cast<unsigned>(Cp / kBN), static_cast<unsigned>(Np / kBM));
     gemm_tf32x3_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(mAhi, mAlo, mBhi, mBlo, N, C, static_cast<int>(Dp / kBK), P, ldp);
     return check_launch();
+}
+
+// ---- cos / cos^3 host: transposed hi/lo operands (neuron slabs bound the workspace), then the long-contraction GEMM ------
+constexpr int64_t kCosSlab = 8192;                       // neurons per slab
+
+size_t cos_matmul_tc_workspace(int64_t N, int64_t K, int64_t C) {
+    const int64_t Np = ceil_div<int64_t>(N, kBK) * kBK, Cp = ceil_div<int64_t>(C, kBN) * kBN;
+    const int64_t Ks = K < kCosSlab ? K : kCosSlab, Kp = ceil_div<int64_t>(Ks, kBM) * kBM;
+    return size_t(Kp + Cp) * size_t(Np) * 2 * sizeof(float) + 1024;
+}
+
+int cos_matmul_tc(const float *A, int64_t lda, const float *meanA, const float *normA, const float *P, int64_t ldp,
+                  const float *meanP, const float *normP, int64_t N, int64_t K, int64_t C, int cubed, float *out,
+                  int64_t ldo, void *ws, size_t ws_bytes, cudaStream_t st) {
+    const int64_t Np = ceil_div<int64_t>(N, kBK) * kBK, Cp = ceil_div<int64_t>(C, kBN) * kBN;
+    const int64_t Ks = K < kCosSlab ? K : kCosSlab, Kp = ceil_div<int64_t>(Ks, kBM) * kBM;
+    if (ws_bytes < cos_matmul_tc_workspace(N, K, C)) return MCD_ERR_WORKSPACE;
+    if (Np > (int64_t(1) << 31) - 64) return MCD_ERR_UNSUPPORTED;      // TMA coordinates are 32-bit
+    if (!encode_fn2()) return MCD_ERR_UNSUPPORTED;
+    char *w = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
+    float *Phi = reinterpret_cast<float *>(w);
+    float *Plo = Phi + Cp * Np;
+    float *Ahi = Plo + Cp * Np;
+    float *Alo = Ahi + Kp * Np;
+    if (cudaFuncSetAttribute(gemm_tf32x3_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTcSmemBytes)) != cudaSuccess)
+        return MCD_ERR_CUDA;
+    CUtensorMap mBhi, mBlo;
+    if (!make_operand_map(&mBhi, Phi, Cp, Np, kBN) || !make_operand_map(&mBlo, Plo, Cp, Np, kBN)) return MCD_ERR_UNSUPPORTED;
+    dim3 pgrid(static_cast<unsigned>(Cp / 32), static_cast<unsigned>(Np / 32));
+    if (cubed) prepare_cols_kernel<kPrepCos3><<<pgrid, 256, 0, st>>>(P, ldp, N, C, meanP, normP, Phi, Plo, Np);
+    else prepare_cols_kernel<kPrepCos><<<pgrid, 256, 0, st>>>(P, ldp, N, C, nullptr, normP, Phi, Plo, Np);
+    int rc = check_launch();
+    if (rc != MCD_OK) return rc;
+    for (int64_t k0 = 0; k0 < K; k0 += kCosSlab) {
+        const int64_t kn = K - k0 < kCosSlab ? K - k0 : kCosSlab, kp = ceil_div<int64_t>(kn, kBM) * kBM;
+        CUtensorMap mAhi, mAlo;
+        if (!make_operand_map(&mAhi, Ahi, kp, Np, kBM) || !make_operand_map(&mAlo, Alo, kp, Np, kBM)) return MCD_ERR_UNSUPPORTED;
+        dim3 agrid(static_cast<unsigned>(kp / 32), static_cast<unsigned>(Np / 32));
+        if (cubed) prepare_cols_kernel<kPrepCos3><<<agrid, 256, 0, st>>>(A + k0, lda, N, kn, meanA + k0, normA + k0, Ahi, Alo, Np);
+        else prepare_cols_kernel<kPrepCos><<<agrid, 256, 0, st>>>(A + k0, lda, N, kn, nullptr, normA + k0, Ahi, Alo, Np);
+        rc = check_launch();
+        if (rc != MCD_OK) return rc;
+        dim3 grid(static_cast<unsigned>(Cp / kBN), static_cast<unsigned>(kp / kBM));
+        gemm_tf32x3_long_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(mAhi, mAlo, mBhi, mBlo, kn, C, static_cast<int>(Np / kBK),
+                                                                        out + k0 * ldo, ldo);
+        rc = check_launch();
+        if (rc != MCD_OK) return rc;
+    }
+    return MCD_OK;
 }
 
 }  // namespace mcd

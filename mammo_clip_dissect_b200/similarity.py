@@ -489,10 +489,16 @@ def _cos(clip_feats, target_feats, device, cubed, min_norm):
         _lib.check(lib.mcd_col_stats_f32(_ptr(A), _ld(A), N, K, int(cubed), float(min_norm), _ptr(meanA), _ptr(normA),
                                          st), "mcd_col_stats_f32")
         out = torch.empty((K, C), dtype=torch.float32, device=dev)
-        _lib.check(lib.mcd_cos_matmul_f32(_ptr(A), _ld(A), _ptr(meanA), _ptr(normA), _ptr(P), _ld(P), _ptr(meanP),
-                                          _ptr(normP), N, K, C, int(cubed), _ptr(out), _ld(out), st),
-                   "mcd_cos_matmul_f32")
+        ws = _workspace(int(lib.mcd_cos_matmul_workspace_bytes(N, K, C)), dev)
+        _lib.check(lib.mcd_cos_matmul_tc_f32(_ptr(A), _ld(A), _ptr(meanA), _ptr(normA), _ptr(P), _ld(P), _ptr(meanP),
+                                             _ptr(normP), N, K, C, int(cubed), _ptr(out), _ld(out), _ptr(ws), ws.numel(),
+                                             st), "mcd_cos_matmul_tc_f32")
     return out
+
+
+def last_cos_path():
+    """Which kernel the last cos_similarity / cos_similarity_cubed call ran: 'tcgen05' or 'fp32_ffma'."""
+    return {1: "tcgen05", 3: "fp32_ffma"}.get(int(_lib.lib().mcd_last_cos_path()), "none")
 
 
 def cos_similarity_cubed(clip_feats, target_feats, device='cuda', batch_size=10000, min_norm=1e-3, top_k=None):

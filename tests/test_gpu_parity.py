@@ -353,6 +353,43 @@ def test_golden_odd_misc(sim, golden):
     assert (sim.wpmi(P, A, top_k=5, a=7, lam=1.5, min_prob=1e-5, device=DEV).cpu() - g["wpmi_params"]).abs().max().item() <= 1e-3
 
 
+@pytest.mark.parametrize("N,K,C", [(5000, 512, 763), (20011, 300, 763), (130, 37, 33), (4096, 129, 1), (33, 5, 200)])
+@pytest.mark.parametrize("cubed", [False, True])
+def test_cos_similarities_on_the_tensor_cores(sim, N, K, C, cubed):
+    """cos / cos^3 run as a tcgen05 3xTF32 GEMM with the contraction over the probe images (accumulators flushed into
+    fp32 registers every 8 k-blocks): fp32-grade against the reference's formula in fp64 for any N, and the same
+    numbers (to fp32 noise) as the exact CUDA-core kernel."""
+    from mammo_clip_dissect_b200 import _lib
+    P = torch.randn(N, C, generator=gen(N + 1)) * 0.05 + 0.2
+    A = torch.randn(N, K, generator=gen(N + 2)) * torch.rand(1, K, generator=gen(N + 3)) * 3 + 0.7
+    fn = sim.cos_similarity_cubed if cubed else sim.cos_similarity
+    got = fn(P, A, device=DEV).cpu()
+    assert sim.last_cos_path() == "tcgen05"
+    ref64 = (orc.cos_similarity_cubed if cubed else orc.cos_similarity)(P.double(), A.double())
+    try:
+        _lib.set_tunable("gemm_variant", 1)
+        ffma = fn(P, A, device=DEV).cpu()
+        assert sim.last_cos_path() == "fp32_ffma"
+    finally:
+        _lib.set_tunable("gemm_variant", 0)
+    scale = ref64.abs().max().item()
+    e_tc, e_ffma = (got.double() - ref64).abs().max().item(), (ffma.double() - ref64).abs().max().item()
+    assert e_tc <= 1e-5 * scale, (e_tc, e_ffma, scale)
+    assert e_tc <= max(4 * e_ffma, 2e-6 * scale), (e_tc, e_ffma)          # no worse than true-fp32 arithmetic
+
+
+def test_cos_similarity_cubed_single_is_the_matched_pair_diagonal(sim):
+    """Not in the reference tree (BASELINE's north star names it): the diagonal of cos_similarity_cubed for equally shaped
+    inputs."""
+    X = torch.randn(700, 41, generator=gen(71))
+    Y = X * 0.5 + torch.randn(700, 41, generator=gen(72))
+    d = sim.cos_similarity_cubed_single(X, Y, device=DEV).cpu()
+    full = orc.cos_similarity_cubed(X.double(), Y.double())
+    assert tuple(d.shape) == (41,) and (d.double() - torch.diagonal(full)).abs().max().item() <= 1e-5
+    with pytest.raises(RuntimeError):
+        sim.cos_similarity_cubed_single(X, Y[:, :40], device=DEV)
+
+
 def test_config_c1_full(sim):
     """BASELINE config c1: clip_feats 2000 x 763, target_feats 2000 x 2048, top_k = 100."""
     I = torch.randn(2000, 512, generator=gen(0))
