@@ -186,15 +186,16 @@ int mcd_cos_matmul_f32(const float *A, int64_t lda, const float *meanA, const fl
                        int64_t N, int64_t K, int64_t C, int cubed,
                        float *out, int64_t ldo, mcd_stream_t stream);
 
-/* the same contraction on the tensor cores: f(A), f(P) are written transposed as hi + lo fp32 pairs into `workspace`
- * (neurons in slabs of 8192) and multiplied by a tcgen05 kind::tf32 3-term-split GEMM whose TMEM accumulators are
- * flushed into fp32 registers every 8 k-blocks (fp32-grade result for any N).  mcd_last_cos_path(): 1 tensor cores,
- * 3 the CUDA-core kernel above (tensor-map encoder unavailable, or tunable gemm_variant = 1). */
-size_t mcd_cos_matmul_workspace_bytes(int64_t N, int64_t K, int64_t C);
-int mcd_cos_matmul_tc_f32(const float *A, int64_t lda, const float *meanA, const float *normA,
-                          const float *P, int64_t ldp, const float *meanP, const float *normP,
-                          int64_t N, int64_t K, int64_t C, int cubed, float *out, int64_t ldo,
-                          void *workspace, size_t workspace_bytes, mcd_stream_t stream);
+/* the whole cos_similarity / cos_similarity_cubed call (similarity.py:7-47) behind one entry point, on the tensor cores:
+ * row-parallel column statistics of P [N,C] and A [N,K]; f(A), f(P) written transposed as hi + lo fp32 pairs into
+ * `workspace` (neurons in slabs of 8192); out [K,C] = f(A)^T f(P) by a tcgen05 kind::tf32 3-term-split GEMM whose TMEM
+ * accumulators are flushed into fp32 registers every 8 k-blocks (fp32-grade result for any N), split-K when the output
+ * tiles alone would leave SMs idle.  min_norm is used by the cubed form only.  mcd_last_cos_path(): 1 tensor cores,
+ * 3 the CUDA-core kernels above (tensor-map encoder unavailable, or tunable gemm_variant = 1). */
+size_t mcd_cos_similarity_workspace_bytes(int64_t N, int64_t K, int64_t C);
+int mcd_cos_similarity_f32(const float *P, int64_t ldp, const float *A, int64_t lda, int64_t N, int64_t K, int64_t C,
+                           int cubed, float min_norm, float *out, int64_t ldo,
+                           void *workspace, size_t workspace_bytes, mcd_stream_t stream);
 int mcd_last_cos_path(void);
 
 /* ---- rank_reorder (similarity.py:99-132).  idx / vals [top_n, K] from mcd_topk_cols_f32 (top_n = int(0.05 N) <= 512),

@@ -177,38 +177,43 @@ extern "C" int mcd_cos_matmul_f32(const float *A, int64_t lda, const float *mean
 }
 
 namespace mcd {
-size_t cos_matmul_tc_workspace(int64_t N, int64_t K, int64_t C);                                  // gemm_tf32x3.cu
-int cos_matmul_tc(const float *A, int64_t lda, const float *meanA, const float *normA, const float *P, int64_t ldp,
-                  const float *meanP, const float *normP, int64_t N, int64_t K, int64_t C, int cubed, float *out,
-                  int64_t ldo, void *ws, size_t ws_bytes, cudaStream_t st);
+size_t cos_similarity_tc_workspace(int64_t N, int64_t K, int64_t C);                              // gemm_tf32x3.cu
+int cos_similarity_tc(const float *P, int64_t ldp, const float *A, int64_t lda, int64_t N, int64_t K, int64_t C, int cubed,
+                      float min_norm, float *out, int64_t ldo, void *ws, size_t ws_bytes, cudaStream_t st);
 static int g_last_cos_path = 0;
 }  // namespace mcd
 
 extern "C" int mcd_last_cos_path(void) { return mcd::g_last_cos_path; }
 
-extern "C" size_t mcd_cos_matmul_workspace_bytes(int64_t N, int64_t K, int64_t C) {
+extern "C" size_t mcd_cos_similarity_workspace_bytes(int64_t N, int64_t K, int64_t C) {
     if (N < 1 || K < 1 || C < 1) return 0;
-    return mcd::cos_matmul_tc_workspace(N, K, C);
+    // the tensor-core path's buffers, or the CUDA-core path's column statistics (2 x (K + C) floats)
+    const size_t tc = mcd::cos_similarity_tc_workspace(N, K, C), cc = size_t(2) * size_t(K + C) * sizeof(float) + 256;
+    return tc > cc ? tc : cc;
 }
 
-// tensor-core form (tcgen05 kind::tf32, 3-term split, periodic accumulator flush); falls back to the exact CUDA-core
-// kernel only when the tensor-map encoder is unavailable or tunable gemm_variant = 1 asks for it (mcd_last_cos_path tells)
-extern "C" int mcd_cos_matmul_tc_f32(const float *A, int64_t lda, const float *meanA, const float *normA, const float *P,
-                                     int64_t ldp, const float *meanP, const float *normP, int64_t N, int64_t K, int64_t C,
-                                     int cubed, float *out, int64_t ldo, void *workspace, size_t workspace_bytes,
-                                     mcd_stream_t stream) {
+// The whole cos_similarity / cos_similarity_cubed call (similarity.py:7-47) behind one entry point: column statistics of
+// both matrices, then out [K, C] = f(A)^T f(P) on the tensor cores (gemm_tf32x3.cu).  Falls back to the exact CUDA-core
+// kernels only when the tensor-map encoder is unavailable or tunable gemm_variant = 1 asks for it (mcd_last_cos_path tells).
+extern "C" int mcd_cos_similarity_f32(const float *P, int64_t ldp, const float *A, int64_t lda, int64_t N, int64_t K,
+                                      int64_t C, int cubed, float min_norm, float *out, int64_t ldo, void *workspace,
+                                      size_t workspace_bytes, mcd_stream_t stream) {
     using namespace mcd;
-    if (!A || !P || !normA || !normP || !out || N < 1 || K < 1 || C < 1 || lda < K || ldp < C || ldo < C)
-        return MCD_ERR_INVALID_ARGUMENT;
-    if (cubed && (!meanA || !meanP)) return MCD_ERR_INVALID_ARGUMENT;
+    if (!P || !A || !out || N < 1 || K < 1 || C < 1 || ldp < C || lda < K || ldo < C) return MCD_ERR_INVALID_ARGUMENT;
+    if (!workspace || workspace_bytes < mcd_cos_similarity_workspace_bytes(N, K, C)) return MCD_ERR_WORKSPACE;
     int rc = MCD_ERR_UNSUPPORTED;
     if (tunable(kGemmVariant) != 1) {
-        if (!workspace || workspace_bytes < cos_matmul_tc_workspace(N, K, C)) return MCD_ERR_WORKSPACE;
-        rc = cos_matmul_tc(A, lda, meanA, normA, P, ldp, meanP, normP, N, K, C, cubed, out, ldo, workspace, workspace_bytes,
-                           static_cast<cudaStream_t>(stream));
+        rc = cos_similarity_tc(P, ldp, A, lda, N, K, C, cubed, min_norm, out, ldo, workspace, workspace_bytes,
+                               static_cast<cudaStream_t>(stream));
         if (rc == MCD_OK) g_last_cos_path = 1;
     }
     if (rc == MCD_ERR_UNSUPPORTED) {
+        float *st = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+        float *meanP = st, *normP = st + C, *meanA = st + 2 * C, *normA = st + 2 * C + K;
+        rc = mcd_col_stats_f32(P, ldp, N, C, cubed, min_norm, meanP, normP, stream);
+        if (rc != MCD_OK) return rc;
+        rc = mcd_col_stats_f32(A, lda, N, K, cubed, min_norm, meanA, normA, stream);
+        if (rc != MCD_OK) return rc;
         rc = mcd_cos_matmul_f32(A, lda, meanA, normA, P, ldp, meanP, normP, N, K, C, cubed, out, ldo, stream);
         if (rc == MCD_OK) g_last_cos_path = 3;
     }

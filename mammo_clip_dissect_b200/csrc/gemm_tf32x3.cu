@@ -396,16 +396,67 @@ gemm_tf32x3_band_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid
 // 128 running sums).  The error therefore no longer grows with N.
 enum { kPrepCos = 1, kPrepCos3 = 2 };
 
+// Column statistics in two row-parallel passes (the thread-per-column form of dense_sim.cu leaves all but a few SMs idle
+// for the 763-concept matrix): grid (column groups of 32, row chunks); a block reduces its chunk over 8 row lanes and
+// writes one partial per column, part[chunk][column]; consumers add the chunks in order (fixed order: deterministic).
+//   STAT 0: sum x                      STAT 1: sum x^2                      STAT 2: sum ((x - mean)^3)^2
+template <int STAT>
+__global__ void __launch_bounds__(256)
+col_partial_kernel(const float *__restrict__ X, int64_t ldx, int64_t N, int64_t M, int64_t rows_per_chunk,
+                   const float *__restrict__ sum_part, int n_chunks, float *__restrict__ part) {
+    __shared__ float red[8][33];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int64_t m = int64_t(blockIdx.x) * 32 + cx;
+    const int64_t r0 = int64_t(blockIdx.y) * rows_per_chunk, r1 = min(N, r0 + rows_per_chunk);
+    float mean = 0.f;
+    if (STAT == 2 && m < M) {
+        float t = 0.f;
+        for (int q = 0; q < n_chunks; ++q) t += sum_part[int64_t(q) * M + m];
+        mean = t / static_cast<float>(N);
+    }
+    float s = 0.f;
+    if (m < M)
+        for (int64_t i = r0 + ry; i < r1; i += 8) {
+            float v = X[i * ldx + m];
+            if (STAT == 2) {
+                const float d = __fsub_rn(v, mean);
+                v = __fmul_rn(__fmul_rn(d, d), d);
+            }
+            s = STAT == 0 ? s + v : fmaf(v, v, s);
+        }
+    red[ry][cx] = s;
+    __syncthreads();
+    if (ry == 0 && m < M) {
+        float t = red[0][cx];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) t += red[q][cx];
+        part[int64_t(blockIdx.y) * M + m] = t;
+    }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256)
-prepare_cols_kernel(const float *__restrict__ X, int64_t ldx, int64_t N, int64_t M, const float *__restrict__ mean,
-                    const float *__restrict__ norm, float *__restrict__ Thi, float *__restrict__ Tlo, int64_t Npad) {
+prepare_cols_kernel(const float *__restrict__ X, int64_t ldx, int64_t N, int64_t M, const float *__restrict__ sum_part,
+                    const float *__restrict__ sq_part, int n_chunks, int64_t part_ld, float min_norm,
+                    float *__restrict__ Thi, float *__restrict__ Tlo, int64_t Npad) {
     __shared__ float s_hi[32][33], s_lo[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int64_t m0 = int64_t(blockIdx.x) * 32, i0 = int64_t(blockIdx.y) * 32;
     const int64_t m = m0 + tx;
-    const float mu = (MODE == kPrepCos3 && m < M) ? mean[m] : 0.f;
-    const float nr = m < M ? norm[m] : 1.f;
+    float mu = 0.f, nr = 1.f;
+    if (m < M) {
+        float t = 0.f, q2 = 0.f;
+        for (int q = 0; q < n_chunks; ++q) {
+            if (MODE == kPrepCos3) t += sum_part[int64_t(q) * part_ld + m];
+            q2 += sq_part[int64_t(q) * part_ld + m];
+        }
+        mu = t / static_cast<float>(N);
+        nr = sqrtf(q2);
+        if (MODE == kPrepCos3) {
+            nr = fmaxf(nr, min_norm);            // torch.clip(norm, min_norm); NaN stays NaN
+            if (q2 != q2) nr = q2;
+        }
+    }
 #pragma unroll
     for (int r = ty; r < 32; r += 8) {
         const int64_t i = i0 + r;
@@ -432,12 +483,24 @@ prepare_cols_kernel(const float *__restrict__ X, int64_t ldx, int64_t N, int64_t
     }
 }
 
+// out = sum of the split-K partial tiles, in split order
+__global__ void __launch_bounds__(256)
+splitk_combine_kernel(const float *__restrict__ part, int splits, int64_t M, int64_t Nn, int64_t ldpart, int64_t plane,
+                      float *__restrict__ out, int64_t ldo) {
+    const int64_t n = int64_t(blockIdx.x) * 256 + threadIdx.x, m = blockIdx.y;
+    if (n >= Nn) return;
+    float t = part[m * ldpart + n];
+    for (int s = 1; s < splits; ++s) t = __fadd_rn(t, part[int64_t(s) * plane + m * ldpart + n]);
+    out[m * ldo + n] = t;
+}
+
 constexpr int kFlushBlocks = 8;                          // k-blocks per accumulator group (2 accumulators x 4 k-blocks)
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tf32x3_long_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                         const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
-                        int64_t M, int64_t Nn, int num_kb, float *__restrict__ Cout, int64_t ldc) {
+                        int64_t M, int64_t Nn, int total_kb, int kb_per_split, float *__restrict__ Cout, int64_t ldc,
+                        int64_t split_plane) {
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     unsigned char *aligned = smem_dyn + (base - smem_u32(smem_dyn));
@@ -449,6 +512,10 @@ gemm_tf32x3_long_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+    // split-K: blockIdx.z takes k-blocks [kb_first, kb_first + num_kb) and writes its own output plane
+    const int kb_first = blockIdx.z * kb_per_split;
+    const int num_kb = min(kb_per_split, total_kb - kb_first);
+    Cout += int64_t(blockIdx.z) * split_plane;
     const int ngroups = (num_kb + kFlushBlocks - 1) / kFlushBlocks;
 
     if (threadIdx.x == 0) {
@@ -478,7 +545,7 @@ gemm_tf32x3_long_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid
                 if (use > 0) mbar_wait_bounded(&empty[s], (use - 1) & 1);
                 mbar_arrive_expect_tx(&full[s], kStageBytes);
                 const uint32_t st = base + s * kStageBytes;
-                const int kx = kb * kBK;
+                const int kx = (kb_first + kb) * kBK;
                 tma_load_2d(st, &mapAhi, kx, m_tile * kBM, &full[s]);
                 tma_load_2d(st + kATileBytes, &mapAlo, kx, m_tile * kBM, &full[s]);
                 tma_load_2d(st + 2 * kATileBytes, &mapBhi, kx, n_tile * kBN, &full[s]);
@@ -630,51 +697,115 @@ int sim_matrix_tc(const float *I, int64_t ldi, const float *T, int64_t ldt, int6
     return check_launch();
 }
 
-// ---- cos / cos^3 host: transposed hi/lo operands (neuron slabs bound the workspace), then the long-contraction GEMM ------
+// ---- cos / cos^3 host: column statistics, transposed hi/lo operands (neuron slabs bound the workspace), long GEMM ---------
 constexpr int64_t kCosSlab = 8192;                       // neurons per slab
+constexpr int kMaxStatChunks = 64;
 
-size_t cos_matmul_tc_workspace(int64_t N, int64_t K, int64_t C) {
-    const int64_t Np = ceil_div<int64_t>(N, kBK) * kBK, Cp = ceil_div<int64_t>(C, kBN) * kBN;
-    const int64_t Ks = K < kCosSlab ? K : kCosSlab, Kp = ceil_div<int64_t>(Ks, kBM) * kBM;
-    return size_t(Kp + Cp) * size_t(Np) * 2 * sizeof(float) + 1024;
+struct CosLayout {
+    int64_t Np, Cp, Kp;
+    int chunks, splits, kb_per_split;
+    int64_t rows_per_chunk;
+    size_t stat_off, p_off, a_off, part_off, total;
+};
+static CosLayout cos_layout(int64_t N, int64_t K, int64_t C) {
+    CosLayout l;
+    l.Np = ceil_div<int64_t>(N, kBK) * kBK;
+    l.Cp = ceil_div<int64_t>(C, kBN) * kBN;
+    const int64_t Ks = K < kCosSlab ? K : kCosSlab;
+    l.Kp = ceil_div<int64_t>(Ks, kBM) * kBM;
+    // row chunks of the statistics passes: enough blocks for the machine with the narrower matrix
+    int64_t ch = ceil_div<int64_t>(4 * int64_t(num_sms()), ceil_div<int64_t>(C < K ? C : K, 32));
+    if (ch > kMaxStatChunks) ch = kMaxStatChunks;
+    if (ch > N / 64) ch = N / 64;
+    if (ch < 1) ch = 1;
+    l.rows_per_chunk = ceil_div<int64_t>(N, ch);
+    l.chunks = static_cast<int>(ceil_div<int64_t>(N, l.rows_per_chunk));
+    // split-K when the output tiles alone leave SMs idle (a split keeps >= 16 k-blocks)
+    const int64_t tiles = (l.Cp / kBN) * (l.Kp / kBM), nkb = l.Np / kBK;
+    int64_t sp = ceil_div<int64_t>(num_sms(), tiles);
+    if (sp > nkb / 16) sp = nkb / 16;
+    if (sp > 32) sp = 32;
+    if (sp < 1) sp = 1;
+    l.kb_per_split = static_cast<int>(ceil_div<int64_t>(nkb, sp));
+    l.splits = static_cast<int>(ceil_div<int64_t>(nkb, l.kb_per_split));
+    auto up = [](size_t x) { return (x + 1023) / 1024 * 1024; };
+    l.stat_off = 1024;                                                   // alignment slack in front
+    l.p_off = l.stat_off + up(size_t(2) * l.chunks * size_t(C + K) * sizeof(float));
+    l.a_off = l.p_off + up(size_t(l.Cp) * l.Np * 2 * sizeof(float));
+    l.part_off = l.a_off + up(size_t(l.Kp) * l.Np * 2 * sizeof(float));
+    l.total = l.part_off + (l.splits > 1 ? up(size_t(l.splits) * l.Kp * l.Cp * sizeof(float)) : 0);
+    return l;
 }
 
-int cos_matmul_tc(const float *A, int64_t lda, const float *meanA, const float *normA, const float *P, int64_t ldp,
-                  const float *meanP, const float *normP, int64_t N, int64_t K, int64_t C, int cubed, float *out,
-                  int64_t ldo, void *ws, size_t ws_bytes, cudaStream_t st) {
-    const int64_t Np = ceil_div<int64_t>(N, kBK) * kBK, Cp = ceil_div<int64_t>(C, kBN) * kBN;
-    const int64_t Ks = K < kCosSlab ? K : kCosSlab, Kp = ceil_div<int64_t>(Ks, kBM) * kBM;
-    if (ws_bytes < cos_matmul_tc_workspace(N, K, C)) return MCD_ERR_WORKSPACE;
-    if (Np > (int64_t(1) << 31) - 64) return MCD_ERR_UNSUPPORTED;      // TMA coordinates are 32-bit
+size_t cos_similarity_tc_workspace(int64_t N, int64_t K, int64_t C) { return cos_layout(N, K, C).total; }
+
+template <int STAT>
+static int launch_col_partial(const float *X, int64_t ldx, int64_t N, int64_t M, const CosLayout &l, const float *sum_part,
+                              float *part, cudaStream_t st) {
+    dim3 grid(static_cast<unsigned>(ceil_div<int64_t>(M, 32)), static_cast<unsigned>(l.chunks));
+    col_partial_kernel<STAT><<<grid, 256, 0, st>>>(X, ldx, N, M, l.rows_per_chunk, sum_part, l.chunks, part);
+    return check_launch();
+}
+
+// out [K, C] = f(A)^T f(P): the whole cos_similarity / cos_similarity_cubed call
+int cos_similarity_tc(const float *P, int64_t ldp, const float *A, int64_t lda, int64_t N, int64_t K, int64_t C, int cubed,
+                      float min_norm, float *out, int64_t ldo, void *ws, size_t ws_bytes, cudaStream_t st) {
+    const CosLayout l = cos_layout(N, K, C);
+    if (ws_bytes < l.total) return MCD_ERR_WORKSPACE;
+    if (l.Np > (int64_t(1) << 31) - 64) return MCD_ERR_UNSUPPORTED;      // TMA coordinates are 32-bit
     if (!encode_fn2()) return MCD_ERR_UNSUPPORTED;
     char *w = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
-    float *Phi = reinterpret_cast<float *>(w);
-    float *Plo = Phi + Cp * Np;
-    float *Ahi = Plo + Cp * Np;
-    float *Alo = Ahi + Kp * Np;
+    float *sumP = reinterpret_cast<float *>(w + l.stat_off - 1024);
+    float *sumA = sumP + size_t(l.chunks) * C;
+    float *sqP = sumA + size_t(l.chunks) * K;
+    float *sqA = sqP + size_t(l.chunks) * C;
+    float *Phi = reinterpret_cast<float *>(w + l.p_off - 1024), *Plo = Phi + l.Cp * l.Np;
+    float *Ahi = reinterpret_cast<float *>(w + l.a_off - 1024), *Alo = Ahi + l.Kp * l.Np;
+    float *part = reinterpret_cast<float *>(w + l.part_off - 1024);
+    int rc;
+    // ---- column statistics of both matrices ----
+    if (cubed) {
+        if ((rc = launch_col_partial<0>(P, ldp, N, C, l, nullptr, sumP, st)) != MCD_OK) return rc;
+        if ((rc = launch_col_partial<0>(A, lda, N, K, l, nullptr, sumA, st)) != MCD_OK) return rc;
+        if ((rc = launch_col_partial<2>(P, ldp, N, C, l, sumP, sqP, st)) != MCD_OK) return rc;
+        if ((rc = launch_col_partial<2>(A, lda, N, K, l, sumA, sqA, st)) != MCD_OK) return rc;
+    } else {
+        if ((rc = launch_col_partial<1>(P, ldp, N, C, l, nullptr, sqP, st)) != MCD_OK) return rc;
+        if ((rc = launch_col_partial<1>(A, lda, N, K, l, nullptr, sqA, st)) != MCD_OK) return rc;
+    }
     if (cudaFuncSetAttribute(gemm_tf32x3_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTcSmemBytes)) != cudaSuccess)
         return MCD_ERR_CUDA;
     CUtensorMap mBhi, mBlo;
-    if (!make_operand_map(&mBhi, Phi, Cp, Np, kBN) || !make_operand_map(&mBlo, Plo, Cp, Np, kBN)) return MCD_ERR_UNSUPPORTED;
-    dim3 pgrid(static_cast<unsigned>(Cp / 32), static_cast<unsigned>(Np / 32));
-    if (cubed) prepare_cols_kernel<kPrepCos3><<<pgrid, 256, 0, st>>>(P, ldp, N, C, meanP, normP, Phi, Plo, Np);
-    else prepare_cols_kernel<kPrepCos><<<pgrid, 256, 0, st>>>(P, ldp, N, C, nullptr, normP, Phi, Plo, Np);
-    int rc = check_launch();
-    if (rc != MCD_OK) return rc;
+    if (!make_operand_map(&mBhi, Phi, l.Cp, l.Np, kBN) || !make_operand_map(&mBlo, Plo, l.Cp, l.Np, kBN)) return MCD_ERR_UNSUPPORTED;
+    dim3 pgrid(static_cast<unsigned>(l.Cp / 32), static_cast<unsigned>(l.Np / 32));
+    if (cubed) prepare_cols_kernel<kPrepCos3><<<pgrid, 256, 0, st>>>(P, ldp, N, C, sumP, sqP, l.chunks, C, min_norm, Phi, Plo, l.Np);
+    else prepare_cols_kernel<kPrepCos><<<pgrid, 256, 0, st>>>(P, ldp, N, C, nullptr, sqP, l.chunks, C, min_norm, Phi, Plo, l.Np);
+    if ((rc = check_launch()) != MCD_OK) return rc;
+    const int total_kb = static_cast<int>(l.Np / kBK);
     for (int64_t k0 = 0; k0 < K; k0 += kCosSlab) {
         const int64_t kn = K - k0 < kCosSlab ? K - k0 : kCosSlab, kp = ceil_div<int64_t>(kn, kBM) * kBM;
         CUtensorMap mAhi, mAlo;
-        if (!make_operand_map(&mAhi, Ahi, kp, Np, kBM) || !make_operand_map(&mAlo, Alo, kp, Np, kBM)) return MCD_ERR_UNSUPPORTED;
-        dim3 agrid(static_cast<unsigned>(kp / 32), static_cast<unsigned>(Np / 32));
-        if (cubed) prepare_cols_kernel<kPrepCos3><<<agrid, 256, 0, st>>>(A + k0, lda, N, kn, meanA + k0, normA + k0, Ahi, Alo, Np);
-        else prepare_cols_kernel<kPrepCos><<<agrid, 256, 0, st>>>(A + k0, lda, N, kn, nullptr, normA + k0, Ahi, Alo, Np);
-        rc = check_launch();
-        if (rc != MCD_OK) return rc;
-        dim3 grid(static_cast<unsigned>(Cp / kBN), static_cast<unsigned>(kp / kBM));
-        gemm_tf32x3_long_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(mAhi, mAlo, mBhi, mBlo, kn, C, static_cast<int>(Np / kBK),
-                                                                        out + k0 * ldo, ldo);
-        rc = check_launch();
-        if (rc != MCD_OK) return rc;
+        if (!make_operand_map(&mAhi, Ahi, kp, l.Np, kBM) || !make_operand_map(&mAlo, Alo, kp, l.Np, kBM)) return MCD_ERR_UNSUPPORTED;
+        dim3 agrid(static_cast<unsigned>(kp / 32), static_cast<unsigned>(l.Np / 32));
+        // (the partial arrays are indexed by the column inside the whole matrix: offset pointer, full width K)
+        if (cubed)
+            prepare_cols_kernel<kPrepCos3><<<agrid, 256, 0, st>>>(A + k0, lda, N, kn, sumA + k0, sqA + k0, l.chunks, K, min_norm, Ahi, Alo, l.Np);
+        else
+            prepare_cols_kernel<kPrepCos><<<agrid, 256, 0, st>>>(A + k0, lda, N, kn, nullptr, sqA + k0, l.chunks, K, min_norm, Ahi, Alo, l.Np);
+        if ((rc = check_launch()) != MCD_OK) return rc;
+        dim3 grid(static_cast<unsigned>(l.Cp / kBN), static_cast<unsigned>(kp / kBM), static_cast<unsigned>(l.splits));
+        if (l.splits == 1) {
+            gemm_tf32x3_long_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(mAhi, mAlo, mBhi, mBlo, kn, C, total_kb, l.kb_per_split,
+                                                                            out + k0 * ldo, ldo, 0);
+            if ((rc = check_launch()) != MCD_OK) return rc;
+        } else {
+            gemm_tf32x3_long_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(mAhi, mAlo, mBhi, mBlo, kn, C, total_kb, l.kb_per_split,
+                                                                            part, l.Cp, l.Kp * l.Cp);
+            if ((rc = check_launch()) != MCD_OK) return rc;
+            dim3 cgrid(static_cast<unsigned>(ceil_div<int64_t>(C, 256)), static_cast<unsigned>(kn));
+            splitk_combine_kernel<<<cgrid, 256, 0, st>>>(part, l.splits, kn, C, l.Cp, l.Kp * l.Cp, out + k0 * ldo, ldo);
+            if ((rc = check_launch()) != MCD_OK) return rc;
+        }
     }
     return MCD_OK;
 }

@@ -481,18 +481,11 @@ def _cos(clip_feats, target_feats, device, cubed, min_norm):
             raise RuntimeError("clip_feats and target_feats must share the probe-image axis")
         N, C = P.shape
         K = A.shape[1]
-        st = _stream(dev)
-        stats = torch.empty((2, C + K), dtype=torch.float32, device=dev)
-        meanP, normP, meanA, normA = stats[0, :C], stats[1, :C], stats[0, C:], stats[1, C:]
-        _lib.check(lib.mcd_col_stats_f32(_ptr(P), _ld(P), N, C, int(cubed), float(min_norm), _ptr(meanP), _ptr(normP),
-                                         st), "mcd_col_stats_f32")
-        _lib.check(lib.mcd_col_stats_f32(_ptr(A), _ld(A), N, K, int(cubed), float(min_norm), _ptr(meanA), _ptr(normA),
-                                         st), "mcd_col_stats_f32")
         out = torch.empty((K, C), dtype=torch.float32, device=dev)
-        ws = _workspace(int(lib.mcd_cos_matmul_workspace_bytes(N, K, C)), dev)
-        _lib.check(lib.mcd_cos_matmul_tc_f32(_ptr(A), _ld(A), _ptr(meanA), _ptr(normA), _ptr(P), _ld(P), _ptr(meanP),
-                                             _ptr(normP), N, K, C, int(cubed), _ptr(out), _ld(out), _ptr(ws), ws.numel(),
-                                             st), "mcd_cos_matmul_tc_f32")
+        ws = _call_workspace(int(lib.mcd_cos_similarity_workspace_bytes(N, K, C)), dev)
+        _lib.check(lib.mcd_cos_similarity_f32(_ptr(P), _ld(P), _ptr(A), _ld(A), N, K, C, int(cubed), float(min_norm),
+                                              _ptr(out), _ld(out), _ptr(ws), ws.numel(), _stream(dev)),
+                   "mcd_cos_similarity_f32")
     return out
 
 

@@ -374,8 +374,9 @@ def test_cos_similarities_on_the_tensor_cores(sim, N, K, C, cubed):
         _lib.set_tunable("gemm_variant", 0)
     scale = ref64.abs().max().item()
     e_tc, e_ffma = (got.double() - ref64).abs().max().item(), (ffma.double() - ref64).abs().max().item()
-    assert e_tc <= 1e-5 * scale, (e_tc, e_ffma, scale)
-    assert e_tc <= max(4 * e_ffma, 2e-6 * scale), (e_tc, e_ffma)          # no worse than true-fp32 arithmetic
+    # the error floor is the fp32 evaluation of the column statistics and of f(x), shared by both kernels: the tensor-core
+    # product must be no worse than true-fp32 arithmetic, and within 1e-5 of the largest similarity where that is wider
+    assert e_tc <= max(1e-5 * scale, 1.5 * e_ffma + 1e-7), (e_tc, e_ffma, scale)
 
 
 def test_cos_similarity_cubed_single_is_the_matched_pair_diagonal(sim):
