@@ -198,12 +198,20 @@ int mcd_cos_similarity_f32(const float *P, int64_t ldp, const float *A, int64_t 
                            void *workspace, size_t workspace_bytes, mcd_stream_t stream);
 int mcd_last_cos_path(void);
 
-/* ---- rank_reorder (similarity.py:99-132).  idx / vals [top_n, K] from mcd_topk_cols_f32 (top_n = int(0.05 N) <= 512),
- *      perms [K, 5, top_n] int32: the reference's torch.randperm stream replayed on the host, baseline_ws [K] scratch.
- *      out[j,c] = -(mean_r |t_r - asc[rank_rc]|^p / baseline_j) / (mean_r P[idx_r, c])^scale_p */
+/* ---- rank_reorder (similarity.py:99-132).  idx / vals [top_n, K] from mcd_topk_cols_f32 (top_n = int(0.05 N) <= 8192).
+ *      out[j,c] = -(mean_r |t_r - asc[rank_rc]|^p / baseline_j) / (mean_r P[idx_r, c])^scale_p, ranks by sorting
+ *      (registers for top_n <= 512, shared memory beyond), ties among the gathered cosines by row position.
+ *      baseline_j: the reference's 5 x torch.randperm(top_n) per neuron from the global CPU generator, either as
+ *        mcd_rank_reorder_f32        perms [K, 5, top_n] int32 drawn on the host, baseline_ws [5 K] floats of scratch;
+ *        mcd_rank_reorder_draws_f32  draws [K, 5, top_n - 1] uint32: the generator's raw 32-bit outputs (torch.randperm
+ *                                    = Fisher-Yates with z = draw % (n - i)); the shuffles run on the device. */
 int mcd_rank_reorder_f32(const float *P, int64_t ldp, int64_t N, int64_t C, const int32_t *idx, const float *vals,
                          int64_t K, int64_t top_n, const int32_t *perms, float p, float scale_p,
                          float *baseline_ws, float *out, int64_t ldo, mcd_stream_t stream);
+size_t mcd_rank_reorder_workspace_bytes(int64_t K, int64_t top_n);
+int mcd_rank_reorder_draws_f32(const float *P, int64_t ldp, int64_t N, int64_t C, const int32_t *idx, const float *vals,
+                               int64_t K, int64_t top_n, const uint32_t *draws, float p, float scale_p,
+                               void *workspace, size_t workspace_bytes, float *out, int64_t ldo, mcd_stream_t stream);
 
 #ifdef __cplusplus
 }

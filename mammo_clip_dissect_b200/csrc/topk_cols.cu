@@ -518,7 +518,7 @@ topk_finish_kernel(const unsigned long long *__restrict__ cand, int M, int Mpad,
                    const int *__restrict__ redo_flags) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t col = col_first + int64_t(blockIdx.x) * kFinishWarps + warp;
+    const int64_t col = col_first + int64_t(blockIdx.x) * (blockDim.x >> 5) + warp;     // 1 - 4 warps per CTA (shared memory)
     if (col >= col_end) return;
     if (redo_flags && redo_flags[col] >= k) return;      // resolved by the select kernel: only flagged columns are redone
     unsigned long long *buf = reinterpret_cast<unsigned long long *>(smem_raw) + size_t(warp) * Mpad;
@@ -818,8 +818,11 @@ namespace mcd {
 // ---- host side ----------------------------------------------------------------------------------
 constexpr size_t kSmemPerSM = 228 * 1024, kSmemCtaReserve = 1024;
 
+constexpr int64_t kScanMaxK = 512;              // kept-set groups of the scan: 8 x 64 entries at most
+constexpr int64_t kSelectMaxK = 16384;          // radix select + shared-memory sort of the k selected words (one warp: 128 KB)
+
 static bool make_plan(int64_t N, int64_t K, int64_t k64, TopkPlan *p) {
-    if (k64 < 1 || k64 > 512) return false;     // kept-set groups: 8 x 64 entries at most
+    if (k64 < 1 || k64 > kScanMaxK) return false;
     const int k = static_cast<int>(k64);
     const int64_t sms = num_sms();
     // ring depth: enough scan warps per SM (the scan is latency-bound per warp) with a few tiles in flight each
@@ -1016,12 +1019,16 @@ static int launch_finish(const TopkPlan &p, const unsigned long long *cand, int 
                                                                               vals_out, col_first, col_end, redo_flags);
         return check_launch();
     }
-    const size_t fsmem = size_t(kFinishWarps) * p.mpad * sizeof(unsigned long long);
+    // a warp sorts its column's mpad words in shared memory: as many warps per CTA as 160 KB hold (large k: one or two)
+    int fw = static_cast<int>((size_t(160) << 10) / (size_t(p.mpad) * sizeof(unsigned long long)));
+    if (fw > kFinishWarps) fw = kFinishWarps;
+    if (fw < 1) return MCD_ERR_UNSUPPORTED;
+    const size_t fsmem = size_t(fw) * p.mpad * sizeof(unsigned long long);
     if (cudaFuncSetAttribute(topk_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(fsmem)) != cudaSuccess)
         return MCD_ERR_CUDA;
-    const unsigned fgrid = static_cast<unsigned>(ceil_div<int64_t>(ncol, kFinishWarps));
-    topk_finish_kernel<<<fgrid, kFinishWarps * 32, fsmem, st>>>(cand, p.splits * k, p.mpad, k, K, A, lda, idx64_out, idx32_out,
-                                                                vals_out, col_first, col_end, redo_flags);
+    const unsigned fgrid = static_cast<unsigned>(ceil_div<int64_t>(ncol, fw));
+    topk_finish_kernel<<<fgrid, fw * 32, fsmem, st>>>(cand, p.splits * k, p.mpad, k, K, A, lda, idx64_out, idx32_out,
+                                                      vals_out, col_first, col_end, redo_flags);
     return check_launch();
 }
 
@@ -1146,7 +1153,9 @@ int topk_filter_finish(const TopkFilterCall &c, int64_t col0, int64_t col1, int6
 
 extern "C" size_t mcd_topk_cols_workspace_bytes(int64_t N, int64_t K, int64_t k) {
     mcd::TopkPlan p;
-    if (N < 1 || K < 1 || k < 1 || k > N || !mcd::make_plan(N, K, k, &p)) return 0;
+    if (N < 1 || K < 1 || k < 1 || k > N) return 0;
+    if (k > mcd::kScanMaxK) return k <= mcd::kSelectMaxK ? (size_t(k) * size_t(K) * 8 + 255) / 256 * 256 : 0;   // radix select: candidates only
+    if (!mcd::make_plan(N, K, k, &p)) return 0;
     return plan_total_bytes(p);
 }
 
@@ -1156,15 +1165,22 @@ extern "C" int mcd_topk_cols_f32(const float *A, int64_t lda, int64_t N, int64_t
     using namespace mcd;
     if (!A || N < 1 || K < 1 || k < 1 || k > N || lda < K || N >= 0x7FFFFFFFll) return MCD_ERR_INVALID_ARGUMENT;
     TopkPlan p;
-    if (!make_plan(N, K, k, &p)) return MCD_ERR_UNSUPPORTED;
-    if (!workspace || workspace_bytes < plan_total_bytes(p)) return MCD_ERR_WORKSPACE;
+    const bool large_k = k > kScanMaxK;         // beyond the kept sets of the scan (rank_reorder: k = 5 % of N): radix select
+    if (large_k) {
+        if (k > kSelectMaxK) return MCD_ERR_UNSUPPORTED;
+        memset(&p, 0, sizeof(p));
+        if (!workspace || workspace_bytes < size_t(k) * size_t(K) * 8) return MCD_ERR_WORKSPACE;
+    } else {
+        if (!make_plan(N, K, k, &p)) return MCD_ERR_UNSUPPORTED;
+        if (!workspace || workspace_bytes < plan_total_bytes(p)) return MCD_ERR_WORKSPACE;
+    }
     if (reinterpret_cast<uintptr_t>(workspace) % 8 != 0) return MCD_ERR_INVALID_ARGUMENT;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     auto *cand = static_cast<unsigned long long *>(workspace);
     auto *kept = reinterpret_cast<uint32_t *>(static_cast<char *>(workspace) + p.cand_bytes);
 
     // short columns of an L2-resident matrix: exact radix select (tunable topk_small: 1 = never, else automatic)
-    if (takes_small_path(N, K)) {
+    if (large_k || takes_small_path(N, K)) {
         // rows of a column group split over a cluster of R CTAs when the column groups alone would leave SMs idle
         const int64_t ncb_s = ceil_div<int64_t>(K, kUnitCols);
         int R = 1;

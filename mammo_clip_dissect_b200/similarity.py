@@ -161,7 +161,7 @@ def topk_cols(target_feats, k, device="cuda", want_values=False, want_int32=Fals
     vals = torch.empty((k, K), dtype=torch.float32, device=dev) if want_values else None
     need = lib.mcd_topk_cols_workspace_bytes(N, K, k)
     if need == 0:
-        raise RuntimeError("top_k=%d is outside the supported range of the column top-k kernel (<= 512)" % k)
+        raise RuntimeError("top_k=%d is outside the supported range of the column top-k kernel (<= 16384)" % k)
     ws = _workspace(need, dev)
     with torch.cuda.device(dev):
         _lib.check(lib.mcd_topk_cols_f32(_ptr(A), _ld(A), N, K, k, _ptr(idx64), _ptr(idx32), _ptr(vals), _ptr(ws),
@@ -179,7 +179,7 @@ def _topk_int32(A, k, dev):
     idx32 = torch.empty((k, K), dtype=torch.int32, device=dev)
     need = lib.mcd_topk_cols_workspace_bytes(N, K, k)
     if need == 0:
-        raise RuntimeError("top_k=%d is outside the supported range of the column top-k kernel (<= 512)" % k)
+        raise RuntimeError("top_k=%d is outside the supported range of the column top-k kernel (<= 16384)" % k)
     with torch.cuda.device(dev):
         ws = _workspace(need, dev)
         _lib.check(lib.mcd_topk_cols_f32(_ptr(A), _ld(A), N, K, k, None, _ptr(idx32), None, _ptr(ws), ws.numel(),
@@ -287,7 +287,7 @@ def pmi_logsums(clip_feats, target_feats, top_k, a, device, min_prob, ramp):
         lib = _lib.lib()
         need = int(lib.mcd_pmi_scores_workspace_bytes(N, K, C, top_k))
         if need == 0:
-            raise RuntimeError("top_k=%d is outside the supported range of the column top-k kernel (<= 512)" % top_k)
+            raise RuntimeError("top_k=%d is outside the supported range of the column top-k kernel (<= 16384)" % top_k)
         ws = _call_workspace(need, dev)
         weights = ramp.to(dev) if ramp is not None else None
         L = torch.empty((K, C), dtype=torch.float32, device=dev)
@@ -320,7 +320,7 @@ def pmi_scores(clip_feats, target_feats, top_k, a, lam, device, min_prob, ramp, 
             lib = _lib.lib()
             need = int(lib.mcd_pmi_scores_workspace_bytes(N, K, C, top_k))
             if need == 0:
-                raise RuntimeError("top_k=%d is outside the supported range of the column top-k kernel (<= 512)" % top_k)
+                raise RuntimeError("top_k=%d is outside the supported range of the column top-k kernel (<= 16384)" % top_k)
             ws = _call_workspace(need, dev)
             weights = ramp.to(dev) if ramp is not None else None
             out = torch.empty((K, C), dtype=torch.float32, device=dev)
@@ -512,11 +512,88 @@ def cos_similarity_cubed_single(clip_feats, target_feats, device='cuda', min_nor
     return torch.diagonal(_cos(clip_feats, target_feats, device, True, min_norm)).clone()
 
 
+# ---- the reference's RNG stream for rank_reorder -------------------------------------------------------------------
+# The reference draws 5 x torch.randperm(top_n) per neuron from the GLOBAL CPU generator (similarity.py:119).  On the CPU
+# torch.randperm(n) is a Fisher-Yates shuffle that consumes one raw 32-bit Mersenne-Twister output per step
+# (z = draw % (n - i); swap i, i + z; n - 1 steps), so instead of 5 K Python-level randperm calls the generator's raw
+# outputs are produced in one vectorised numpy call (same MT19937 state), the generator is advanced by exactly that many
+# draws, and the shuffles run on the device (mcd_rank_reorder_draws_f32).  The replay is verified against torch.randperm
+# itself the first time it is used; if the installed torch ever draws differently, the per-call loop is used instead.
+_MT_N = 624
+_replay_ok = None
+
+
+def _mt_state_to_numpy(state):
+    """torch CPU generator state (legacy layout: seed u64, left i32, seeded i32, next u64, state u64[624], ...) ->
+    (numpy MT19937 key, pos)."""
+    import numpy as np
+    raw = state.numpy().tobytes()
+    left = int(np.frombuffer(raw, dtype=np.int32, count=1, offset=8)[0])
+    nxt = int(np.frombuffer(raw, dtype=np.uint64, count=1, offset=16)[0])
+    key = np.frombuffer(raw, dtype=np.uint64, count=_MT_N, offset=24).astype(np.uint32)
+    # ATen twists when --left hits 0; after the twist left + next == 625
+    pos = _MT_N if left == 1 else nxt
+    if not (0 <= pos <= _MT_N) or (left != 1 and left + nxt != _MT_N + 1):
+        raise RuntimeError("unexpected CPU generator state layout")
+    return key, pos
+
+
+def _mt_state_from_numpy(state, key, pos):
+    import numpy as np
+    buf = bytearray(state.numpy().tobytes())
+    np.frombuffer(buf, dtype=np.int32, count=1, offset=8)[0] = _MT_N + 1 - pos
+    np.frombuffer(buf, dtype=np.uint64, count=1, offset=16)[0] = pos
+    np.frombuffer(buf, dtype=np.uint64, count=_MT_N, offset=24)[:] = key.astype(np.uint64)
+    return torch.frombuffer(buf, dtype=torch.uint8).clone()
+
+
+def _raw_draws(count, generator=None):
+    """The next `count` raw 32-bit outputs of the (global) CPU generator as a uint32 numpy array; advances the generator."""
+    import numpy as np
+    gen = torch.default_generator if generator is None else generator
+    state = gen.get_state()
+    key, pos = _mt_state_to_numpy(state)
+    mt = np.random.MT19937()
+    st = mt.state
+    st["state"]["key"] = key
+    st["state"]["pos"] = pos
+    mt.state = st
+    draws = mt.random_raw(int(count)).astype(np.uint32)
+    gen.set_state(_mt_state_from_numpy(state, mt.state["state"]["key"], int(mt.state["state"]["pos"])))
+    return draws
+
+
+def _replay_works():
+    """One-time self-check on a scratch generator: raw draws + Fisher-Yates == torch.randperm, and the generator ends in
+    the same state."""
+    global _replay_ok
+    if _replay_ok is None:
+        try:
+            ok = True
+            for seed, n, reps in ((7, 10, 3), (123, 257, 2), (5, 1000, 1)):
+                g1, g2 = torch.Generator().manual_seed(seed), torch.Generator().manual_seed(seed)
+                torch.randn(5, generator=g1), torch.randn(5, generator=g2)          # not at a fresh-seed state
+                want = [torch.randperm(n, generator=g1) for _ in range(reps)]
+                d = _raw_draws(reps * (n - 1), g2).reshape(reps, n - 1)
+                for r in range(reps):
+                    perm = list(range(n))
+                    for i in range(n - 1):
+                        z = i + int(d[r, i]) % (n - i)
+                        perm[i], perm[z] = perm[z], perm[i]
+                    ok = ok and perm == want[r].tolist()
+                ok = ok and torch.equal(torch.randperm(9, generator=g1), torch.randperm(9, generator=g2))
+            _replay_ok = bool(ok)
+        except Exception:
+            _replay_ok = False
+    return _replay_ok
+
+
 def rank_reorder(clip_feats, target_feats, device="cuda", p=3, top_fraction=0.05, scale_p=0.5, top_k=None):
-    """Reference similarity.py:99-132 on the GPU.  The reference draws 5 x torch.randperm(top_n) per neuron from
-    the GLOBAL CPU generator (in neuron order); the same stream is drawn here on the host and shipped to the
-    kernel, so under the same torch.manual_seed the two implementations see identical permutations.
-    Limits: top_n = int(N * top_fraction) <= 512 (N <= 10240 at the default 5 %) and K <= 65535."""
+    """Reference similarity.py:99-132 on the GPU.  The reference draws 5 x torch.randperm(top_n) per neuron from the
+    GLOBAL CPU generator (in neuron order); the same stream is consumed here (see _raw_draws above), so under the same
+    torch.manual_seed the two implementations see identical permutations and leave the generator in the same state.
+    Limits: top_n = int(N * top_fraction) <= 8192 (N <= 163 840 at the default 5 %) and K <= 65535 per call."""
+    import numpy as np
     dev = _cuda_device(device)
     lib = _lib.lib()
     with torch.no_grad(), torch.cuda.device(dev):
@@ -529,15 +606,22 @@ def rank_reorder(clip_feats, target_feats, device="cuda", p=3, top_fraction=0.05
         top_n = int(N * top_fraction)
         if top_n < 1:
             raise RuntimeError("rank_reorder: top_fraction selects no probe image")
-        if top_n > 512 or K > 65535:
-            raise NotImplementedError("rank_reorder on the B200 path supports top_n <= 512 and K <= 65535 "
+        if top_n > 8192 or K > 65535:
+            raise NotImplementedError("rank_reorder on the B200 path supports top_n <= 8192 and K <= 65535 "
                                       "(got top_n=%d, K=%d)" % (top_n, K))
         (vals, _), idx32 = topk_cols(A, top_n, dev, want_values=True, want_int32=True)
-        # the reference's RNG stream: for every neuron, five permutations of range(top_n)
+        out = torch.empty((K, C), dtype=torch.float32, device=dev)
+        if top_n > 1 and _replay_works():
+            draws = torch.from_numpy(_raw_draws(K * 5 * (top_n - 1)).view(np.int32)).to(dev)
+            ws = _workspace(int(lib.mcd_rank_reorder_workspace_bytes(K, top_n)), dev)
+            _lib.check(lib.mcd_rank_reorder_draws_f32(_ptr(P), _ld(P), N, C, _ptr(idx32), _ptr(vals), K, top_n, _ptr(draws),
+                                                      float(p), float(scale_p), _ptr(ws), ws.numel(), _ptr(out), _ld(out),
+                                                      _stream(dev)), "mcd_rank_reorder_draws_f32")
+            return out
+        # the reference's RNG stream call by call: for every neuron, five permutations of range(top_n)
         perms = torch.stack([torch.stack([torch.randperm(top_n) for _ in range(5)]) for _ in range(K)]).to(torch.int32)
         perms = perms.to(dev)
-        base = torch.empty((K,), dtype=torch.float32, device=dev)
-        out = torch.empty((K, C), dtype=torch.float32, device=dev)
+        base = torch.empty((K * 5,), dtype=torch.float32, device=dev)
         _lib.check(lib.mcd_rank_reorder_f32(_ptr(P), _ld(P), N, C, _ptr(idx32), _ptr(vals), K, top_n, _ptr(perms), float(p),
                                             float(scale_p), _ptr(base), _ptr(out), _ld(out), _stream(dev)),
                    "mcd_rank_reorder_f32")

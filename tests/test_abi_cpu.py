@@ -47,7 +47,8 @@ def test_workspace_queries_are_pure_host_functions(lib):
     ws = lib.mcd_topk_cols_workspace_bytes(100_000, 32_768, 100)
     assert ws >= 100 * 32_768 * 8
     assert lib.mcd_topk_cols_workspace_bytes(50, 8, 100) == 0          # k > N
-    assert lib.mcd_topk_cols_workspace_bytes(10_000, 8, 1000) == 0     # beyond the streaming kernel (k <= 512)
+    assert lib.mcd_topk_cols_workspace_bytes(10_000, 8, 1000) == 1000 * 8 * 8      # k > 512: radix select, candidates only
+    assert lib.mcd_topk_cols_workspace_bytes(100_000, 8, 20_000) == 0      # beyond the radix select (k <= 16384)
     assert lib.mcd_pool_nchw_workspace_bytes(4, 24, 760, 456) > 0      # large planes are split
     assert lib.mcd_pool_nchw_workspace_bytes(64, 512, 12, 9) == 0      # small planes, many of them: no partials in either memory order
     assert lib.mcd_gemm_nt_softmax_workspace_bytes(2000, 763, 512) >= (2000 + 763) * 4

@@ -930,15 +930,77 @@ def test_rank_reorder_golden(sim, golden):
 
 
 @pytest.mark.parametrize("N,C,K,kw", [(2000, 763, 40, {}), (5000, 100, 24, {}), (1000, 37, 9, dict(p=2, top_fraction=0.1, scale_p=1.0)),
-                                       (3000, 64, 16, dict(p=2.5, scale_p=0.25))])
-def test_rank_reorder_vs_oracle(sim, N, C, K, kw):
+                                       (3000, 64, 16, dict(p=2.5, scale_p=0.25)),
+                                       (9000, 50, 12, {}),                          # top_n = 450: ranks in registers, 16 words per lane
+                                       (12000, 41, 9, {}),                          # top_n = 600: shared-memory sort; K2 by radix select
+                                       (100000, 33, 5, {}),                         # the c4 probe count: top_n = 5000
+                                       (40, 7, 3, {})])                             # top_n = 2
+@pytest.mark.parametrize("replay", ["raw_draws", "randperm_calls"])
+def test_rank_reorder_vs_oracle(sim, N, C, K, kw, replay):
+    """The reference's RNG stream is consumed either as raw generator outputs (shuffles on the device) or call by call;
+    both match the oracle under the same seed and leave the global generator in the oracle's state."""
+    if replay == "randperm_calls" and N > 12000:
+        pytest.skip("the call-by-call replay is the fallback; covered at the smaller sizes")
     P = torch.randn(N, C, generator=gen(N)) * 0.05 + 0.04          # mixed-sign means: some concepts give NaN
+    P[::3] = P[1::3][: P[::3].shape[0]]                            # duplicated rows: equal cosines -> ties in the ranks
     A = torch.randn(N, K, generator=gen(K))
-    torch.manual_seed(123)
-    got = sim.rank_reorder(P, A, device=DEV, **kw).cpu()
+    saved = sim._replay_ok
+    try:
+        if replay == "randperm_calls":
+            sim._replay_ok = False
+        else:
+            assert sim._replay_works()
+        torch.manual_seed(123)
+        got = sim.rank_reorder(P, A, device=DEV, **kw).cpu()
+        tail = torch.rand(4)
+    finally:
+        sim._replay_ok = saved
     torch.manual_seed(123)
     ref = orc.rank_reorder(P, A, **kw)
+    assert torch.equal(tail, torch.rand(4))                        # same generator state afterwards
     assert got.shape == ref.shape == (K, C)
     assert _same_with_nan(got, ref, 5e-5)
+
+
+@pytest.mark.parametrize("K", [24, 176, 512])
+@pytest.mark.parametrize("top_k", [10, 28, 50, 100, 200])
+def test_c5_sweep_against_the_oracle(sim, K, top_k):
+    """BASELINE configs[4]: the similarity functions x top_k 10 - 200 on EfficientNet-B5-shaped layers (N = 5000 probes,
+    24 / 176 / 512 channels), each against the oracle: wpmi and soft_wpmi at every top_k (the cos functions and
+    rank_reorder take no top_k and are swept over the layer widths)."""
+    N, C = 5000, 763
+    P = torch.randn(N, C, generator=gen(500 + K)) * 0.044
+    A = torch.randn(N, K, generator=gen(600 + K))
+    for name, ours, ref in (("wpmi", sim.wpmi, orc.wpmi_fast), ("soft_wpmi", sim.soft_wpmi, orc.soft_wpmi_fast)):
+        out = ours(P, A, top_k=top_k, device=DEV).cpu()
+        want, L, _ = ref(P, A, top_k=top_k, return_parts=True)
+        err = (out - want).abs().max().item()
+        assert err <= 1e-5 * L.abs().max().item(), (name, K, top_k, err)
+        gap = want.topk(2, dim=1).values
+        sure = (gap[:, 0] - gap[:, 1]) > 2e-5 * L.abs().max().item()
+        assert bool((out.argmax(1) == want.argmax(1))[sure].all()), (name, K, top_k)
+    if top_k == 10:
+        for name, ours, ref in (("cos_similarity_cubed", sim.cos_similarity_cubed, orc.cos_similarity_cubed),
+                                ("cos_similarity", sim.cos_similarity, orc.cos_similarity)):
+            out = ours(P, A, device=DEV, top_k=top_k).cpu()            # top_k is accepted and ignored (utils.py:602 passes it)
+            want = ref(P.double(), A.double())
+            assert (out.double() - want).abs().max().item() <= 1e-5 * want.abs().max().item() + 2e-7, (name, K)
+        Pp = P.abs() + 0.01                                             # positive cosines: no NaN rows
+        torch.manual_seed(9)
+        out = sim.rank_reorder(Pp, A, device=DEV, top_k=top_k).cpu()
+        torch.manual_seed(9)
+        assert _same_with_nan(out, orc.rank_reorder(Pp, A), 5e-5), ("rank_reorder", K)
+
+
+def test_rank_reorder_limits(sim):
     with pytest.raises(NotImplementedError):
-        sim.rank_reorder(torch.randn(20000, 8), torch.randn(20000, 4), device=DEV)      # top_n = 1000 > 512
+        sim.rank_reorder(torch.randn(170000, 8), torch.randn(170000, 2), device=DEV)    # top_n = 8500 > 8192
+
+
+@pytest.mark.parametrize("N,K,k", [(12000, 20, 600), (100000, 8, 5000), (3000, 33, 1500), (20000, 5, 513)])
+def test_topk_large_k_by_radix_select(sim, N, K, k):
+    """k beyond the scan's kept sets (rank_reorder takes 5 % of the probe images): radix select over the column."""
+    A = torch.randn(N, K, generator=gen(N + k)).round(decimals=2)           # plenty of ties
+    vals, idx = sim.topk_cols(A, k, device=DEV, want_values=True)
+    rv, ri = orc.topk_cols(A, k)
+    assert torch.equal(idx.cpu(), ri) and torch.equal(vals.cpu(), rv)

@@ -59,3 +59,12 @@ for name, fn in (("wpmi(top_k=28)", lambda: sim.wpmi(P, A, device=dev)),
                  ("rank_reorder", lambda: sim.rank_reorder(P, A, device=dev))):
     t = med(fn, iters=10)
     print("| c5: N=5000, K=512 | %s | %.3f | %.2f M |" % (name, t, 512 / t / 1e3))
+import time
+torch.cuda.synchronize(); t0 = time.perf_counter()
+for _ in range(5):
+    sim.rank_reorder(P, A, device=dev)
+torch.cuda.synchronize()
+print("| c5: N=5000, K=512 | rank_reorder, wall clock incl. the host's RNG replay | %.3f | |" % ((time.perf_counter() - t0) / 5 * 1e3))
+P, A = inputs(100000, 64)
+t = med(lambda: sim.rank_reorder(P, A, device=dev), iters=3)
+print("| N=100000, K=64 (top_n = 5000) | rank_reorder | %.3f | %.4f M |" % (t, 64 / t / 1e3))
