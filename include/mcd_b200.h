@@ -153,6 +153,21 @@ int mcd_pmi_finalize_bcast_f32(const float *L, int64_t K, int64_t C, const float
                                float *prob_d_out, float *const *dest_bases, int n_dest,
                                int64_t row_offset, mcd_stream_t stream);
 
+/* ---- K3b's finalize fused with the per-neuron top concepts: out = L - lam log p(d) as above, and in the same pass
+ *      (a warp per neuron row, the finalized values still in registers) the t <= 64 best (value, concept) pairs of
+ *      every row, sorted descending (value desc, concept index asc, NaN largest) -- what the callers compute next with
+ *      torch.topk(sim, 10, dim=1) / torch.max(sim, 1) (describe_broad_neurons.py:101, describe_clip_neurons.py:64).
+ *      C <= 1024.  The _seg_ form serves several layers in one matrix: row_seg [K] names the layer of every row. */
+int mcd_pmi_finalize_topk_f32(const float *L, int64_t ldl, int64_t K, int64_t C, const float *partials_all,
+                              int64_t n_blocks_total, int64_t K_total, float lam, float *prob_d_out,
+                              float *out, int64_t ldo, int64_t t, float *top_vals_out, int64_t *top_idx_out,
+                              mcd_stream_t stream);
+int mcd_pmi_finalize_seg_topk_f32(const float *L, int64_t ldl, int64_t K, int64_t C, const float *partials,
+                                  const int32_t *row_seg, int64_t n_blocks, const int32_t *seg_tab,
+                                  const double *seg_log_count, int64_t n_seg, float lam, float *prob_d_out,
+                                  float *out, int64_t ldo, int64_t t, float *top_vals_out, int64_t *top_idx_out,
+                                  mcd_stream_t stream);
+
 /* ---- per-neuron top concepts: the t largest entries of every row of the score matrix, sorted
  *      descending (value desc, concept index asc, NaN largest)   replaces torch.topk(sim, 10, dim=1)
  *      / torch.max(sim, 1) in the callers (describe_broad_neurons.py:101, describe_clip_neurons.py:64).

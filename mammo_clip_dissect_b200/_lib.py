@@ -43,6 +43,8 @@ SIGNATURES = {
     "mcd_pmi_logsums_f32": (_i32, [_p, _i64, _p, _i64, _i64, _i64, _i64, _i64, _f32, _p, _f32, _p, _i64, _p, _p, _sz, _p]),
     "mcd_col_lse_partials_seg_f32": (_i32, [_p, _i64, _i64, _p, _i64, _p, _p]),
     "mcd_pmi_finalize_seg_f32": (_i32, [_p, _i64, _i64, _p, _p, _i64, _p, _p, _i64, _f32, _p, _p, _i64, _p]),
+    "mcd_pmi_finalize_topk_f32": (_i32, [_p, _i64, _i64, _i64, _p, _i64, _i64, _f32, _p, _p, _i64, _i64, _p, _p, _p]),
+    "mcd_pmi_finalize_seg_topk_f32": (_i32, [_p, _i64, _i64, _i64, _p, _p, _i64, _p, _p, _i64, _f32, _p, _p, _i64, _i64, _p, _p, _p]),
     "mcd_row_topk_f32": (_i32, [_p, _i64, _i64, _i64, _i64, _p, _p, _p]),
     "mcd_pool_nchw_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64]),
     "mcd_pool_nchw": (_i32, [_p, _i32, _i64, _i64, _i64, _i64, _i32, _p, _p, _sz, _p]),

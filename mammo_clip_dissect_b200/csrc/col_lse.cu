@@ -157,6 +157,72 @@ pmi_finalize_bcast_kernel(const float *__restrict__ L, int64_t total, int C, con
     }
 }
 
+// K3b's finalize fused with the callers' per-neuron top concepts (describe_broad_neurons.py:101: torch.topk(sim, 10, 1);
+// describe_clip_neurons.py:64: torch.max(sim, 1)): one warp per neuron row computes out = L - lam * log p(d) (the same
+// two roundings as pmi_finalize_kernel), stores the row, and -- the values still in registers -- emits the row's t
+// best (value, concept) pairs under the stated order (value desc, concept asc, NaN largest), so the [K, C] matrix is not
+// read a second time.  row_seg (optional): the layer of every row when several layers share the matrix.
+constexpr int kFinTopWarps = 8;
+
+template <int PER>     // rows up to 32 * PER concepts
+__global__ void __launch_bounds__(kFinTopWarps * 32)
+pmi_finalize_topk_kernel(const float *__restrict__ L, int64_t ldl, int64_t K, int C, const float *__restrict__ prob_d,
+                         const int32_t *__restrict__ row_seg, float lam, float *__restrict__ out, int64_t ldo, int t,
+                         float *__restrict__ top_vals, int64_t *__restrict__ top_idx) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = int64_t(blockIdx.x) * kFinTopWarps + (threadIdx.x >> 5);
+    if (row >= K) return;
+    const float *src = L + row * ldl;
+    const float *pd = prob_d + (row_seg ? int64_t(row_seg[row]) * C : 0);
+    float *dst = out + row * ldo;
+    unsigned long long w[PER];          // (ordered key, ~concept); 0 = no entry
+    float v[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int c = lane + 32 * i;
+        w[i] = 0ull;
+        v[i] = 0.f;
+        if (c < C) {
+            v[i] = __fsub_rn(src[c], __fmul_rn(lam, pd[c]));
+            dst[c] = v[i];
+            w[i] = pack_key(ordered_key(v[i]), ~static_cast<uint32_t>(c));
+        }
+    }
+    for (int r = 0; r < t; ++r) {
+        unsigned long long best = w[0];
+#pragma unroll
+        for (int i = 1; i < PER; ++i) best = w[i] > best ? w[i] : best;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+            best = other > best ? other : best;
+        }
+        // the winner's lane writes it (its value is in a register) and retires the entry: entries are distinct
+#pragma unroll
+        for (int i = 0; i < PER; ++i)
+            if (w[i] == best) {
+                top_idx[row * t + r] = static_cast<int64_t>(~static_cast<uint32_t>(best));
+                top_vals[row * t + r] = v[i];
+                w[i] = 0ull;
+            }
+    }
+}
+
+static int launch_finalize_topk(const float *L, int64_t ldl, int64_t K, int64_t C, const float *prob_d, const int32_t *row_seg,
+                                float lam, float *out, int64_t ldo, int64_t t, float *top_vals, int64_t *top_idx,
+                                cudaStream_t st) {
+    if (C > 32 * 32 || t > 64 || t > C || t < 1) return MCD_ERR_UNSUPPORTED;
+    const unsigned grid = static_cast<unsigned>(ceil_div<int64_t>(K, kFinTopWarps));
+    const int Ci = static_cast<int>(C), ti = static_cast<int>(t);
+    if (C <= 32 * 8)
+        pmi_finalize_topk_kernel<8><<<grid, kFinTopWarps * 32, 0, st>>>(L, ldl, K, Ci, prob_d, row_seg, lam, out, ldo, ti, top_vals, top_idx);
+    else if (C <= 32 * 24)
+        pmi_finalize_topk_kernel<24><<<grid, kFinTopWarps * 32, 0, st>>>(L, ldl, K, Ci, prob_d, row_seg, lam, out, ldo, ti, top_vals, top_idx);
+    else
+        pmi_finalize_topk_kernel<32><<<grid, kFinTopWarps * 32, 0, st>>>(L, ldl, K, Ci, prob_d, row_seg, lam, out, ldo, ti, top_vals, top_idx);
+    return check_launch();
+}
+
 }  // namespace mcd
 
 extern "C" int mcd_col_lse_partials_f32(const float *L, int64_t ldl, int64_t K, int64_t C, float *partials,
@@ -189,6 +255,22 @@ extern "C" int mcd_pmi_finalize_f32(const float *L, int64_t ldl, int64_t K, int6
     dim3 grid(static_cast<unsigned>(ceil_div<int64_t>(C, 256)), static_cast<unsigned>(rows));
     pmi_finalize_kernel<<<grid, 256, 0, st>>>(L, ldl, K, int(C), prob_d_out, lam, out, ldo);
     return check_launch();
+}
+
+extern "C" int mcd_pmi_finalize_topk_f32(const float *L, int64_t ldl, int64_t K, int64_t C, const float *partials_all,
+                                         int64_t n_blocks_total, int64_t K_total, float lam, float *prob_d_out, float *out,
+                                         int64_t ldo, int64_t t, float *top_vals_out, int64_t *top_idx_out,
+                                         mcd_stream_t stream) {
+    using namespace mcd;
+    if (!L || !partials_all || !prob_d_out || !out || !top_vals_out || !top_idx_out || K < 1 || C < 1 || ldl < C || ldo < C ||
+        n_blocks_total < 1 || K_total < 1)
+        return MCD_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    lse_combine_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(C, 32)), 256, 0, st>>>(
+        partials_all, n_blocks_total, int(C), log(double(K_total)), prob_d_out, nullptr, nullptr);
+    int rc = check_launch();
+    if (rc != MCD_OK) return rc;
+    return launch_finalize_topk(L, ldl, K, C, prob_d_out, nullptr, lam, out, ldo, t, top_vals_out, top_idx_out, st);
 }
 
 extern "C" int mcd_pmi_finalize_bcast_f32(const float *L, int64_t K, int64_t C, const float *partials_all,
@@ -250,4 +332,22 @@ extern "C" int mcd_pmi_finalize_seg_f32(const float *L, int64_t ldl, int64_t C, 
     dim3 fgrid(static_cast<unsigned>(ceil_div<int64_t>(C, 256)), static_cast<unsigned>(n_blocks));
     pmi_finalize_seg_kernel<<<fgrid, 256, 0, st>>>(L, ldl, int(C), prob_d_out, block_tab, lam, out, ldo);
     return check_launch();
+}
+
+extern "C" int mcd_pmi_finalize_seg_topk_f32(const float *L, int64_t ldl, int64_t K, int64_t C, const float *partials,
+                                             const int32_t *row_seg, int64_t n_blocks, const int32_t *seg_tab,
+                                             const double *seg_log_count, int64_t n_seg, float lam, float *prob_d_out,
+                                             float *out, int64_t ldo, int64_t t, float *top_vals_out,
+                                             int64_t *top_idx_out, mcd_stream_t stream) {
+    using namespace mcd;
+    if (!L || !partials || !row_seg || !seg_tab || !seg_log_count || !prob_d_out || !out || !top_vals_out || !top_idx_out ||
+        K < 1 || C < 1 || ldl < C || ldo < C || n_blocks < 1 || n_seg < 1)
+        return MCD_ERR_INVALID_ARGUMENT;
+    if (n_seg > 65535) return MCD_ERR_UNSUPPORTED;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    dim3 cgrid(static_cast<unsigned>(ceil_div<int64_t>(C, 32)), static_cast<unsigned>(n_seg));
+    lse_combine_kernel<<<cgrid, 256, 0, st>>>(partials, 0, int(C), 0.0, prob_d_out, seg_tab, seg_log_count);
+    int rc = check_launch();
+    if (rc != MCD_OK) return rc;
+    return launch_finalize_topk(L, ldl, K, C, prob_d_out, row_seg, lam, out, ldo, t, top_vals_out, top_idx_out, st);
 }

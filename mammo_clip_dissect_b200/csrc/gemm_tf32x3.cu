@@ -722,7 +722,7 @@ static CosLayout cos_layout(int64_t N, int64_t K, int64_t C) {
     l.chunks = static_cast<int>(ceil_div<int64_t>(N, l.rows_per_chunk));
     // split-K when the output tiles alone leave SMs idle (a split keeps >= 16 k-blocks)
     const int64_t tiles = (l.Cp / kBN) * (l.Kp / kBM), nkb = l.Np / kBK;
-    int64_t sp = ceil_div<int64_t>(num_sms(), tiles);
+    int64_t sp = int64_t(num_sms()) / tiles;              // one wave: tiles x splits <= SMs
     if (sp > nkb / 16) sp = nkb / 16;
     if (sp > 32) sp = 32;
     if (sp < 1) sp = 1;

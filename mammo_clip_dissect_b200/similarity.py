@@ -32,8 +32,8 @@ import torch
 from . import _lib
 
 __all__ = ["soft_wpmi", "wpmi", "cos_similarity", "cos_similarity_cubed", "cos_similarity_cubed_single", "rank_reorder",
-           "soft_wpmi_layers", "wpmi_layers", "top_concepts", "topk_cols", "concept_probabilities", "pmi_scores",
-           "pmi_logsums"]
+           "soft_wpmi_layers", "wpmi_layers", "soft_wpmi_top", "wpmi_top", "top_concepts", "topk_cols",
+           "concept_probabilities", "pmi_scores", "pmi_logsums"]
 
 _S_ALIGN = 32  # leading dimension of the probability matrix: rows start on 128-byte boundaries
 
@@ -249,6 +249,26 @@ def pmi_finalize(L, partials_all, K_total, lam, out=None):
     return out, prob_d
 
 
+def pmi_finalize_top(L, partials_all, K_total, lam, t, out=None):
+    """K3b part 2 fused with the per-neuron top concepts: (out, log p(d) [C], top values [K, t], top concept indices
+    [K, t] int64), out = L - lam * log p(d) in place by default; one pass over the matrix (mcd_pmi_finalize_topk_f32)."""
+    K, C = L.shape
+    if out is None:
+        out = L
+    t = int(t)
+    if t < 1 or t > min(C, 64) or C > 1024:
+        raise RuntimeError("top concepts: 1 <= t <= min(C, 64) and C <= 1024 (got t=%d, C=%d)" % (t, C))
+    with torch.cuda.device(L.device):
+        prob_d = torch.empty((C,), dtype=torch.float32, device=L.device)
+        vals = torch.empty((K, t), dtype=torch.float32, device=L.device)
+        idx = torch.empty((K, t), dtype=torch.int64, device=L.device)
+        _lib.check(_lib.lib().mcd_pmi_finalize_topk_f32(_ptr(L), _ld(L), K, C, _ptr(partials_all), partials_all.shape[0],
+                                                        int(K_total), float(lam), _ptr(prob_d), _ptr(out), _ld(out), t,
+                                                        _ptr(vals), _ptr(idx), _stream(L.device)),
+                   "mcd_pmi_finalize_topk_f32")
+    return out, prob_d, vals, idx
+
+
 def pmi_finalize_bcast(L, partials_all, K_total, lam, dest_ptrs, row_offset):
     """K3b fused with the score all-gather: finalize this rank's contiguous [K, C] log-sums and store the slice into
     rows [row_offset, row_offset + K) of every [K_total, C] matrix in dest_ptrs (device pointers: the peers' symmetric
@@ -356,7 +376,7 @@ def _segment_tables(Ks, dev):
     if hit is not None:
         return hit
     import math
-    blocks, segs, logs, row = [], [], [], 0
+    blocks, segs, logs, row, row_seg = [], [], [], 0, []
     for s_id, K in enumerate(key[0]):
         first = len(blocks)
         for j0 in range(0, K, _lib.LSE_BLOCK):
@@ -364,15 +384,16 @@ def _segment_tables(Ks, dev):
         segs.append((first, len(blocks) - first))
         logs.append(math.log(float(K)))          # libm log of a double, like the single-layer entry point
         row += K
+        row_seg.append(torch.full((K,), s_id, dtype=torch.int32))
     out = (torch.tensor(blocks, dtype=torch.int32).to(dev), torch.tensor(segs, dtype=torch.int32).to(dev),
-           torch.tensor(logs, dtype=torch.float64).to(dev), len(blocks))
+           torch.tensor(logs, dtype=torch.float64).to(dev), len(blocks), torch.cat(row_seg).to(dev))
     if len(_seg_cache) > 16:
         _seg_cache.clear()
     _seg_cache[key] = out
     return out
 
 
-def pmi_scores_layers(clip_feats, target_feats_list, top_k, a, lam, device, min_prob, ramp):
+def pmi_scores_layers(clip_feats, target_feats_list, top_k, a, lam, device, min_prob, ramp, top_concepts=None):
     """[pmi_scores(clip_feats, t, ...) for t in target_feats_list], bit for bit, with ONE pass of every kernel over
     the layers stacked along the neuron axis: one softmax, one column top-k and one
     gather/log-sum over [N, sum K_l], and log p(d) per layer from segment-wise 256-neuron blocks."""
@@ -408,32 +429,69 @@ def pmi_scores_layers(clip_feats, target_feats_list, top_k, a, lam, device, min_
         with _Stage("wpmi_accum"):
             L = log_sums(S, idx32, ramp, min_prob)
         C = L.shape[1]
-        block_tab, seg_tab, seg_log, n_blocks = _segment_tables(Ks, dev)
+        block_tab, seg_tab, seg_log, n_blocks, row_seg = _segment_tables(Ks, dev)
         lib = _lib.lib()
         with _Stage("lse_finalize"):
             part = torch.empty((n_blocks, 2, C), dtype=torch.float32, device=dev)
             prob_d = torch.empty((len(Ks), C), dtype=torch.float32, device=dev)
             _lib.check(lib.mcd_col_lse_partials_seg_f32(_ptr(L), _ld(L), C, _ptr(block_tab), n_blocks, _ptr(part),
                                                         _stream(dev)), "mcd_col_lse_partials_seg_f32")
-            _lib.check(lib.mcd_pmi_finalize_seg_f32(_ptr(L), _ld(L), C, _ptr(part), _ptr(block_tab), n_blocks,
-                                                    _ptr(seg_tab), _ptr(seg_log), len(Ks), float(lam), _ptr(prob_d),
-                                                    _ptr(L), _ld(L), _stream(dev)), "mcd_pmi_finalize_seg_f32")
+            if top_concepts is None:
+                _lib.check(lib.mcd_pmi_finalize_seg_f32(_ptr(L), _ld(L), C, _ptr(part), _ptr(block_tab), n_blocks,
+                                                        _ptr(seg_tab), _ptr(seg_log), len(Ks), float(lam), _ptr(prob_d),
+                                                        _ptr(L), _ld(L), _stream(dev)), "mcd_pmi_finalize_seg_f32")
+            else:
+                t = int(top_concepts)
+                if t < 1 or t > min(C, 64) or C > 1024:
+                    raise RuntimeError("top concepts: 1 <= t <= min(C, 64) and C <= 1024 (got t=%d, C=%d)" % (t, C))
+                Kt = L.shape[0]
+                vals = torch.empty((Kt, t), dtype=torch.float32, device=dev)
+                idx = torch.empty((Kt, t), dtype=torch.int64, device=dev)
+                _lib.check(lib.mcd_pmi_finalize_seg_topk_f32(_ptr(L), _ld(L), Kt, C, _ptr(part), _ptr(row_seg), n_blocks,
+                                                             _ptr(seg_tab), _ptr(seg_log), len(Ks), float(lam),
+                                                             _ptr(prob_d), _ptr(L), _ld(L), t, _ptr(vals), _ptr(idx),
+                                                             _stream(dev)), "mcd_pmi_finalize_seg_topk_f32")
+    if top_concepts is not None:
+        return list(torch.split(L, Ks, dim=0)), list(torch.split(vals, Ks, dim=0)), list(torch.split(idx, Ks, dim=0))
     return list(torch.split(L, Ks, dim=0))
 
 
 def soft_wpmi_layers(clip_feats, target_feats_list, top_k=100, a=10, lam=1, device='cuda',
-                     min_prob=1e-7, p_start=0.998, p_end=0.97):
+                     min_prob=1e-7, p_start=0.998, p_end=0.97, top_concepts=None):
     """soft_wpmi for all layers of a model in one pass: returns [soft_wpmi(clip_feats, t, ...) for t in the list]
     (views of one [sum K_l, C] matrix), identical bits.  The reference scores layer by layer
-    (describe_broad_neurons.py:83-119); this is the same loop with the per-call work done once."""
+    (describe_broad_neurons.py:83-119); this is the same loop with the per-call work done once.
+    top_concepts=t: also the t best (value, concept) pairs of every neuron, emitted by the finalize pass itself -- what
+    the caller computes next with torch.topk(similarities, k=10, dim=1) (describe_broad_neurons.py:101); returns
+    (scores per layer, top values per layer [K_l, t], top concept indices per layer [K_l, t])."""
     dev = _cuda_device(device)
     ramp = _device_ramp(_reference_ramp(int(top_k), p_start, p_end), top_k, p_start, p_end, dev)
-    return pmi_scores_layers(clip_feats, target_feats_list, top_k, a, lam, dev, min_prob, ramp)
+    return pmi_scores_layers(clip_feats, target_feats_list, top_k, a, lam, dev, min_prob, ramp, top_concepts)
 
 
-def wpmi_layers(clip_feats, target_feats_list, top_k=28, a=2, lam=0.6, device='cuda', min_prob=1e-7):
+def wpmi_layers(clip_feats, target_feats_list, top_k=28, a=2, lam=0.6, device='cuda', min_prob=1e-7, top_concepts=None):
     """wpmi for all layers of a model in one pass (see soft_wpmi_layers)."""
-    return pmi_scores_layers(clip_feats, target_feats_list, top_k, a, lam, device, min_prob, None)
+    return pmi_scores_layers(clip_feats, target_feats_list, top_k, a, lam, device, min_prob, None, top_concepts)
+
+
+def soft_wpmi_top(clip_feats, target_feats, top_concepts=10, top_k=100, a=10, lam=1, device='cuda',
+                  min_prob=1e-7, p_start=0.998, p_end=0.97):
+    """(soft_wpmi scores [K, C], top values [K, t], top concept indices [K, t]): the scores of soft_wpmi(...) bit for bit,
+    with the t best concepts of every neuron emitted by the finalize pass (no second read of the matrix) -- the
+    reference's callers' torch.topk(similarities, 10, 1) / torch.max(similarities, 1)."""
+    dev = _cuda_device(device)
+    ramp = _device_ramp(_reference_ramp(int(top_k), p_start, p_end), top_k, p_start, p_end, dev)
+    L, part = pmi_logsums(clip_feats, target_feats, top_k, a, dev, min_prob, ramp)
+    out, _, vals, idx = pmi_finalize_top(L, part, L.shape[0], lam, top_concepts)
+    return out, vals, idx
+
+
+def wpmi_top(clip_feats, target_feats, top_concepts=10, top_k=28, a=2, lam=0.6, device='cuda', min_prob=1e-7):
+    """wpmi with the per-neuron top concepts (see soft_wpmi_top)."""
+    dev = _cuda_device(device)
+    L, part = pmi_logsums(clip_feats, target_feats, top_k, a, dev, min_prob, None)
+    out, _, vals, idx = pmi_finalize_top(L, part, L.shape[0], lam, top_concepts)
+    return out, vals, idx
 
 
 def top_concepts(scores, k=10):

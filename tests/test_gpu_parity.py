@@ -210,7 +210,7 @@ def _filter_case(kind, N, K, seed=77):
 
 @pytest.mark.parametrize("kind", ["randn", "spikes_on_sampled_rows", "overflow", "relu", "const", "nan_cols", "sorted_up",
                                   "sorted_down", "round1", "mixed"])
-@pytest.mark.parametrize("N,K,k", [(20000, 200, 100), (17017, 131, 28), (33333, 260, 10), (60000, 100, 256)])
+@pytest.mark.parametrize("N,K,k", [(30000, 200, 100), (17017, 131, 28), (33333, 260, 10), (60000, 100, 256)])
 def test_topk_filter_form(sim, kind, N, K, k):
     """Long TMA-aligned columns take the filter form (sample threshold -> filter scan -> select, exact redo of flagged
     column groups).  Same bits as the oracle and as the kept-set scan (tunable topk_filter = 1), values included."""
@@ -254,7 +254,7 @@ def test_pipelined_call_equals_the_staged_path(sim, chunks):
     """mcd_pmi_scores_f32 cuts the neurons into column chunks and runs chunk q's select + K3 + partials on a side stream
     under the scan of chunk q + 1: same bits as the staged single-stream path, for any chunk count."""
     from mammo_clip_dissect_b200 import _lib
-    N, K, C = 12000, 2304, 763
+    N, K, C = 30000, 2304, 763
     A = torch.randn(N, K, generator=gen(91)).to(DEV)
     A[:, 700] = 1.0                                       # a flagged column inside a chunk
     P = (torch.randn(N, C, generator=gen(92)) * 0.05).to(DEV)
@@ -637,6 +637,31 @@ def test_top_concepts_per_neuron(sim, K, C, t):
 # ------------------------------------------------------------------------------------------------
 # K1 similarity matrix, K4 hook
 # ------------------------------------------------------------------------------------------------
+def test_finalize_pass_emits_the_top_concepts(sim):
+    """soft_wpmi_top / soft_wpmi_layers(top_concepts=t): scores bit-identical to soft_wpmi, and the (value, concept)
+    pairs equal the stand-alone row top-k of that matrix (stated order; NaN-free here), for one layer and for stacked
+    layers."""
+    N, C = 3000, 763
+    P = torch.randn(N, C, generator=gen(81)) * 0.05
+    layers = [torch.randn(N, w, generator=gen(82 + w)) for w in (24, 300, 513)]
+    for t in (1, 10, 64):
+        out, vals, idx = sim.soft_wpmi_top(P, layers[1], top_concepts=t, device=DEV)
+        assert torch.equal(out, sim.soft_wpmi(P, layers[1], device=DEV))
+        rv, ri = sim.top_concepts(out, t)
+        assert torch.equal(vals, rv) and torch.equal(idx, ri)
+        assert torch.equal(vals, out.gather(1, idx))
+    w_out, w_vals, w_idx = sim.wpmi_top(P, layers[0], top_concepts=5, device=DEV)
+    assert torch.equal(w_out, sim.wpmi(P, layers[0], device=DEV)) and torch.equal(w_idx, sim.top_concepts(w_out, 5)[1])
+    scores, vals_l, idx_l = sim.soft_wpmi_layers(P, layers, device=DEV, top_concepts=10)
+    plain = sim.soft_wpmi_layers(P, layers, device=DEV)
+    for l in range(3):
+        assert torch.equal(scores[l], plain[l])
+        rv, ri = sim.top_concepts(scores[l], 10)
+        assert torch.equal(vals_l[l], rv) and torch.equal(idx_l[l], ri)
+    with pytest.raises(RuntimeError):
+        sim.soft_wpmi_top(P, layers[0], top_concepts=65, device=DEV)
+
+
 def test_similarity_matrix(sim, golden):
     from mammo_clip_dissect_b200 import features
     g = golden("itt_40x29.npz")
@@ -942,7 +967,7 @@ def test_rank_reorder_vs_oracle(sim, N, C, K, kw, replay):
     if replay == "randperm_calls" and N > 12000:
         pytest.skip("the call-by-call replay is the fallback; covered at the smaller sizes")
     P = torch.randn(N, C, generator=gen(N)) * 0.05 + 0.04          # mixed-sign means: some concepts give NaN
-    P[::3] = P[1::3][: P[::3].shape[0]]                            # duplicated rows: equal cosines -> ties in the ranks
+    P[::3][: P[1::3].shape[0]] = P[1::3]                           # duplicated rows: equal cosines -> ties in the ranks
     A = torch.randn(N, K, generator=gen(K))
     saved = sim._replay_ok
     try:

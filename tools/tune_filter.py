@@ -75,6 +75,14 @@ def main():
                 timeit(lambda: sim.soft_wpmi(P, A, device=dev)), alg)
     _lib.set_tunable("pipe_chunks", 0)
     _lib.set_tunable("filter_stages", 0)
+    if not args.quick:
+        for n2, k2 in ((10000, 9216), (20000, 8192), (40000, 8192)):
+            A2 = torch.randn(n2, k2, generator=g, device=dev)
+            for flt in (0, 1):
+                _lib.set_tunable("topk_filter", flt)
+                say("K2 at N=%d K=%d, %s" % (n2, k2, "kept-set scan" if flt else "filter form"),
+                    timeit(lambda: sim._topk_int32(A2, 100, dev)), 4.0 * n2 * k2 / 1e9)
+            del A2
     _lib.set_tunable("topk_filter", 1)
     _lib.set_tunable("pipe_chunks", -1)
     say("soft_wpmi, round-1 kernels (kept-set scan, one stream)", timeit(lambda: sim.soft_wpmi(P, A, device=dev)), alg)
