@@ -113,7 +113,8 @@ def test_segment_tables_restart_the_lse_blocks_at_every_layer():
     import math
     import torch
     from mammo_clip_dissect_b200 import similarity as sim
-    blocks, segs, logs, n = sim._segment_tables([24, 300, 513, 256], torch.device("cpu"))
+    blocks, segs, logs, n, row_seg = sim._segment_tables([24, 300, 513, 256], torch.device("cpu"))
+    assert row_seg.dtype == torch.int32 and row_seg.tolist() == [0] * 24 + [1] * 300 + [2] * 513 + [3] * 256
     assert n == 7 and blocks.dtype == torch.int32 and logs.dtype == torch.float64
     assert blocks.tolist() == [[0, 24, 0], [24, 256, 1], [280, 44, 1], [324, 256, 2], [580, 256, 2], [836, 1, 2],
                                [837, 256, 3]]
