@@ -18,7 +18,7 @@ struct TopkPlan {
     size_t pre_bytes;                   // tau [K] floats, flags [ncb] ints, kept regions of the pre-pass
     // filter form (topk_filter.cuh): survivor lists instead of kept sets
     int filter;                         // 1: the call takes the filter path
-    int f_cap, f_chunk_tiles, f_chunks, f_nstage;
+    int f_cap, f_chunk_tiles, f_chunks, f_nstage, f_rows;
     size_t f_cnt_bytes, f_list_bytes;   // survivor counts [K] + item counters, lists [K][f_cap]
 };
 

@@ -901,7 +901,7 @@ static bool make_plan(int64_t N, int64_t K, int64_t k64, TopkPlan *p) {
     // elements above the start threshold plus 7 standard deviations (the count of column elements above the j-th
     // largest of a 1/stride sample has relative spread ~ 1/sqrt(j)); an overflowing column is redone exactly.
     p->filter = 0;
-    p->f_cap = p->f_chunk_tiles = p->f_chunks = p->f_nstage = 0;
+    p->f_cap = p->f_chunk_tiles = p->f_chunks = p->f_nstage = p->f_rows = 0;
     p->f_cnt_bytes = p->f_list_bytes = 0;
     // Taken when the 1-in-32 sample applies (N >= ~24 000 rows): measured on B200 at K = 8192 .. 9216 the filter form wins
     // from N = 40 000 (0.42 against 0.75 ms) and loses at N <= 20 000 (1.37 against 0.62 ms), where the denser samples
@@ -919,7 +919,8 @@ static bool make_plan(int64_t N, int64_t K, int64_t k64, TopkPlan *p) {
             int ns = static_cast<int>(tunable(kFilterStages));
             if (ns < 2 || ns > kFMaxStages) ns = 2;         // 18 KB per warp: 12 resident warps per SM, 96 KB in flight (measured best)
             p->f_nstage = ns;
-            const int64_t tiles_total = N / kFRows, nblk = ceil_div<int64_t>(K, kFCols);
+            p->f_rows = tunable(kFilterOrder) == 16 ? 16 : kFRows;          // tunable "filter_order" = 16: 16-row tiles
+            const int64_t tiles_total = N / p->f_rows, nblk = ceil_div<int64_t>(K, kFCols);
             int64_t ct = tunable(kFilterChunkTiles);
             if (ct <= 0) {
                 // a work item = one single-warp CTA; ~32 items per resident warp (8 per SM): the tail of the launch and the
@@ -1048,7 +1049,7 @@ int topk_filter_prepare(const float *A, int64_t lda, int64_t N, int64_t K, int64
     if (reinterpret_cast<uintptr_t>(workspace) % 256 != 0) return MCD_ERR_INVALID_ARGUMENT;
     memset(&c->map_filter, 0, sizeof(CUtensorMap));
     memset(&c->map_scan, 0, sizeof(CUtensorMap));
-    if (!make_tile_map(&c->map_filter, A, lda, N, K, kFCols, kFRows) || !make_tile_map(&c->map_scan, A, lda, N, K, kUnitCols, kTileRows))
+    if (!make_tile_map(&c->map_filter, A, lda, N, K, kFCols, p.f_rows) || !make_tile_map(&c->map_scan, A, lda, N, K, kUnitCols, kTileRows))
         return MCD_ERR_UNSUPPORTED;
     c->plan = p;
     c->A = A;
@@ -1097,19 +1098,20 @@ int topk_filter_scan(const TopkFilterCall &c, int64_t col0, int64_t col1, int la
     a.cnt = c.cnt;
     a.lists = c.lists;
     (void)launch_id;
-    const size_t smem = filter_smem_bytes(p.f_nstage);
-    if (cudaFuncSetAttribute(filter_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess)
-        return MCD_ERR_CUDA;
-    if (c.N >= kFRows) {
+    const int rows = p.f_rows;
+    const size_t smem = filter_smem_bytes(p.f_nstage, rows);
+    auto kern = rows == 16 ? filter_scan_kernel<16> : filter_scan_kernel<8>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)) != cudaSuccess) return MCD_ERR_CUDA;
+    if (c.N >= rows) {
         // blockIdx.x = 128-column block (fastest: neighbours in a wave read neighbouring pieces of the same rows),
         // blockIdx.y = row chunk
         dim3 grid(static_cast<unsigned>(ceil_div<int64_t>(col1 - col0, kFCols)), static_cast<unsigned>(p.f_chunks));
-        filter_scan_kernel<<<grid, kFThreads, smem, st>>>(c.map_filter, a);
+        kern<<<grid, kFThreads, smem, st>>>(c.map_filter, a);
     }
     int rc = check_launch();
-    if (rc != MCD_OK || c.N % kFRows == 0) return rc;
+    if (rc != MCD_OK || c.N % rows == 0) return rc;
     filter_tail_rows_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(col1 - col0, 256)), 256, 0, st>>>(
-        c.A, c.lda, c.N / kFRows * kFRows, c.N, col0, col1, c.tau, c.cnt, c.lists, p.f_cap);
+        c.A, c.lda, c.N / rows * rows, c.N, col0, col1, c.tau, c.cnt, c.lists, p.f_cap);
     return check_launch();
 }
 
@@ -1120,18 +1122,9 @@ int topk_filter_finish(const TopkFilterCall &c, int64_t col0, int64_t col1, int6
     const unsigned sgrid = static_cast<unsigned>(ceil_div<int64_t>(col1 - col0, kSelWarps));
     int kpad = 32;
     while (kpad < c.k) kpad <<= 1;
-    // two launches split the columns: lists that fit the registers (the usual case), and -- only if the capacity allows
-    // longer ones at all -- the rest
-#define MCD_SELECT(PER)                                                                                                      \
-    do {                                                                                                                     \
-        topk_select_kernel<PER, true><<<sgrid, kSelWarps * 32, 0, st>>>(c.lists, c.cnt, p.f_cap, c.k, col0, col1, c.K, c.A,  \
-                                                                        c.lda, idx64, idx32, vals, c.flags);                \
-        if (p.f_cap > 32 * kSelRegWords) {                                                                                   \
-            count_launch(1);                                                                                                 \
-            topk_select_kernel<PER, false><<<sgrid, kSelWarps * 32, 0, st>>>(c.lists, c.cnt, p.f_cap, c.k, col0, col1, c.K,  \
-                                                                             c.A, c.lda, idx64, idx32, vals, c.flags);      \
-        }                                                                                                                    \
-    } while (0)
+#define MCD_SELECT(PER)                                                                                               \
+    topk_select_kernel<PER><<<sgrid, kSelWarps * 32, 0, st>>>(c.lists, c.cnt, p.f_cap, c.k, col0, col1, c.K, c.A, c.lda, \
+                                                             idx64, idx32, vals, c.flags)
     switch (kpad) {
         case 32: MCD_SELECT(1); break;
         case 64: MCD_SELECT(2); break;

@@ -31,12 +31,12 @@
 namespace mcd {
 
 constexpr int kFCols = 128;                          // columns per work item = TMA box width (a lane owns 4)
-constexpr int kFRows = 8;                            // rows per tile
+constexpr int kFRows = 8;                            // rows per tile (default; filter_scan_kernel<16> is the 16-row variant)
 constexpr int kFThreads = 32;                        // one warp per CTA
 constexpr int kFBagCap = 8;                          // entries of one half of a lane-private bag (an entry = 4 values of one row)
 constexpr int kFBagStep = 4;                         // 4 rows append at most 4 entries per lane
 constexpr int kFMaxStages = 8;
-constexpr uint32_t kFTileBytes = kFCols * kFRows * 4;
+constexpr uint32_t kFRowBytes = kFCols * 4;
 constexpr uint32_t kFBagValBytes = 32 * 16, kFBagRowBytes = 32 * 4;      // bag slot strides: float4 / row per lane
 constexpr int kFMaxLaunches = 64;                    // (spare counters behind the survivor counts)
 
@@ -46,7 +46,7 @@ struct FilterTail {
     uint32_t bagr[2][kFBagCap][32];                  // ... and the row
     uint64_t full[kFMaxStages];
 };
-__host__ __device__ inline size_t filter_smem_bytes(int nstage) { return size_t(nstage) * kFTileBytes + sizeof(FilterTail); }
+__host__ __device__ inline size_t filter_smem_bytes(int nstage, int rows) { return size_t(nstage) * rows * kFRowBytes + sizeof(FilterTail); }
 
 __device__ __forceinline__ uint64_t global_timer_ns() {
     uint64_t t;
@@ -86,20 +86,22 @@ struct FilterArgs {
     unsigned long long *lists;           // [K][cap] survivor words (ordered key << 32 | ~row)
 };
 
+template <int ROWS>
 __global__ void __launch_bounds__(kFThreads)
 filter_scan_kernel(const __grid_constant__ CUtensorMap tmap, const FilterArgs a) {
+    constexpr uint32_t kFTileBytes = ROWS * kFRowBytes;
     extern __shared__ __align__(1024) unsigned char fsm[];
     FilterTail &t = *reinterpret_cast<FilterTail *>(fsm + size_t(a.nstage) * kFTileBytes);
     const int lane = threadIdx.x;
     const uint32_t ring_addr = smem_u32(fsm), full_addr = smem_u32(&t.full[0]);
     const int nstage = a.nstage;
     const int64_t c0 = a.col_begin + int64_t(blockIdx.x) * kFCols;
-    const int64_t tiles_total = a.N / kFRows;        // whole tiles; filter_tail_rows_kernel takes the last N % 8 rows
+    const int64_t tiles_total = a.N / ROWS;          // whole tiles; filter_tail_rows_kernel takes the last N % ROWS rows
     const int64_t tile0 = int64_t(blockIdx.y) * a.chunk_tiles;
     const int ntile = static_cast<int>(min(int64_t(a.chunk_tiles), tiles_total - tile0));
     if (ntile <= 0) return;
     const uint64_t policy = l2_policy_evict_first();
-    const int tx = static_cast<int>(c0), ty0 = static_cast<int>(tile0 * kFRows);
+    const int tx = static_cast<int>(c0), ty0 = static_cast<int>(tile0 * ROWS);
 
     if (lane == 0) {
         for (int i = 0; i < nstage; ++i) mbar_init(&t.full[i], 1);
@@ -110,7 +112,7 @@ filter_scan_kernel(const __grid_constant__ CUtensorMap tmap, const FilterArgs a)
     if (lane == 0) {
         for (int i = 0; i < nstage && i < ntile; ++i) {
             mbar_arrive_expect_tx_addr(full_addr + i * 8, kFTileBytes);
-            tma_tile_g2s(ring_addr + i * kFTileBytes, &tmap, tx, ty0 + i * kFRows, full_addr + i * 8, policy);
+            tma_tile_g2s(ring_addr + i * kFTileBytes, &tmap, tx, ty0 + i * ROWS, full_addr + i * 8, policy);
         }
     }
     // this lane's 4 columns and their thresholds (columns outside the launch's range never pass)
@@ -198,17 +200,17 @@ filter_scan_kernel(const __grid_constant__ CUtensorMap tmap, const FilterArgs a)
     int stage = 0, use = 0;
     uint32_t row0 = static_cast<uint32_t>(ty0);
 #pragma unroll 1
-    for (int tl = 0; tl < ntile; ++tl, row0 += kFRows) {
+    for (int tl = 0; tl < ntile; ++tl, row0 += ROWS) {
         mbar_wait_bounded(full_addr + stage * 8, uint32_t(use) & 1u);
         const uint32_t tile = ring_addr + uint32_t(stage) * kFTileBytes + uint32_t(lane) * 16u;
-        float4 v[kFRows];
+        float4 v[ROWS];
 #pragma unroll
-        for (int i = 0; i < kFRows; ++i) v[i] = lds_v4(tile + uint32_t(i) * (kFCols * 4));
+        for (int i = 0; i < ROWS; ++i) v[i] = lds_v4(tile + uint32_t(i) * (kFCols * 4));
         __syncwarp();                                // every lane has the tile's rows in registers
         if (lane == 0 && tl + nstage < ntile) {
             fence_proxy_async();                     // generic-proxy reads before the async-proxy refill
             mbar_arrive_expect_tx_addr(full_addr + stage * 8, kFTileBytes);
-            tma_tile_g2s(ring_addr + uint32_t(stage) * kFTileBytes, &tmap, tx, static_cast<int>(row0) + nstage * kFRows,
+            tma_tile_g2s(ring_addr + uint32_t(stage) * kFTileBytes, &tmap, tx, static_cast<int>(row0) + nstage * ROWS,
                          full_addr + stage * 8, policy);
         }
         if (++stage == nstage) {
@@ -216,13 +218,20 @@ filter_scan_kernel(const __grid_constant__ CUtensorMap tmap, const FilterArgs a)
             ++use;
         }
 #pragma unroll 1
-        for (int ph = 0; ph < 2; ++ph) {
+        for (int ph = 0; ph < ROWS / 4; ++ph) {
+            // (a switch over static register indices: v[] must not be indexed dynamically)
             if (ph == 0) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) append(v[i], row0, i);
-            } else {
+            } else if (ph == 1) {
 #pragma unroll
                 for (int i = 4; i < 8; ++i) append(v[i], row0, i);
+            } else if (ROWS > 8 && ph == 2) {
+#pragma unroll
+                for (int i = 8; i < 12; ++i) append(v[i < ROWS ? i : 0], row0, i);
+            } else if (ROWS > 8) {
+#pragma unroll
+                for (int i = 12; i < 16; ++i) append(v[i < ROWS ? i : 0], row0, i);
             }
             // 4 rows add at most 4 entries per lane: switch halves when a lane has fewer than 4 free slots left
             if (__any_sync(0xffffffffu, pr > half_limit)) flush_issue();
@@ -270,7 +279,7 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
     return v;
 }
 
-constexpr int kSelWarps = 4;
+constexpr int kSelWarps = 8;
 
 struct SelSmem {
     uint32_t hist[kSelWarps][32];
@@ -279,17 +288,15 @@ struct SelSmem {
 };
 
 // flags[col] = k when the column was resolved here, 0 when it has to be redone exactly (list short of k or overflowed).
-// A list of up to 32 * T words is read ONCE (coalesced) and kept in registers, T words per lane -- the usual case: ~576
-// words at c4 --; longer lists are re-read from L2 in every pass (REG = false).
-constexpr int kSelRegWords = 32;
-
-template <int PER, bool REG>
+// The list (~576 words at c4, L2-resident: it was written moments ago) is read once per pass.  Keeping it in registers
+// (96 registers, unrolled predicated passes) or in shared memory (30 KB per CTA) was measured and is slower: 0.21 ms and
+// 0.19 ms against 0.13 ms at c4 -- the passes are instruction-bound, not load-bound.
+template <int PER>
 __global__ void __launch_bounds__(kSelWarps * 32)
 topk_select_kernel(const unsigned long long *__restrict__ lists, const int *__restrict__ cnt, int cap, int k,
                    int64_t col_first, int64_t col_end, int64_t K, const float *__restrict__ A, int64_t lda,
                    int64_t *__restrict__ idx64, int32_t *__restrict__ idx32, float *__restrict__ vals,
                    int *__restrict__ flags) {
-    constexpr int T = kSelRegWords;
     __shared__ SelSmem sm;
     __shared__ unsigned long long sortbuf[kSelWarps][32 * PER];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -297,31 +304,13 @@ topk_select_kernel(const unsigned long long *__restrict__ lists, const int *__re
     if (col >= col_end) return;
     const int n = cnt[col];
     if (n < k || n > cap) {
-        if (lane == 0 && REG) flags[col] = 0;
+        if (lane == 0) flags[col] = 0;
         return;
     }
-    // the two instantiations split the columns between them: REG takes the lists that fit the registers
-    if (REG != (n <= 32 * T)) return;
     if (lane == 0) flags[col] = k;
     const unsigned long long *ent = lists + col * cap;
-    const int tn = (n + 31) >> 5;                            // words per lane (rounded up)
-    unsigned long long e[T];
-    if (REG) {
-#pragma unroll
-        for (int t = 0; t < T; ++t) {
-            const int i = t * 32 + lane;
-            e[t] = (t < tn && i < n) ? ent[i] : 0ull;        // 0 sorts below every real word
-        }
-    }
-    // visit every word of the list: from the registers, or from L2 again
     auto for_each = [&](auto &&fn) {
-        if (REG) {
-#pragma unroll
-            for (int t = 0; t < T; ++t)
-                if (t < tn && e[t] != 0ull) fn(e[t]);
-        } else {
-            for (int i = lane; i < n; i += 32) fn(ent[i]);
-        }
+        for (int i = lane; i < n; i += 32) fn(ent[i]);
     };
     unsigned long long lo = ~0ull, hi = 0ull;
     for_each([&](unsigned long long w) {

@@ -222,8 +222,7 @@ def test_topk_filter_form(sim, kind, N, K, k):
     n0 = _lib.launch_count()
     vals, idx = sim.topk_cols(A, k, device=DEV, want_values=True)
     # sample tile maxima, sample select, filter scan (+ the last N % 8 rows), select, redo scan, redo finish
-    # (+ a second select launch for lists that do not fit the registers when the list capacity allows such lists)
-    assert 6 + (N % 8 != 0) <= _lib.launch_count() - n0 <= 7 + (N % 8 != 0)
+    assert _lib.launch_count() - n0 == 6 + (N % 8 != 0)
     assert torch.equal(idx.cpu(), ref_i), kind
     assert torch.equal(vals.cpu().nan_to_num(7.0), ref_v.nan_to_num(7.0))
     try:

@@ -54,6 +54,12 @@ def main():
         _lib.set_tunable("filter_stages", ns)
         say("K2 filter form, per-warp ring of %d x 4 KB" % ns, timeit(topk))
     _lib.set_tunable("filter_stages", 0)
+    for rows, stages in ((16, 2), (16, 3), (8, 2), (8, 3)):
+        _lib.set_tunable("filter_order", rows)
+        _lib.set_tunable("filter_stages", stages)
+        say("K2 filter form, %d-row tiles, ring of %d" % (rows, stages), timeit(topk))
+    _lib.set_tunable("filter_order", 0)
+    _lib.set_tunable("filter_stages", 0)
     if not args.quick:
         for ct in (43, 85, 170, 340):
             _lib.set_tunable("filter_chunk_tiles", ct)
