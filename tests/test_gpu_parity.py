@@ -693,12 +693,15 @@ def test_similarity_matrix_tensor_core_vs_fp32(sim, N, C, D, normalize):
     scale = ref.abs().max().item()
     n0 = _lib.launch_count()
     P_tc = features.similarity_matrix(I, T, device=DEV, normalize=normalize).cpu()
-    assert _lib.launch_count() - n0 == 3                 # 2 x prepare_rows + gemm_tf32x3 (the tensor-core path ran)
-    try:
+    assert _lib.launch_count() - n0 == 3                 # 2 x prepare_rows + gemm_tf32x3
+    assert features.last_gemm_path() == "tcgen05"        # ... and the library says which GEMM it ran (the CUDA-core
+    try:                                                 # fallback is 3 launches too: 2 x row_norm + sgemm)
         _lib.set_tunable("gemm_variant", 1)
         P_32 = features.similarity_matrix(I, T, device=DEV, normalize=normalize).cpu()
+        assert features.last_gemm_path() == "fp32_ffma"
     finally:
         _lib.set_tunable("gemm_variant", 0)
+    assert not torch.equal(P_tc, P_32) or N * C < 64     # two different arithmetic paths: not the same bits
     e_tc = (P_tc.double() - ref).abs().max().item() / scale
     e_32 = (P_32.double() - ref).abs().max().item() / scale
     print("K1 max err / max|P|: tcgen05 3xTF32 %.3g, fp32 CUDA-core %.3g" % (e_tc, e_32))
@@ -719,6 +722,7 @@ def test_similarity_matrix_tensor_core_vs_fp32(sim, N, C, D, normalize):
         n0 = _lib.launch_count()
         P_f, S_f = features.similarity_matrix(I, T, device=DEV, normalize=normalize, softmax_scale=10)
         assert _lib.launch_count() - n0 == 3             # 2 x prepare_rows + the band kernel: no softmax launch
+        assert features.last_gemm_path() == "tcgen05_fused_softmax"
     finally:
         _lib.set_tunable("gemm_variant", 0)
     assert torch.equal(P_f, P_s) and torch.equal(P_f.cpu(), P_tc)
