@@ -74,7 +74,7 @@ int mcd_device_check(void) {
 }
 
 int mcd_set_tunable(const char *name, int64_t value) {
-    static const char *names[] = {"topk_splits", "accum_tile", "topk_variant", "accum_unroll", "topk_cols", "topk_stages", "topk_occ", "gemm_variant", "topk_pre", "topk_small", "topk_filter", "filter_stages", "filter_chunk_tiles", "pipe_chunks", "filter_order"};
+    static const char *names[] = {"topk_splits", "accum_tile", "topk_variant", "accum_unroll", "topk_cols", "topk_stages", "topk_occ", "gemm_variant", "topk_pre", "topk_small", "topk_filter", "filter_stages", "filter_chunk_tiles", "pipe_chunks", "filter_order", "accum_pad_kb"};
     constexpr int n_names = sizeof(names) / sizeof(names[0]);
     if (!name) return MCD_ERR_INVALID_ARGUMENT;
     for (int i = 0; i < n_names; ++i)
@@ -219,7 +219,10 @@ int pmi_logsums(const float *P, int64_t ldp, const float *A, int64_t lda, int64_
             return MCD_ERR_CUDA;
         rc = topk_filter_finish(call, c0, c1, nullptr, idx, nullptr, side);
         if (rc != MCD_OK) return rc;
-        rc = wpmi_accum_range(S, l.lds, N, C, idx + c0, K, c1 - c0, k, p, min_prob, L + c0 * ldl, ldl, side, true);
+        // all chunks but the last run beside the scan of the next chunk: pad their shared memory (tunable accum_pad_kb) so
+        // that only one or two of K3's CTAs fit next to the scan's resident warps on an SM -- the scan needs >= 9 of them
+        const size_t pad = q + 1 < nq ? size_t(tunable(kAccumPadKb)) << 10 : 0;
+        rc = wpmi_accum_range(S, l.lds, N, C, idx + c0, K, c1 - c0, k, p, min_prob, L + c0 * ldl, ldl, side, true, pad);
         if (rc != MCD_OK) return rc;
         rc = mcd_col_lse_partials_f32(L + c0 * ldl, ldl, c1 - c0, C, part + (c0 / MCD_LSE_BLOCK) * 2 * C, side);
         if (rc != MCD_OK) return rc;

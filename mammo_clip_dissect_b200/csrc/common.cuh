@@ -13,7 +13,7 @@ constexpr int kNumSMsB200 = 148;
 void count_launch(int n = 1);          // abi.cu
 int64_t tunable(int which);            // abi.cu
 enum Tunable { kTopkSplits = 0, kAccumTile = 1, kTopkVariant = 2, kAccumUnroll = 3, kTopkCols = 4, kTopkStages = 5, kTopkOcc = 6, kGemmVariant = 7,
-               kTopkPre = 8, kTopkSmall = 9, kTopkFilter = 10, kFilterStages = 11, kFilterChunkTiles = 12, kPipeChunks = 13, kFilterOrder = 14,
+               kTopkPre = 8, kTopkSmall = 9, kTopkFilter = 10, kFilterStages = 11, kFilterChunkTiles = 12, kPipeChunks = 13, kFilterOrder = 14, kAccumPadKb = 15,
                kNumTunables = 16 };
 int num_sms();                         // abi.cu (cached cudaDevAttrMultiProcessorCount)
 

@@ -54,6 +54,7 @@ int topk_filter_finish(const TopkFilterCall &c, int64_t col0, int64_t col1, int6
 // K3 on a column range: idx points at the range's first column of the [k, idx_ld] index matrix
 // probabilities: the caller vouches for S in [0, 1] (what the softmax kernels write): enables the grouped-log evaluation
 int wpmi_accum_range(const float *S, int64_t lds, int64_t N, int64_t C, const int32_t *idx, int64_t idx_ld, int64_t K,
-                     int64_t k, const float *p, float min_prob, float *L, int64_t ldl, cudaStream_t st, bool probabilities);
+                     int64_t k, const float *p, float min_prob, float *L, int64_t ldl, cudaStream_t st, bool probabilities,
+                     size_t pad_smem = 0);
 
 }  // namespace mcd

@@ -205,7 +205,7 @@ wpmi_accum_kernel(const float *__restrict__ S, int64_t lds, int C, const int32_t
 
 template <int TPN, bool SOFT, bool VEC>
 static int launch_accum(const float *S, int64_t lds, int C, const int32_t *idx, int64_t idx_ld, int64_t K, int k,
-                        const float *p, float eps, float *L, int64_t ldl, cudaStream_t st, bool probabilities) {
+                        const float *p, float eps, float *L, int64_t ldl, cudaStream_t st, bool probabilities, size_t pad_smem) {
     const bool ftz = eps >= 1.17549435e-38f;
     constexpr int NPB = kAccumThreads / TPN;
     const int n_tiles = ceil_div(C, TPN * 4);
@@ -219,7 +219,8 @@ static int launch_accum(const float *S, int64_t lds, int C, const int32_t *idx, 
     // entry two negative terms would multiply to a positive product and the log would come out finite instead of NaN
     const bool grouped = probabilities && eps >= 1e-9f && eps <= 1.0f && mode != 1;
     const unsigned nb = static_cast<unsigned>(blocks);
-    const size_t sm = size_t(NPB + 2) * size_t((k + 3) & ~3) * 4;
+    // pad_smem: unused shared memory that caps how many of these CTAs fit beside another resident kernel (abi.cu)
+    const size_t sm = size_t(NPB + 2) * size_t((k + 3) & ~3) * 4 + pad_smem;
     const int ng = static_cast<int>(n_groups);
     if (grouped && mode != 2)
         wpmi_accum_kernel<TPN, 8, SOFT, VEC, true, true, true><<<nb, kAccumThreads, sm, st>>>(S, lds, C, idx, idx_ld, K, k, p, eps, L, ldl, ng);
@@ -234,19 +235,21 @@ static int launch_accum(const float *S, int64_t lds, int C, const int32_t *idx, 
 
 template <bool SOFT, bool VEC>
 static int dispatch_tile(int tpn, const float *S, int64_t lds, int C, const int32_t *idx, int64_t idx_ld, int64_t K, int k,
-                         const float *p, float eps, float *L, int64_t ldl, cudaStream_t st, bool probabilities) {
+                         const float *p, float eps, float *L, int64_t ldl, cudaStream_t st, bool probabilities,
+                         size_t pad_smem) {
     switch (tpn) {
-        case 192: return launch_accum<192, SOFT, VEC>(S, lds, C, idx, idx_ld, K, k, p, eps, L, ldl, st, probabilities);
-        case 96: return launch_accum<96, SOFT, VEC>(S, lds, C, idx, idx_ld, K, k, p, eps, L, ldl, st, probabilities);
-        case 64: return launch_accum<64, SOFT, VEC>(S, lds, C, idx, idx_ld, K, k, p, eps, L, ldl, st, probabilities);
-        case 48: return launch_accum<48, SOFT, VEC>(S, lds, C, idx, idx_ld, K, k, p, eps, L, ldl, st, probabilities);
-        case 16: return launch_accum<16, SOFT, VEC>(S, lds, C, idx, idx_ld, K, k, p, eps, L, ldl, st, probabilities);
-        default: return launch_accum<32, SOFT, VEC>(S, lds, C, idx, idx_ld, K, k, p, eps, L, ldl, st, probabilities);
+        case 192: return launch_accum<192, SOFT, VEC>(S, lds, C, idx, idx_ld, K, k, p, eps, L, ldl, st, probabilities, pad_smem);
+        case 96: return launch_accum<96, SOFT, VEC>(S, lds, C, idx, idx_ld, K, k, p, eps, L, ldl, st, probabilities, pad_smem);
+        case 64: return launch_accum<64, SOFT, VEC>(S, lds, C, idx, idx_ld, K, k, p, eps, L, ldl, st, probabilities, pad_smem);
+        case 48: return launch_accum<48, SOFT, VEC>(S, lds, C, idx, idx_ld, K, k, p, eps, L, ldl, st, probabilities, pad_smem);
+        case 16: return launch_accum<16, SOFT, VEC>(S, lds, C, idx, idx_ld, K, k, p, eps, L, ldl, st, probabilities, pad_smem);
+        default: return launch_accum<32, SOFT, VEC>(S, lds, C, idx, idx_ld, K, k, p, eps, L, ldl, st, probabilities, pad_smem);
     }
 }
 
 int wpmi_accum_range(const float *S, int64_t lds, int64_t N, int64_t C, const int32_t *idx, int64_t idx_ld, int64_t K,
-                     int64_t k, const float *p, float min_prob, float *L, int64_t ldl, cudaStream_t st, bool probabilities) {
+                     int64_t k, const float *p, float min_prob, float *L, int64_t ldl, cudaStream_t st, bool probabilities,
+                     size_t pad_smem) {
     if (!S || !idx || !L || N < 1 || C < 1 || K < 1 || k < 1 || lds < C || ldl < C || idx_ld < K) return MCD_ERR_INVALID_ARGUMENT;
     if (k > kAccumMaxK || C > (1 << 24) || N * lds >= (int64_t(1) << 30)) return MCD_ERR_UNSUPPORTED;
     // 16-byte loads need aligned rows and must stay inside a row (padding included)
@@ -265,10 +268,10 @@ int wpmi_accum_range(const float *S, int64_t lds, int64_t N, int64_t C, const in
     else if (want > 16) tpn = 32;
     else tpn = 16;
     const int Ci = static_cast<int>(C), ki = static_cast<int>(k);
-    if (p) return vec ? dispatch_tile<true, true>(tpn, S, lds, Ci, idx, idx_ld, K, ki, p, min_prob, L, ldl, st, probabilities)
-                      : dispatch_tile<true, false>(tpn, S, lds, Ci, idx, idx_ld, K, ki, p, min_prob, L, ldl, st, probabilities);
-    return vec ? dispatch_tile<false, true>(tpn, S, lds, Ci, idx, idx_ld, K, ki, p, min_prob, L, ldl, st, probabilities)
-               : dispatch_tile<false, false>(tpn, S, lds, Ci, idx, idx_ld, K, ki, p, min_prob, L, ldl, st, probabilities);
+    if (p) return vec ? dispatch_tile<true, true>(tpn, S, lds, Ci, idx, idx_ld, K, ki, p, min_prob, L, ldl, st, probabilities, pad_smem)
+                      : dispatch_tile<true, false>(tpn, S, lds, Ci, idx, idx_ld, K, ki, p, min_prob, L, ldl, st, probabilities, pad_smem);
+    return vec ? dispatch_tile<false, true>(tpn, S, lds, Ci, idx, idx_ld, K, ki, p, min_prob, L, ldl, st, probabilities, pad_smem)
+               : dispatch_tile<false, false>(tpn, S, lds, Ci, idx, idx_ld, K, ki, p, min_prob, L, ldl, st, probabilities, pad_smem);
 }
 
 }  // namespace mcd
@@ -276,11 +279,11 @@ int wpmi_accum_range(const float *S, int64_t lds, int64_t N, int64_t C, const in
 extern "C" int mcd_wpmi_accum_f32(const float *S, int64_t lds, int64_t N, int64_t C, const int32_t *idx, int64_t K,
                                   int64_t k, const float *p, float min_prob, float *L, int64_t ldl,
                                   mcd_stream_t stream) {
-    return mcd::wpmi_accum_range(S, lds, N, C, idx, K, K, k, p, min_prob, L, ldl, static_cast<cudaStream_t>(stream), false);
+    return mcd::wpmi_accum_range(S, lds, N, C, idx, K, K, k, p, min_prob, L, ldl, static_cast<cudaStream_t>(stream), false, 0);
 }
 
 extern "C" int mcd_wpmi_accum_prob_f32(const float *S, int64_t lds, int64_t N, int64_t C, const int32_t *idx, int64_t K,
                                        int64_t k, const float *p, float min_prob, float *L, int64_t ldl,
                                        mcd_stream_t stream) {
-    return mcd::wpmi_accum_range(S, lds, N, C, idx, K, K, k, p, min_prob, L, ldl, static_cast<cudaStream_t>(stream), true);
+    return mcd::wpmi_accum_range(S, lds, N, C, idx, K, K, k, p, min_prob, L, ldl, static_cast<cudaStream_t>(stream), true, 0);
 }

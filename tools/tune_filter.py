@@ -81,6 +81,14 @@ def main():
                 timeit(lambda: sim.soft_wpmi(P, A, device=dev)), alg)
     _lib.set_tunable("pipe_chunks", 0)
     _lib.set_tunable("filter_stages", 0)
+    for q in (2, 3, 4, 6):
+        for pad in (19, 21, 24, 30, 40):
+            _lib.set_tunable("pipe_chunks", q)
+            _lib.set_tunable("accum_pad_kb", pad)
+            say("soft_wpmi, %d column chunks, K3 padded by %d KB beside the scan" % (q, pad),
+                timeit(lambda: sim.soft_wpmi(P, A, device=dev)), alg)
+    _lib.set_tunable("pipe_chunks", 0)
+    _lib.set_tunable("accum_pad_kb", 0)
     if not args.quick:
         for n2, k2 in ((10000, 9216), (20000, 8192), (40000, 8192)):
             A2 = torch.randn(n2, k2, generator=g, device=dev)
