@@ -422,10 +422,27 @@ def run_ours(args):
         torch.cuda.empty_cache()
         A = torch.randn(N_IMG, K_NEURONS, generator=torch.Generator(device=dev).manual_seed(2 + 1000 * rank), device=dev)
         wsizes = [K_NEURONS] * world
-        ms_w = timed(lambda: mdist.soft_wpmi_sharded(P, A, wsizes, top_k=TOP_K, device=dev, backend=backend,
-                                                    gather_scores=False), max(3, args.steps // 2), 2)
+        wfn = lambda: mdist.soft_wpmi_sharded(P, A, wsizes, top_k=TOP_K, device=dev, backend=backend, gather_scores=False)  # noqa: E731
+        wsampler = ClockSampler(local_rank)
+        if rank == 0:
+            wsampler.start()
+            time.sleep(0.25)
+        ms_w = timed(wfn, max(10, 2 * args.steps), 3)
+        if rank == 0:
+            time.sleep(0.1)
+        wclocks = wsampler.stop() if rank == 0 else None
+        similarity.PROFILE = []
+        for _ in range(3):
+            wfn()
+        wstage = {k: round(max_over_ranks(v), 4) for k, v in sorted(similarity.profile_summary().items())}
+        similarity.PROFILE = None
+        # the same call without the exchange of the LSE partials: what a rank does on its own
+        solo = timed(lambda: similarity.pmi_logsums(P, A, TOP_K, 10, dev, 1e-7,
+                                                    similarity._device_ramp(similarity._reference_ramp(TOP_K, 0.998, 0.97), TOP_K, 0.998, 0.97, dev)),
+                     max(5, args.steps), 2)
         weak = {"ms_per_step": round(ms_w, 4), "value": round(K_NEURONS * world / (ms_w / 1e3), 1), "unit": UNIT,
-                "K_per_gpu": K_NEURONS, "K_total": K_NEURONS * world,
+                "K_per_gpu": K_NEURONS, "K_total": K_NEURONS * world, "stage_ms": wstage, "clocks": wclocks,
+                "ms_per_step_without_the_partials_exchange": round(solo, 4),
                 "note": "every rank scores 32768 neurons (layer width grows with N); LSE partials all-gathered, shards stay local"}
         del A
         torch.cuda.empty_cache()

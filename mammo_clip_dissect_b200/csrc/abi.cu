@@ -192,7 +192,11 @@ int pmi_logsums(const float *P, int64_t ldp, const float *A, int64_t lda, int64_
     // every overlapped variant LOSES to the plain sequence (3.19 ms; 2 chunks 3.46, 4 chunks 3.62) -- K3's CTAs take
     // resident-warp slots and L2 bandwidth from the scan, which needs >= 9 resident warps per SM to saturate HBM, and
     // each chunk re-reads the concept-tile slices of S from DRAM -- so the pipeline stays an option, not the default.
-    PipeRes *pr = tunable(kPipeChunks) > 0 ? pipe_resources() : nullptr;
+    // What IS worth a second stream: the softmax (K1b) beside the sample pass and the scan when the neuron shard is narrow
+    // (a rank of the 8-GPU call: 4096 neurons) -- the softmax over all N images does not shrink with the shard and would
+    // otherwise be a third of the rank's step; at full width both are HBM-bound and the overlap is neutral.
+    const bool side_softmax = tunable(kPipeChunks) == 0 && N * C >= (int64_t(1) << 23) && K <= 16384;
+    PipeRes *pr = (tunable(kPipeChunks) > 0 || side_softmax) ? pipe_resources() : nullptr;
     int rc = pr ? topk_filter_prepare(A, lda, N, K, k, w + l.topk_off, workspace_bytes - l.topk_off, &call) : MCD_ERR_UNSUPPORTED;
     if (rc != MCD_OK && rc != MCD_ERR_UNSUPPORTED) return rc;
     if (rc == MCD_ERR_UNSUPPORTED) {
