@@ -317,6 +317,14 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def per_rank(x):
+        if world == 1:
+            return [round(x, 4)]
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [round(float(o.item()), 4) for o in out]
+
     parity = {}
     if world > 1:
         parity["sharded_vs_single_gpu"] = sharded_parity(similarity, mdist, dev, world, rank)
@@ -437,12 +445,21 @@ def run_ours(args):
         wstage = {k: round(max_over_ranks(v), 4) for k, v in sorted(similarity.profile_summary().items())}
         similarity.PROFILE = None
         # the same call without the exchange of the LSE partials: what a rank does on its own
-        solo = timed(lambda: similarity.pmi_logsums(P, A, TOP_K, 10, dev, 1e-7,
-                                                    similarity._device_ramp(similarity._reference_ramp(TOP_K, 0.998, 0.97), TOP_K, 0.998, 0.97, dev)),
-                     max(5, args.steps), 2)
+        solo_fn = lambda: similarity.pmi_logsums(P, A, TOP_K, 10, dev, 1e-7, similarity._device_ramp(  # noqa: E731
+            similarity._reference_ramp(TOP_K, 0.998, 0.97), TOP_K, 0.998, 0.97, dev))
+        solo = timed(solo_fn, max(5, args.steps), 2)
+        # ... and every rank's own time for it (no collective inside): tells a slow GPU from a scaling effect
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            solo_fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        solo_ranks = per_rank(e0.elapsed_time(e1) / 5)
         weak = {"ms_per_step": round(ms_w, 4), "value": round(K_NEURONS * world / (ms_w / 1e3), 1), "unit": UNIT,
                 "K_per_gpu": K_NEURONS, "K_total": K_NEURONS * world, "stage_ms": wstage, "clocks": wclocks,
-                "ms_per_step_without_the_partials_exchange": round(solo, 4),
+                "ms_per_step_without_the_partials_exchange": round(solo, 4), "the_same_per_rank_ms": solo_ranks,
                 "note": "every rank scores 32768 neurons (layer width grows with N); LSE partials all-gathered, shards stay local"}
         del A
         torch.cuda.empty_cache()

@@ -897,9 +897,8 @@ static bool make_plan(int64_t N, int64_t K, int64_t k64, TopkPlan *p) {
             }
         }
     }
-    // Filter form (topk_filter.cuh) for long columns: survivor lists sized for the expected pre_k * pre_stride
-    // elements above the start threshold plus 7 standard deviations (the count of column elements above the j-th
-    // largest of a 1/stride sample has relative spread ~ 1/sqrt(j)); an overflowing column is redone exactly.
+    // Filter form (topk_filter.cuh) for long columns: survivor lists sized so that a column overflows with probability
+    // <= 1e-10 (below); a column that does overflow, or comes up short of k, is redone exactly.
     p->filter = 0;
     p->f_cap = p->f_chunk_tiles = p->f_chunks = p->f_nstage = p->f_rows = 0;
     p->f_cnt_bytes = p->f_list_bytes = 0;
@@ -908,8 +907,19 @@ static bool make_plan(int64_t N, int64_t K, int64_t k64, TopkPlan *p) {
     // (1 tile in 16 .. 4) cost as much as the scan itself and the kept-set scan's start-up is still cheap.
     if (p->pre_stride == 32 && N < (int64_t(1) << 30) && tunable(kTopkFilter) != 1 && tunable(kTopkVariant) == 0 &&
         tunable(kTopkSplits) <= 0) {
-        const double mean = double(p->pre_k) * p->pre_stride;
-        int cap = static_cast<int>(mean * (1.0 + 7.0 / sqrt(double(p->pre_k)))) + 31;
+        // the number of column elements above the j-th largest of a 1/stride sample is ~ stride * Gamma(j): the list
+        // holds stride * x elements with P(Gamma(j) > x) = P(Poisson(x) <= j - 1) <= 1e-10 (x = 59.25 for j = 18: 3.3 x the
+        // mean; "mean + 7 sigma" of a normal fit would let one column in 200 000 overflow -- the tail is a gamma's)
+        double x = double(p->pre_k);
+        for (;; x += 0.25) {
+            double term = exp(-x), cdf = 0.0;
+            for (int i = 0; i < p->pre_k; ++i) {
+                cdf += term;
+                term *= x / double(i + 1);
+            }
+            if (cdf <= 1e-10 || x > 40.0 * p->pre_k) break;
+        }
+        int cap = static_cast<int>(x * p->pre_stride) + 31;
         if (cap < 2 * k + 64) cap = 2 * k + 64;
         cap = cap / 32 * 32;
         const size_t list_bytes = size_t(K) * size_t(cap) * 8;

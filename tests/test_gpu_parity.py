@@ -188,7 +188,7 @@ def _filter_case(kind, N, K, seed=77):
     if kind == "spikes_on_sampled_rows":
         A[::32] += 50.0                      # the sample only sees the spikes: threshold far too high -> short lists -> redo
     elif kind == "overflow":
-        A[(tile % 32 == 5) | (tile % 32 == 7)] += 50.0      # rows no sample stride (32/16/8/4) visits: lists overflow -> redo
+        A[(tile % 8 == 5) | (tile % 8 == 7)] += 50.0        # a quarter of the rows, none in a sampled tile: lists overflow -> redo
     elif kind == "relu":
         A = torch.relu(A - 2.5)              # 99.4 % exact zeros
     elif kind == "const":
