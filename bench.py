@@ -550,8 +550,9 @@ def run_ours(args):
                               "note": "B_alg = 4NK + 4NC + 4KC (SURVEY.md 8d; P and its softmax are replicated, so 4NC "
                                       "counts once per GPU); gather re-reads not counted; peak = N x one GPU's measured HBM peak"},
             "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
-            "stage_note": "stage_ms is the staged single-stream pass (max over ranks); ms_per_step is the public call, "
-                          "which pipelines column chunks (K3 of chunk q under the scan of chunk q+1, softmax under the scan)",
+            "stage_note": "stage_ms is a separate staged pass with CUDA events between the stages (max over ranks); "
+                          "ms_per_step is the public call (one C entry point; the softmax of a narrow shard runs on a "
+                          "side stream beside the sample pass and the scan)",
             "with_score_exchange": with_exchange, "weak": weak, "parity": parity, "reference_gpu": ref_gpu}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()

@@ -1,7 +1,7 @@
 """Turn an `ncu --metrics gpu__time_duration.sum --csv` launch list into profiles/<name>.md (+ a cleaned .csv).
 usage: python tools/launch_list.py gpurun_out/launches.csv profiles/r1_launches "<command that was profiled>" [bench.json]
 
-The role of a launch is derived from the kernel NAME (and, for the two scans, from their order inside a call); one
+The role of a launch is derived from the kernel NAME; one
 call of soft_wpmi = the launches between two softmax_rows kernels.  The table shows the LAST complete call of the
 capture (warm allocator, same as the timed region) and the per-kernel mean over all complete calls."""
 import csv
@@ -12,8 +12,12 @@ ROLES = [
     ("softmax_rows_kernel", "K1b softmax(a*P) rows"),
     ("sample_tilemax_kernel", "K2 sample: per-column maxima of 1 tile in 32"),
     ("sample_select_kernel", "K2 sample: j-th largest tile maximum = start threshold"),
-    ("topk_scan_kernel", None),
-    ("topk_finish", "K2 finish (sort survivors, emit indices)"),
+    ("filter_scan_kernel", "K2 filter scan: stream A once, append elements above the column threshold"),
+    ("filter_tail_rows_kernel", "K2 filter: the last N % 8 rows"),
+    ("topk_select_kernel", "K2 select: exact top k of every survivor list, sorted, indices out"),
+    ("topk_scan_kernel", "K2 exact redo of flagged column groups (kept-set scan)"),
+    ("topk_finish", "K2 redo finish (flagged columns only)"),
+    ("topk_small_kernel", "K2 radix select (short or wide-k problems)"),
     ("wpmi_accum_kernel", "K3 gather + rank-weighted log-sum"),
     ("col_lse_partials_kernel", "K3b 256-neuron block partials (max, sum exp)"),
     ("lse_combine_kernel", "K3b combine partials -> logsumexp per concept"),
@@ -47,23 +51,20 @@ def main():
     n_per = max(len(c) for c in calls)
     full = [c for c in calls if len(c) == n_per]
     last = full[-1]
-    lines = ["# ncu launch list (round 1)", "", "Command: `%s`" % cmd, "",
+    import os
+    lines = ["# ncu launch list (%s)" % os.path.basename(out), "", "Command: `%s`" % cmd, "",
              "%d launches of this library's kernels captured = %d complete `soft_wpmi` calls of %d launches each "
              "(c4: N = 100000 probe images, K = 32768 neurons, C = 763 concepts, top_k = 100).  The table is the last "
              "complete call; `mean` is over all complete calls.  Per-launch times under ncu are cold-cache and "
              "serialised: compare SHARES with bench.py's `stage_ms`, not absolutes." % (len(launches), len(full), n_per),
              "", "| # | kernel | role | grid | block | ms | mean ms | share |", "|---|---|---|---|---|---|---|---|"]
     tot = sum(l[3] for l in last)
-    scans = 0
     stage = {"K1b": 0.0, "K2": 0.0, "K3": 0.0, "K3b": 0.0}
     for i, l in enumerate(last):
         role = "?"
         for pat, r in ROLES:
             if l[0].startswith(pat):
                 role = r
-        if l[0].startswith("topk_scan_kernel"):
-            role = "K2 scan (starts from the sampled threshold)" if scans == 0 else "K2 redo pass (only flagged column groups)"
-            scans += 1
         mean = sum(c[i][3] for c in full) / len(full)
         stage[role.split()[0]] = stage.get(role.split()[0], 0.0) + l[3]
         lines.append("| %d | `%s` | %s | %s | %s | %.4f | %.4f | %.1f %% |" % (i, l[0], role, l[1], l[2], l[3], mean, 100 * l[3] / tot))
