@@ -224,6 +224,11 @@ int mcd_rank_reorder_f32(const float *P, int64_t ldp, int64_t N, int64_t C, cons
                          int64_t K, int64_t top_n, const int32_t *perms, float p, float scale_p,
                          float *baseline_ws, float *out, int64_t ldo, mcd_stream_t stream);
 size_t mcd_rank_reorder_workspace_bytes(int64_t K, int64_t top_n);
+/* The raw draws themselves: continues MT19937 (torch's CPU generator engine, ATen/core/MersenneTwister.h as used by
+ * torch.randperm in similarity.py:119) on the device.  state_io: 624 state words + 1 word "index of the next output"
+ * (624 = twist before the next draw); on return it holds the state after `count` outputs, for the host to write back
+ * into the generator.  draws [count] uint32. */
+int mcd_mt19937_draws(uint32_t *state_io, int64_t count, uint32_t *draws, mcd_stream_t stream);
 int mcd_rank_reorder_draws_f32(const float *P, int64_t ldp, int64_t N, int64_t C, const int32_t *idx, const float *vals,
                                int64_t K, int64_t top_n, const uint32_t *draws, float p, float scale_p,
                                void *workspace, size_t workspace_bytes, float *out, int64_t ldo, mcd_stream_t stream);

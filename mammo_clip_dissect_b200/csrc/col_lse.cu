@@ -15,7 +15,7 @@ namespace mcd {
 constexpr int kLseThreads = 128;
 
 // thread per concept, one pass over the block's 256 rows with an online (max, sum) pair: the running sum is
-// rescaled whenever the maximum rises (the rescale factor is exactly 1 otherwise), loads 4 rows ahead
+// rescaled whenever the maximum rises (the rescale factor is exactly 1 otherwise), 16 rows per step
 __global__ void __launch_bounds__(kLseThreads)
 col_lse_partials_kernel(const float *__restrict__ L, int64_t ldl, int64_t K, int C, float *__restrict__ partials,
                         const int32_t *__restrict__ block_tab) {
@@ -28,18 +28,21 @@ col_lse_partials_kernel(const float *__restrict__ L, int64_t ldl, int64_t K, int
     const float *col = L + c;
     float m = -INFINITY, s = 0.f;
     int64_t j = j0;
-    for (; j + 4 <= j1; j += 4) {
-        const float x0 = col[j * ldl], x1 = col[(j + 1) * ldl], x2 = col[(j + 2) * ldl], x3 = col[(j + 3) * ldl];
-        const float mx = fmaxf(fmaxf(x0, x1), fmaxf(x2, x3));
+    constexpr int kAhead = 16;      // independent row loads in flight per thread (20 warps per SM x 16 x 128 B)
+    for (; j + kAhead <= j1; j += kAhead) {
+        float x[kAhead];
+#pragma unroll
+        for (int u = 0; u < kAhead; ++u) x[u] = col[(j + u) * ldl];
+        float mx = x[0];
+#pragma unroll
+        for (int u = 1; u < kAhead; ++u) mx = fmaxf(mx, x[u]);
         if (mx > m) {
             s *= (m == -INFINITY) ? 0.f : expf(m - mx);
             m = mx;
         }
         const float ms = (m == -INFINITY) ? 0.f : m;
-        s += expf(x0 - ms);
-        s += expf(x1 - ms);
-        s += expf(x2 - ms);
-        s += expf(x3 - ms);
+#pragma unroll
+        for (int u = 0; u < kAhead; ++u) s += expf(x[u] - ms);
     }
     for (; j < j1; ++j) {
         const float x = col[j * ldl];

@@ -175,8 +175,8 @@ __device__ __forceinline__ float lg2_approx(float x) {
 
 // bitonic sort, descending, of 32 * PER words held as word i = PER * lane + slot (strides below PER exchange inside a
 // lane, the others with shfl.xor)
-template <int PER>
-__device__ __forceinline__ void bitonic_desc_regs(unsigned long long (&v)[PER], int lane) {
+template <int PER, typename T>
+__device__ __forceinline__ void bitonic_desc_regs(T (&v)[PER], int lane) {
     constexpr int TOTAL = 32 * PER;
 #pragma unroll
     for (int size = 2; size <= TOTAL; size <<= 1) {
@@ -189,8 +189,8 @@ __device__ __forceinline__ void bitonic_desc_regs(unsigned long long (&v)[PER], 
                 const bool keep_max = desc != upper;
 #pragma unroll
                 for (int e = 0; e < PER; ++e) {
-                    const unsigned long long o = __shfl_xor_sync(0xffffffffu, v[e], stride / PER);
-                    const unsigned long long hi = v[e] > o ? v[e] : o, lo = v[e] > o ? o : v[e];
+                    const T o = __shfl_xor_sync(0xffffffffu, v[e], stride / PER);
+                    const T hi = v[e] > o ? v[e] : o, lo = v[e] > o ? o : v[e];
                     v[e] = keep_max ? hi : lo;
                 }
             } else {
@@ -198,8 +198,8 @@ __device__ __forceinline__ void bitonic_desc_regs(unsigned long long (&v)[PER], 
                 for (int e = 0; e < PER; ++e) {
                     if ((e & stride) == 0) {
                         const bool desc = size >= TOTAL || ((lane * PER + e) & size) == 0;
-                        const unsigned long long x = v[e], y = v[e + stride < PER ? e + stride : e];
-                        const unsigned long long hi = x > y ? x : y, lo = x > y ? y : x;
+                        const T x = v[e], y = v[e + stride < PER ? e + stride : e];
+                        const T hi = x > y ? x : y, lo = x > y ? y : x;
                         v[e] = desc ? hi : lo;
                         v[e + stride < PER ? e + stride : e] = desc ? lo : hi;
                     }

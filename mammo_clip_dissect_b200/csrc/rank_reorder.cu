@@ -31,15 +31,23 @@ __device__ __forceinline__ float abs_pow(float d, float p) {
 //
 // rank_sorted_warp_kernel<PER>: n <= 32 * PER (PER = 8: n <= 256, PER = 16: n <= 512).  CTA = 8 warps = 8 adjacent
 // concepts of one neuron (the 8 gathers of a probe image share one 32-byte sector); a warp sorts its column in registers.
+// The sorted words are 32 bits wide: the top 24 (23) bits of the ordered cosine and the row r in the low 8 (9) bits -- half
+// the shuffles and a third of the compare instructions of a 64-bit sort.  Cosines that agree in those top bits (about one
+// pair per column for real data) end up adjacent but possibly in the wrong order: such elements are detected after the
+// sort (equal top bits with a neighbour) and their exact position in the full (ordered cosine, r) order is counted
+// directly from the column kept in shared memory.  A constant column degenerates to counting, n^2 / 32 steps.
 template <int PER>
 __global__ void __launch_bounds__(256)
 rank_sorted_warp_kernel(const float *__restrict__ P, int64_t ldp, int C, const int32_t *__restrict__ idx,
                         const float *__restrict__ vals, int64_t K, int n, const float *__restrict__ base_part, float p,
                         float scale_p, float *__restrict__ out, int64_t ldo) {
+    constexpr int RB = PER <= 8 ? 8 : 9;                         // bits of r
+    constexpr uint32_t RMASK = (1u << RB) - 1u;
     extern __shared__ float smem_f[];
     float *t = smem_f;                                           // [n] descending activations of the neuron
     int32_t *rows = reinterpret_cast<int32_t *>(t + n);          // [n] their probe images
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float *xs = t + 2 * n + warp * n;                            // [n] this warp's gathered column
     const int64_t j = blockIdx.y;
     const int c = blockIdx.x * 8 + warp;
     for (int r = threadIdx.x; r < n; r += 256) {
@@ -48,24 +56,60 @@ rank_sorted_warp_kernel(const float *__restrict__ P, int64_t ldp, int C, const i
     }
     __syncthreads();
     if (c >= C) return;
-    unsigned long long key[PER];
+    uint32_t key[PER];
     float sum_x = 0.f;
 #pragma unroll
     for (int e = 0; e < PER; ++e) {
         const int r = lane * PER + e;
-        key[e] = 0ull;                                           // padding sorts last
+        key[e] = 0u;                                             // padding sorts last (no ordered key has zero top bits)
         if (r < n) {
             const float x = P[int64_t(rows[r]) * ldp + c];
             sum_x += x;
-            key[e] = pack_key(ordered_key(x), static_cast<uint32_t>(r));
+            xs[r] = x;
+            key[e] = (ordered_key(x) & ~RMASK) | static_cast<uint32_t>(r);
         }
     }
     bitonic_desc_regs<PER>(key, lane);
-    float acc = 0.f;
+    // neighbours with the same top bits?
+    const uint32_t before = __shfl_up_sync(0xffffffffu, key[PER - 1], 1), after = __shfl_down_sync(0xffffffffu, key[0], 1);
+    bool amb[PER];
+    bool any_amb = false;
 #pragma unroll
     for (int e = 0; e < PER; ++e) {
-        const int q = lane * PER + e;
-        if (q < n) acc += abs_pow(t[static_cast<uint32_t>(key[e])] - t[q], p);
+        const uint32_t top = key[e] >> RB;
+        const uint32_t prev = e > 0 ? key[e > 0 ? e - 1 : 0] : (lane > 0 ? before : ~key[e]);
+        const uint32_t next = e + 1 < PER ? key[e + 1 < PER ? e + 1 : e] : (lane < 31 ? after : ~key[e]);
+        amb[e] = key[e] != 0u && ((prev >> RB) == top || (next >> RB) == top);
+        any_amb |= amb[e];
+    }
+    float acc = 0.f;
+    if (!__any_sync(0xffffffffu, any_amb)) {
+#pragma unroll
+        for (int e = 0; e < PER; ++e) {
+            const int q = lane * PER + e;
+            if (q < n) acc += abs_pow(t[key[e] & RMASK] - t[q], p);
+        }
+    } else {
+        __syncwarp();                                            // xs[] written by other lanes
+#pragma unroll
+        for (int e = 0; e < PER; ++e) {
+            int q = lane * PER + e;
+            unsigned pending = __ballot_sync(0xffffffffu, amb[e]);
+            while (pending) {
+                const int src = __ffs(pending) - 1;
+                pending &= pending - 1;
+                const uint32_t w = __shfl_sync(0xffffffffu, key[e], src);
+                const uint32_t r0 = w & RMASK, top0 = w >> RB, k0 = ordered_key(xs[r0]);
+                int ahead = 0;                                   // elements before (k0, r0) in the descending (key, r) order
+                for (int r = lane; r < n; r += 32) {
+                    const uint32_t k = ordered_key(xs[r]);
+                    ahead += ((k >> RB) > top0) || ((k >> RB) == top0 && (k > k0 || (k == k0 && uint32_t(r) > r0)));
+                }
+                ahead = __reduce_add_sync(0xffffffffu, ahead);
+                if (lane == src) q = ahead;
+            }
+            if (lane * PER + e < n) acc += abs_pow(t[key[e] & RMASK] - t[q], p);
+        }
     }
     sum_x = warp_sum(sum_x);
     acc = warp_sum(acc);
@@ -197,12 +241,67 @@ rank_perm_given_kernel(const float *__restrict__ vals, int64_t K, int n, const i
     if (threadIdx.x == 0) base_part[id] = red[0] + red[1] + red[2] + red[3];
 }
 
+// The generator itself on the device: MT19937 (the engine behind torch's CPU generator) continued from a given state.
+// One CTA; a twist of the 624-word state runs as four data-parallel phases (word i needs the OLD words i, i+1 and the
+// word i+397 mod 624, which is old for i < 227 and already new beyond), then up to 624 tempered outputs are written
+// in parallel.  state_io: 624 words + the position of the next output (624 = "twist first"); left in place for the
+// host to put back into the generator.  ~0.2 us per 624 draws: 640 k draws (c5) in 0.2 ms instead of 2.5 ms of numpy
+// plus a host-to-device copy.
+constexpr int kMtN = 624, kMtM = 397, kMtThreads = 256;
+
+__global__ void __launch_bounds__(kMtThreads)
+mt19937_draws_kernel(uint32_t *__restrict__ state_io, int64_t count, uint32_t *__restrict__ draws) {
+    __shared__ uint32_t mt[kMtN];
+    __shared__ int pos_s;
+    for (int i = threadIdx.x; i < kMtN; i += kMtThreads) mt[i] = state_io[i];
+    if (threadIdx.x == 0) pos_s = static_cast<int>(state_io[kMtN]);
+    __syncthreads();
+    int pos = pos_s;
+    auto mix = [](uint32_t cur, uint32_t next, uint32_t far) {
+        const uint32_t y = (cur & 0x80000000u) | (next & 0x7FFFFFFFu);
+        return far ^ (y >> 1) ^ ((y & 1u) ? 0x9908B0DFu : 0u);
+    };
+    int64_t done = 0;
+    while (done < count) {
+        if (pos >= kMtN) {
+            // phases [0,227) [227,454) [454,623) {623}: read, barrier, write, barrier
+            const int lo[4] = {0, kMtN - kMtM, 2 * (kMtN - kMtM), kMtN - 1}, hi[4] = {kMtN - kMtM, 2 * (kMtN - kMtM), kMtN - 1, kMtN};
+#pragma unroll
+            for (int ph = 0; ph < 4; ++ph) {
+                const int i = lo[ph] + threadIdx.x;
+                uint32_t v = 0u;
+                const bool on = i < hi[ph];
+                if (on) v = mix(mt[i], mt[(i + 1) % kMtN], mt[(i + kMtM) % kMtN]);
+                __syncthreads();
+                if (on) mt[i] = v;
+                __syncthreads();
+            }
+            pos = 0;
+        }
+        const int64_t left = count - done;
+        const int take = static_cast<int>(left < int64_t(kMtN - pos) ? left : int64_t(kMtN - pos));
+        for (int t = threadIdx.x; t < take; t += kMtThreads) {
+            uint32_t y = mt[pos + t];
+            y ^= y >> 11;
+            y ^= (y << 7) & 0x9D2C5680u;
+            y ^= (y << 15) & 0xEFC60000u;
+            y ^= y >> 18;
+            draws[done + t] = y;
+        }
+        pos += take;
+        done += take;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kMtN; i += kMtThreads) state_io[i] = mt[i];
+    if (threadIdx.x == 0) state_io[kMtN] = static_cast<uint32_t>(pos);
+}
+
 static int launch_rank_sorted(const float *P, int64_t ldp, int64_t C, const int32_t *idx, const float *vals, int64_t K,
                               int64_t n, const float *base_part, float p, float scale_p, float *out, int64_t ldo,
                               cudaStream_t st) {
     if (n <= 512) {
         dim3 grid(static_cast<unsigned>(ceil_div<int64_t>(C, 8)), static_cast<unsigned>(K));
-        const size_t smem = size_t(n) * 8;
+        const size_t smem = size_t(n) * 8 + size_t(n) * 8 * 4;       // t, rows, and a column per warp
         if (n <= 256)
             rank_sorted_warp_kernel<8><<<grid, 256, smem, st>>>(P, ldp, int(C), idx, vals, K, int(n), base_part, p, scale_p, out, ldo);
         else
@@ -237,6 +336,13 @@ extern "C" int mcd_rank_reorder_f32(const float *P, int64_t ldp, int64_t N, int6
     int rc = check_launch();
     if (rc != MCD_OK) return rc;
     return launch_rank_sorted(P, ldp, C, idx, vals, K, top_n, baseline_ws, p, scale_p, out, ldo, st);
+}
+
+extern "C" int mcd_mt19937_draws(uint32_t *state_io, int64_t count, uint32_t *draws, mcd_stream_t stream) {
+    using namespace mcd;
+    if (!state_io || !draws || count < 1) return MCD_ERR_INVALID_ARGUMENT;
+    mt19937_draws_kernel<<<1, kMtThreads, 0, static_cast<cudaStream_t>(stream)>>>(state_io, count, draws);
+    return check_launch();
 }
 
 extern "C" size_t mcd_rank_reorder_workspace_bytes(int64_t K, int64_t top_n) {

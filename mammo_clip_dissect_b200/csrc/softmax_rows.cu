@@ -13,7 +13,7 @@ namespace mcd {
 
 constexpr int kSoftmaxWarps = 8;
 
-template <int PER>   // register-resident rows up to 32*PER columns
+template <int PER, int kFull>   // register-resident rows up to 32*PER columns; the first 32*kFull exist in every row
 __global__ void __launch_bounds__(kSoftmaxWarps * 32)
 softmax_rows_kernel(const float *__restrict__ P, int64_t ldp, float *__restrict__ S, int64_t lds, int64_t n_rows,
                     int n_cols, float a) {
@@ -24,26 +24,47 @@ softmax_rows_kernel(const float *__restrict__ P, int64_t ldp, float *__restrict_
     float *dst = S + row * lds;
     float x[PER];
     float m = -INFINITY;
+    // columns below 32 * kFull exist in every row (the dispatcher guarantees n_cols > 32 * kFull): only the last
+    // register slots carry a bounds check
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
         const int c = lane + 32 * i;
-        x[i] = c < n_cols ? __fmul_rn(a, __ldg(src + c)) : -INFINITY;
+        x[i] = (i < kFull || c < n_cols) ? __fmul_rn(a, __ldg(src + c)) : -INFINITY;
         m = fmaxf(m, x[i]);
     }
     m = warp_max(m);
-    float sum = 0.f;
+    float sum = 0.f, low = 1.f;
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
         const int c = lane + 32 * i;
-        x[i] = c < n_cols ? expf(__fsub_rn(x[i], m)) : 0.f;
+        const bool have = i < kFull || c < n_cols;
+        x[i] = have ? expf(__fsub_rn(x[i], m)) : 0.f;
+        low = fminf(low, have ? x[i] : 1.f);
         sum += x[i];
     }
     sum = warp_sum(sum);
+    // x / sum, correctly rounded, from the shared reciprocal: q0 = x * r, rem = x - q0 * sum (exact in one FMA),
+    // q = q0 + rem * r (Markstein).  It equals the IEEE quotient whenever r = RN(1 / sum) is good enough, which fails only
+    // for divisors with an all-ones mantissa and for quotients near the denormal range: such rows (a warp-uniform
+    // decision) take the division instruction sequence.
+    const float r = __frcp_rn(sum);
+    const bool plain_div = __any_sync(0xFFFFFFFFu, !(low >= 1e-30f)) || (__float_as_uint(sum) & 0x7FFFFFu) == 0x7FFFFFu ||
+                           !(sum < 3.0e38f) || !(m > -3.0e38f);
+    if (plain_div) {
 #pragma unroll
-    for (int i = 0; i < PER; ++i) {
-        const int c = lane + 32 * i;
-        if (c < n_cols) dst[c] = __fdiv_rn(x[i], sum);
-        else if (c < lds) dst[c] = 0.f;
+        for (int i = 0; i < PER; ++i) {
+            const int c = lane + 32 * i;
+            if (i < kFull || c < n_cols) dst[c] = __fdiv_rn(x[i], sum);
+            else if (c < lds) dst[c] = 0.f;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < PER; ++i) {
+            const int c = lane + 32 * i;
+            const float q0 = __fmul_rn(x[i], r);
+            if (i < kFull || c < n_cols) dst[c] = __fmaf_rn(__fmaf_rn(-q0, sum, x[i]), r, q0);
+            else if (c < lds) dst[c] = 0.f;
+        }
     }
     for (int c = 32 * PER + lane; c < lds; c += 32) dst[c] = 0.f;
 }
@@ -83,11 +104,13 @@ extern "C" int mcd_softmax_rows_f32(const float *P, int64_t ldp, float *S, int64
     const int threads = kSoftmaxWarps * 32;
     const int nc = static_cast<int>(n_cols);
     if (n_cols <= 32 * 4)
-        softmax_rows_kernel<4><<<grid, threads, 0, st>>>(P, ldp, S, lds, n_rows, nc, a);
-    else if (n_cols <= 32 * 24)
-        softmax_rows_kernel<24><<<grid, threads, 0, st>>>(P, ldp, S, lds, n_rows, nc, a);
+        softmax_rows_kernel<4, 0><<<grid, threads, 0, st>>>(P, ldp, S, lds, n_rows, nc, a);
+    else if (n_cols <= 32 * 22)
+        softmax_rows_kernel<24, 0><<<grid, threads, 0, st>>>(P, ldp, S, lds, n_rows, nc, a);
+    else if (n_cols <= 32 * 24)          // the 763-concept set: 22 full register slots, bounds checks on the last two
+        softmax_rows_kernel<24, 22><<<grid, threads, 0, st>>>(P, ldp, S, lds, n_rows, nc, a);
     else if (n_cols <= 32 * 64)
-        softmax_rows_kernel<64><<<grid, threads, 0, st>>>(P, ldp, S, lds, n_rows, nc, a);
+        softmax_rows_kernel<64, 0><<<grid, threads, 0, st>>>(P, ldp, S, lds, n_rows, nc, a);
     else
         softmax_rows_wide_kernel<<<grid, threads, 0, st>>>(P, ldp, S, lds, n_rows, n_cols, a);
     return check_launch();

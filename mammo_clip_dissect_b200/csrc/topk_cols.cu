@@ -508,6 +508,47 @@ sample_select_kernel(const uint32_t *__restrict__ tilemax, int ntiles, int64_t K
     tau[col] = key_to_threshold(low);      // NaN (admit everything) if fewer than j tiles or the j-th largest is NaN
 }
 
+// The same for up to 128 sampled tiles (every shape the plans produce up to N = 131072 rows): a CTA takes 32 adjacent
+// columns -- the tile maxima come in as coalesced 128-byte rows through shared memory -- and each warp then serves 4 of
+// them: a lane holds 4 tile maxima of the column, and the j-th largest key is built bit by bit -- the largest v with
+// #{keys >= v} >= j -- with one warp-wide integer reduction per bit (32 x ~8 instructions instead of a serial scan of a
+// j-entry buffer per key).
+constexpr int kSelectWarps = 8, kSelectWarpTiles = 128, kSelectCtaCols = 32;
+
+__global__ void __launch_bounds__(kSelectWarps * 32)
+sample_select_warp_kernel(const uint32_t *__restrict__ tilemax, int ntiles, int64_t K, int j, float *__restrict__ tau) {
+    __shared__ uint32_t keys[kSelectCtaCols][kSelectWarpTiles + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t col0 = int64_t(blockIdx.x) * kSelectCtaCols;
+    for (int t = warp; t < kSelectWarpTiles; t += kSelectWarps)
+        keys[lane][t] = (t < ntiles && col0 + lane < K) ? tilemax[int64_t(t) * K + col0 + lane] : 0u;
+    __syncthreads();
+    for (int cc = warp; cc < kSelectCtaCols; cc += kSelectWarps) {
+        if (col0 + cc >= K) break;
+        uint32_t key[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) key[e] = keys[cc][lane + 32 * e];
+        uint32_t v = 0u;
+#pragma unroll 4
+        for (int bit = 31; bit >= 0; --bit) {
+            const uint32_t cand = v | (1u << bit);
+            const int mine = int(key[0] >= cand) + int(key[1] >= cand) + int(key[2] >= cand) + int(key[3] >= cand);
+            if (__reduce_add_sync(0xFFFFFFFFu, mine) >= j) v = cand;
+        }
+        if (lane == 0) tau[col0 + cc] = key_to_threshold(v);      // v == 0: fewer than j tiles -> NaN (admit everything)
+    }
+}
+
+static int launch_sample_select(const uint32_t *tilemax, int ntiles, int64_t K, int j, float *tau, cudaStream_t st) {
+    if (ntiles <= kSelectWarpTiles)
+        sample_select_warp_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(K, kSelectCtaCols)), kSelectWarps * 32, 0, st>>>(
+            tilemax, ntiles, K, j, tau);
+    else
+        sample_select_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(K, kSelectThreads)), kSelectThreads, 0, st>>>(
+            tilemax, ntiles, K, j, tau);
+    return check_launch();
+}
+
 // One warp per column: sort the splits*k candidates (descending 64-bit words) and emit the top k.
 constexpr int kFinishWarps = 4;
 
@@ -1087,9 +1128,7 @@ int topk_filter_begin(const TopkFilterCall &c, cudaStream_t st) {
     sample_tilemax_kernel<<<sgrid, kSampleThreads, 0, st>>>(c.A, c.lda, c.K, int64_t(kSampleRows) * p.pre_stride, 1, c.tilemax);
     int rc = check_launch();
     if (rc != MCD_OK) return rc;
-    sample_select_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(c.K, kSelectThreads)), kSelectThreads, 0, st>>>(
-        c.tilemax, nsample, c.K, p.pre_k, c.tau);
-    return check_launch();
+    return launch_sample_select(c.tilemax, nsample, c.K, p.pre_k, c.tau, st);
 }
 
 int topk_filter_scan(const TopkFilterCall &c, int64_t col0, int64_t col1, int launch_id, cudaStream_t st) {
@@ -1254,9 +1293,7 @@ extern "C" int mcd_topk_cols_f32(const float *A, int64_t lda, int64_t N, int64_t
             sample_tilemax_kernel<<<sgrid, kSampleThreads, 0, st>>>(A, lda, K, int64_t(kSampleRows) * p.pre_stride, 1, tilemax);
             rc = check_launch();
             if (rc != MCD_OK) return rc;
-            sample_select_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(K, kSelectThreads)), kSelectThreads, 0, st>>>(
-                tilemax, nsample, K, p.pre_k, tau);
-            rc = check_launch();
+            rc = launch_sample_select(tilemax, nsample, K, p.pre_k, tau, st);
             if (rc != MCD_OK) return rc;
             main_args.tau0 = tau;
             main_args.flags = flags;

@@ -646,6 +646,36 @@ def _replay_works():
     return _replay_ok
 
 
+_device_replay_ok = {}
+
+
+def _device_replay_works(dev):
+    """One-time self-check per device: the MT19937 kernel continues a (non-fresh) generator state exactly like the host
+    replay -- same raw draws across several twists, same final state."""
+    import numpy as np
+    key_ = (dev.type, dev.index)
+    if key_ not in _device_replay_ok:
+        try:
+            lib = _lib.lib()
+            g = torch.Generator().manual_seed(20240229)
+            torch.randn(7, generator=g)
+            state = g.get_state()
+            key, pos = _mt_state_to_numpy(state)
+            count = 3 * _MT_N + 101
+            st_dev = torch.from_numpy(np.append(key, np.uint32(pos)).view(np.int32)).to(dev)
+            draws = torch.empty((count,), dtype=torch.int32, device=dev)
+            _lib.check(lib.mcd_mt19937_draws(_ptr(st_dev), count, _ptr(draws), _stream(dev)), "mcd_mt19937_draws")
+            want = _raw_draws(count, g)
+            after_key, after_pos = _mt_state_to_numpy(g.get_state())
+            got_state = st_dev.cpu().numpy().view(np.uint32)
+            ok = np.array_equal(draws.cpu().numpy().view(np.uint32), want)
+            ok = ok and np.array_equal(got_state[:_MT_N], after_key) and int(got_state[_MT_N]) == int(after_pos)
+            _device_replay_ok[key_] = bool(ok)
+        except Exception:
+            _device_replay_ok[key_] = False
+    return _device_replay_ok[key_]
+
+
 def rank_reorder(clip_feats, target_feats, device="cuda", p=3, top_fraction=0.05, scale_p=0.5, top_k=None):
     """Reference similarity.py:99-132 on the GPU.  The reference draws 5 x torch.randperm(top_n) per neuron from the
     GLOBAL CPU generator (in neuron order); the same stream is consumed here (see _raw_draws above), so under the same
@@ -670,11 +700,33 @@ def rank_reorder(clip_feats, target_feats, device="cuda", p=3, top_fraction=0.05
         (vals, _), idx32 = topk_cols(A, top_n, dev, want_values=True, want_int32=True)
         out = torch.empty((K, C), dtype=torch.float32, device=dev)
         if top_n > 1 and _replay_works():
-            draws = torch.from_numpy(_raw_draws(K * 5 * (top_n - 1)).view(np.int32)).to(dev)
+            count = K * 5 * (top_n - 1)
             ws = _workspace(int(lib.mcd_rank_reorder_workspace_bytes(K, top_n)), dev)
+            pending = None
+            if _device_replay_works(dev):
+                # the generator continues on the device (MT19937 kernel); its final state comes back while the scoring
+                # kernels are being enqueued and is put into the CPU generator before this function returns
+                gen = torch.default_generator
+                state = gen.get_state()
+                key, pos = _mt_state_to_numpy(state)
+                st_dev = torch.from_numpy(np.append(key, np.uint32(pos)).view(np.int32)).to(dev)
+                draws = torch.empty((count,), dtype=torch.int32, device=dev)
+                _lib.check(lib.mcd_mt19937_draws(_ptr(st_dev), count, _ptr(draws), _stream(dev)), "mcd_mt19937_draws")
+                back = torch.empty((_MT_N + 1,), dtype=torch.int32, pin_memory=True)
+                back.copy_(st_dev, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record()
+                pending = (gen, state, back, done)
+            else:
+                draws = torch.from_numpy(_raw_draws(count).view(np.int32)).to(dev)
             _lib.check(lib.mcd_rank_reorder_draws_f32(_ptr(P), _ld(P), N, C, _ptr(idx32), _ptr(vals), K, top_n, _ptr(draws),
                                                       float(p), float(scale_p), _ptr(ws), ws.numel(), _ptr(out), _ld(out),
                                                       _stream(dev)), "mcd_rank_reorder_draws_f32")
+            if pending is not None:
+                gen, state, back, done = pending
+                done.synchronize()
+                words = back.numpy().view(np.uint32)
+                gen.set_state(_mt_state_from_numpy(state, words[:_MT_N], int(words[_MT_N])))
             return out
         # the reference's RNG stream call by call: for every neuron, five permutations of range(top_n)
         perms = torch.stack([torch.stack([torch.randperm(top_n) for _ in range(5)]) for _ in range(K)]).to(torch.int32)

@@ -234,6 +234,13 @@ def test_topk_filter_form(sim, kind, N, K, k):
         _lib.set_tunable("topk_filter", 0)
 
 
+@pytest.mark.parametrize("kind", ["randn", "mixed"])
+def test_topk_filter_form_beyond_128_sampled_tiles(sim, kind):
+    """N = 140 000 rows give 136 sampled tiles: the thread-per-column threshold select (the warp-per-column one holds 128)."""
+    A = _filter_case(kind, 140000, 36, seed=9)
+    assert torch.equal(sim.topk_cols(A, 100, device=DEV).cpu(), orc.topk_cols(A, 100)[1])
+
+
 @pytest.mark.parametrize("stages,chunk_tiles", [(2, 1), (3, 1000000), (4, 7)])
 def test_topk_filter_ring_and_item_shapes(sim, stages, chunk_tiles):
     from mammo_clip_dissect_b200 import _lib
@@ -963,31 +970,79 @@ def test_rank_reorder_golden(sim, golden):
                                        (12000, 41, 9, {}),                          # top_n = 600: shared-memory sort; K2 by radix select
                                        (100000, 33, 5, {}),                         # the c4 probe count: top_n = 5000
                                        (40, 7, 3, {})])                             # top_n = 2
-@pytest.mark.parametrize("replay", ["raw_draws", "randperm_calls"])
+@pytest.mark.parametrize("replay", ["device_mt", "raw_draws", "randperm_calls"])
 def test_rank_reorder_vs_oracle(sim, N, C, K, kw, replay):
-    """The reference's RNG stream is consumed either as raw generator outputs (shuffles on the device) or call by call;
-    both match the oracle under the same seed and leave the global generator in the oracle's state."""
-    if replay == "randperm_calls" and N > 12000:
-        pytest.skip("the call-by-call replay is the fallback; covered at the smaller sizes")
+    """The reference's RNG stream is consumed by continuing MT19937 on the device, as raw generator outputs produced on
+    the host (shuffles on the device in both cases), or call by call; all match the oracle under the same seed and leave
+    the global generator in the oracle's state."""
+    if replay != "device_mt" and N > 12000:
+        pytest.skip("the host replays are fallbacks; covered at the smaller sizes")
     P = torch.randn(N, C, generator=gen(N)) * 0.05 + 0.04          # mixed-sign means: some concepts give NaN
     P[::3][: P[1::3].shape[0]] = P[1::3]                           # duplicated rows: equal cosines -> ties in the ranks
     A = torch.randn(N, K, generator=gen(K))
-    saved = sim._replay_ok
+    saved, saved_dev = sim._replay_ok, dict(sim._device_replay_ok)
     try:
+        assert sim._replay_works() and sim._device_replay_works(torch.device(DEV))
         if replay == "randperm_calls":
             sim._replay_ok = False
-        else:
-            assert sim._replay_works()
+        elif replay == "raw_draws":
+            for k_ in list(sim._device_replay_ok):
+                sim._device_replay_ok[k_] = False
         torch.manual_seed(123)
         got = sim.rank_reorder(P, A, device=DEV, **kw).cpu()
         tail = torch.rand(4)
     finally:
         sim._replay_ok = saved
+        sim._device_replay_ok.update(saved_dev)
     torch.manual_seed(123)
     ref = orc.rank_reorder(P, A, **kw)
     assert torch.equal(tail, torch.rand(4))                        # same generator state afterwards
     assert got.shape == ref.shape == (K, C)
     assert _same_with_nan(got, ref, 5e-5)
+
+
+@pytest.mark.parametrize("N,K", [(5000, 12), (9000, 7)])
+@pytest.mark.parametrize("kind", ["crowded", "constant", "two_values"])
+def test_rank_reorder_cosines_that_agree_in_their_leading_bits(sim, N, K, kind):
+    """The register sort orders by the leading 24 (23) bits of the cosine; elements that agree there are placed by an exact
+    count.  Crowded columns (thousands of cosines within 4096 ulps), constant columns and two-valued columns must rank
+    exactly like the oracle's stable argsort."""
+    C = 19
+    g = gen(N + K)
+    if kind == "crowded":
+        P = 0.25 + torch.randint(0, 4096, (N, C), generator=g).float() * 2.0 ** -25
+        P[:, 1] = -P[:, 1]                                         # negative cosines: reversed key order, NaN output
+    elif kind == "constant":
+        P = torch.full((N, C), 0.125)
+    else:
+        P = torch.where(torch.rand(N, C, generator=g) < 0.5, torch.tensor(0.3), torch.tensor(0.3000001))
+    A = torch.randn(N, K, generator=g)
+    torch.manual_seed(5)
+    got = sim.rank_reorder(P, A, device=DEV).cpu()
+    torch.manual_seed(5)
+    ref = orc.rank_reorder(P, A)
+    assert _same_with_nan(got, ref, 5e-5)
+
+
+def test_mt19937_on_the_device_continues_the_cpu_generator(sim):
+    """mcd_mt19937_draws against numpy's MT19937 started from the same torch generator state: a million draws from a
+    mid-block position, and a start exactly at a block boundary."""
+    import numpy as np
+    from mammo_clip_dissect_b200 import _lib
+    lib = _lib.lib()
+    for warm, count in ((7, 1_000_003), (0, 624), (312, 5)):
+        g = torch.Generator().manual_seed(77 + warm)
+        if warm:
+            torch.randint(0, 10, (warm,), generator=g)
+        key, pos = sim._mt_state_to_numpy(g.get_state())
+        st = torch.from_numpy(np.append(key, np.uint32(pos)).view(np.int32)).to(DEV)
+        draws = torch.empty((count,), dtype=torch.int32, device=DEV)
+        assert lib.mcd_mt19937_draws(st.data_ptr(), count, draws.data_ptr(), None) == 0
+        want = sim._raw_draws(count, g)
+        key2, pos2 = sim._mt_state_to_numpy(g.get_state())
+        assert np.array_equal(draws.cpu().numpy().view(np.uint32), want)
+        got = st.cpu().numpy().view(np.uint32)
+        assert np.array_equal(got[:624], key2) and int(got[624]) == int(pos2)
 
 
 @pytest.mark.parametrize("K", [24, 176, 512])

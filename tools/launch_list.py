@@ -11,7 +11,7 @@ import sys
 ROLES = [
     ("softmax_rows_kernel", "K1b softmax(a*P) rows"),
     ("sample_tilemax_kernel", "K2 sample: per-column maxima of 1 tile in 32"),
-    ("sample_select_kernel", "K2 sample: j-th largest tile maximum = start threshold"),
+    ("sample_select", "K2 sample: j-th largest tile maximum = start threshold"),
     ("filter_scan_kernel", "K2 filter scan: stream A once, append elements above the column threshold"),
     ("filter_tail_rows_kernel", "K2 filter: the last N % 8 rows"),
     ("topk_select_kernel", "K2 select: exact top k of every survivor list, sorted, indices out"),
