@@ -216,19 +216,32 @@ int mcd_last_cos_path(void);
 /* ---- rank_reorder (similarity.py:99-132).  idx / vals [top_n, K] from mcd_topk_cols_f32 (top_n = int(0.05 N) <= 8192).
  *      out[j,c] = -(mean_r |t_r - asc[rank_rc]|^p / baseline_j) / (mean_r P[idx_r, c])^scale_p, ranks by sorting
  *      (registers for top_n <= 512, shared memory beyond), ties among the gathered cosines by row position.
- *      baseline_j: the reference's 5 x torch.randperm(top_n) per neuron from the global CPU generator, either as
- *        mcd_rank_reorder_f32        perms [K, 5, top_n] int32 drawn on the host, baseline_ws [5 K] floats of scratch;
- *        mcd_rank_reorder_draws_f32  draws [K, 5, top_n - 1] uint32: the generator's raw 32-bit outputs (torch.randperm
- *                                    = Fisher-Yates with z = draw % (n - i)); the shuffles run on the device. */
+ *      Three steps sharing one workspace (mcd_rank_reorder_workspace_bytes), so that the baseline -- which needs the
+ *      reference's random permutations -- can be produced on another stream while the ranks are being computed:
+ *        mcd_rank_baseline_draws_f32 / _perms_f32   baseline_j = mean over the reference's 5 x torch.randperm(top_n) per
+ *              neuron (similarity.py:119) of |asc_r - asc_perm(r)|^p, from draws [K, 5, top_n - 1] uint32 = the CPU
+ *              generator's raw 32-bit outputs (torch.randperm = Fisher-Yates with z = draw % (n - i); shuffles on the
+ *              device), or from perms [K, 5, top_n] int32 drawn on the host;
+ *        mcd_rank_errors_f32    the gather + rank pass: leaves mean_r |.|^p in out and (mean cosine)^scale_p in the workspace;
+ *        mcd_rank_finish_f32    out = -((e / baseline) / den), the reference's operation order (similarity.py:126-129).
+ *      mcd_rank_reorder_f32 / mcd_rank_reorder_draws_f32 run the three on one stream.
+ *      mcd_mt19937_draws produces the raw draws themselves: it continues MT19937 (the engine of torch's CPU generator) on
+ *      the device.  state_io: 624 state words + 1 word "index of the next output" (624 = twist before the next draw); on
+ *      return it holds the state after `count` outputs, for the host to write back into the generator. */
+size_t mcd_rank_reorder_workspace_bytes(int64_t K, int64_t top_n, int64_t C);
+int mcd_mt19937_draws(uint32_t *state_io, int64_t count, uint32_t *draws, mcd_stream_t stream);
+int mcd_rank_baseline_draws_f32(const float *vals, int64_t K, int64_t top_n, int64_t C, const uint32_t *draws, float p,
+                                void *workspace, size_t workspace_bytes, mcd_stream_t stream);
+int mcd_rank_baseline_perms_f32(const float *vals, int64_t K, int64_t top_n, int64_t C, const int32_t *perms, float p,
+                                void *workspace, size_t workspace_bytes, mcd_stream_t stream);
+int mcd_rank_errors_f32(const float *P, int64_t ldp, int64_t N, int64_t C, const int32_t *idx, const float *vals,
+                        int64_t K, int64_t top_n, float p, float scale_p, void *workspace, size_t workspace_bytes,
+                        float *out, int64_t ldo, mcd_stream_t stream);
+int mcd_rank_finish_f32(int64_t K, int64_t C, int64_t top_n, void *workspace, size_t workspace_bytes, float *out,
+                        int64_t ldo, mcd_stream_t stream);
 int mcd_rank_reorder_f32(const float *P, int64_t ldp, int64_t N, int64_t C, const int32_t *idx, const float *vals,
                          int64_t K, int64_t top_n, const int32_t *perms, float p, float scale_p,
-                         float *baseline_ws, float *out, int64_t ldo, mcd_stream_t stream);
-size_t mcd_rank_reorder_workspace_bytes(int64_t K, int64_t top_n);
-/* The raw draws themselves: continues MT19937 (torch's CPU generator engine, ATen/core/MersenneTwister.h as used by
- * torch.randperm in similarity.py:119) on the device.  state_io: 624 state words + 1 word "index of the next output"
- * (624 = twist before the next draw); on return it holds the state after `count` outputs, for the host to write back
- * into the generator.  draws [count] uint32. */
-int mcd_mt19937_draws(uint32_t *state_io, int64_t count, uint32_t *draws, mcd_stream_t stream);
+                         void *workspace, size_t workspace_bytes, float *out, int64_t ldo, mcd_stream_t stream);
 int mcd_rank_reorder_draws_f32(const float *P, int64_t ldp, int64_t N, int64_t C, const int32_t *idx, const float *vals,
                                int64_t K, int64_t top_n, const uint32_t *draws, float p, float scale_p,
                                void *workspace, size_t workspace_bytes, float *out, int64_t ldo, mcd_stream_t stream);

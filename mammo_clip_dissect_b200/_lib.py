@@ -50,11 +50,15 @@ SIGNATURES = {
     "mcd_pool_nchw": (_i32, [_p, _i32, _i64, _i64, _i64, _i64, _i32, _p, _p, _sz, _p]),
     "mcd_pool_nchw_to": (_i32, [_p, _i32, _i64, _i64, _i64, _i64, _i32, _i32, _p, _i32, _i64, _p, _sz, _p]),
     "mcd_col_stats_f32": (_i32, [_p, _i64, _i64, _i64, _i32, _f32, _p, _p, _p]),
-    "mcd_rank_reorder_f32": (_i32, [_p, _i64, _i64, _i64, _p, _p, _i64, _i64, _p, _f32, _f32, _p, _p, _i64, _p]),
+    "mcd_rank_reorder_f32": (_i32, [_p, _i64, _i64, _i64, _p, _p, _i64, _i64, _p, _f32, _f32, _p, _sz, _p, _i64, _p]),
+    "mcd_rank_baseline_draws_f32": (_i32, [_p, _i64, _i64, _i64, _p, _f32, _p, _sz, _p]),
+    "mcd_rank_baseline_perms_f32": (_i32, [_p, _i64, _i64, _i64, _p, _f32, _p, _sz, _p]),
+    "mcd_rank_errors_f32": (_i32, [_p, _i64, _i64, _i64, _p, _p, _i64, _i64, _f32, _f32, _p, _sz, _p, _i64, _p]),
+    "mcd_rank_finish_f32": (_i32, [_i64, _i64, _i64, _p, _sz, _p, _i64, _p]),
     "mcd_cos_similarity_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "mcd_cos_similarity_f32": (_i32, [_p, _i64, _p, _i64, _i64, _i64, _i64, _i32, _f32, _p, _i64, _p, _sz, _p]),
     "mcd_last_cos_path": (_i32, []),
-    "mcd_rank_reorder_workspace_bytes": (_sz, [_i64, _i64]),
+    "mcd_rank_reorder_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "mcd_mt19937_draws": (_i32, [_p, _i64, _p, _p]),
     "mcd_rank_reorder_draws_f32": (_i32, [_p, _i64, _i64, _i64, _p, _p, _i64, _i64, _p, _f32, _f32, _p, _sz, _p, _i64, _p]),
     "mcd_cos_matmul_f32": (_i32, [_p, _i64, _p, _p, _p, _i64, _p, _p, _i64, _i64, _i64, _i32, _p, _i64, _p]),

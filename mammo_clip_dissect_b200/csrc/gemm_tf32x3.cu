@@ -94,6 +94,19 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// the load alone (asynchronous until tmem_ld_wait): several can be in flight
+__device__ __forceinline__ void tmem_ld_32x32_issue(uint32_t taddr, uint32_t *r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, float *v) {
     uint32_t r[32];
     asm volatile(
@@ -188,12 +201,26 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
 #pragma unroll 1
         for (int c = 0; c < kBN; c += 32) {
             float v[32];
-            tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(c), v);
-            for (int sgm = 1; sgm < nseg; ++sgm) {
-                float w[32];
-                tmem_ld_32x32(tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(sgm * kBN + c), w);
+            const uint32_t t0 = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(c);
+            if (nseg == kAccSegs) {          // all four accumulators of this column chunk in flight, one wait
+                uint32_t r[kAccSegs][32];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = __fadd_rn(v[i], w[i]);
+                for (int sgm = 0; sgm < kAccSegs; ++sgm) tmem_ld_32x32_issue(t0 + uint32_t(sgm * kBN), r[sgm]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    v[i] = __uint_as_float(r[0][i]);
+#pragma unroll
+                    for (int sgm = 1; sgm < kAccSegs; ++sgm) v[i] = __fadd_rn(v[i], __uint_as_float(r[sgm][i]));
+                }
+            } else {
+                tmem_ld_32x32(t0, v);
+                for (int sgm = 1; sgm < nseg; ++sgm) {
+                    float w[32];
+                    tmem_ld_32x32(t0 + uint32_t(sgm * kBN), w);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __fadd_rn(v[i], w[i]);
+                }
             }
             if (row < M) {
                 float *dst = P + row * ldp + col0 + c;

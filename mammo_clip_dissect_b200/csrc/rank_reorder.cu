@@ -39,7 +39,7 @@ __device__ __forceinline__ float abs_pow(float d, float p) {
 template <int PER>
 __global__ void __launch_bounds__(256)
 rank_sorted_warp_kernel(const float *__restrict__ P, int64_t ldp, int C, const int32_t *__restrict__ idx,
-                        const float *__restrict__ vals, int64_t K, int n, const float *__restrict__ base_part, float p,
+                        const float *__restrict__ vals, int64_t K, int n, float *__restrict__ den_out, float p,
                         float scale_p, float *__restrict__ out, int64_t ldo) {
     constexpr int RB = PER <= 8 ? 8 : 9;                         // bits of r
     constexpr uint32_t RMASK = (1u << RB) - 1u;
@@ -113,14 +113,10 @@ rank_sorted_warp_kernel(const float *__restrict__ P, int64_t ldp, int C, const i
     }
     sum_x = warp_sum(sum_x);
     acc = warp_sum(acc);
-    if (lane == 0) {
-        float base = 0.f;
-        for (int s5 = 0; s5 < 5; ++s5) base += base_part[j * 5 + s5];
-        base /= 5.f * static_cast<float>(n);
+    if (lane == 0) {     // the neuron's baseline is applied by rank_normalize_kernel (it may still be in the making)
         const float avg = sum_x / static_cast<float>(n);
-        const float err = (acc / static_cast<float>(n)) / base;
-        const float den = scale_p == 0.5f ? sqrtf(avg) : powf(avg, scale_p);
-        out[j * ldo + c] = -(err / den);
+        out[j * ldo + c] = acc / static_cast<float>(n);
+        den_out[j * C + c] = scale_p == 0.5f ? sqrtf(avg) : powf(avg, scale_p);
     }
 }
 
@@ -131,7 +127,7 @@ constexpr int kRankMaxSort = 8192;
 __global__ void __launch_bounds__(256)
 rank_sorted_cta_kernel(const float *__restrict__ P, int64_t ldp, int C, const int32_t *__restrict__ idx,
                        const float *__restrict__ vals, int64_t K, int n, int npad, int cpb,
-                       const float *__restrict__ base_part, float p, float scale_p, float *__restrict__ out, int64_t ldo) {
+                       float *__restrict__ den_out, float p, float scale_p, float *__restrict__ out, int64_t ldo) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     unsigned long long *key = reinterpret_cast<unsigned long long *>(smem_raw);     // [npad]
     float *t = reinterpret_cast<float *>(key + npad);                                // [n]
@@ -142,9 +138,6 @@ rank_sorted_cta_kernel(const float *__restrict__ P, int64_t ldp, int C, const in
         t[r] = vals[int64_t(r) * K + j];
         rows[r] = idx[int64_t(r) * K + j];
     }
-    float base = 0.f;
-    for (int s5 = 0; s5 < 5; ++s5) base += base_part[j * 5 + s5];
-    base /= 5.f * static_cast<float>(n);
     __syncthreads();
     for (int cc = 0; cc < cpb; ++cc) {
         const int c = blockIdx.x * cpb + cc;
@@ -189,9 +182,8 @@ rank_sorted_cta_kernel(const float *__restrict__ P, int64_t ldp, int C, const in
                 se += red[1][w];
             }
             const float avg = sx / static_cast<float>(n);
-            const float err = (se / static_cast<float>(n)) / base;
-            const float den = scale_p == 0.5f ? sqrtf(avg) : powf(avg, scale_p);
-            out[j * ldo + c] = -(err / den);
+            out[j * ldo + c] = se / static_cast<float>(n);
+            den_out[j * C + c] = scale_p == 0.5f ? sqrtf(avg) : powf(avg, scale_p);
         }
         __syncthreads();
     }
@@ -296,16 +288,30 @@ mt19937_draws_kernel(uint32_t *__restrict__ state_io, int64_t count, uint32_t *_
     if (threadIdx.x == 0) state_io[kMtN] = static_cast<uint32_t>(pos);
 }
 
+// out[j,c] = -((e / baseline_j) / den), e = mean_q |.|^p and den = (mean cosine)^scale_p left by the rank kernels: the
+// reference's operation order (similarity.py:126-129), applied once the baseline kernel has delivered.
+__global__ void __launch_bounds__(256)
+rank_normalize_kernel(const float *__restrict__ base_part, const float *__restrict__ den, int C, int n, float *__restrict__ out,
+                      int64_t ldo) {
+    const int64_t j = blockIdx.y;
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c >= C) return;
+    float base = 0.f;
+    for (int s5 = 0; s5 < 5; ++s5) base += base_part[j * 5 + s5];
+    base /= 5.f * static_cast<float>(n);
+    const float err = out[j * ldo + c] / base;
+    out[j * ldo + c] = -(err / den[j * C + c]);
+}
+
 static int launch_rank_sorted(const float *P, int64_t ldp, int64_t C, const int32_t *idx, const float *vals, int64_t K,
-                              int64_t n, const float *base_part, float p, float scale_p, float *out, int64_t ldo,
-                              cudaStream_t st) {
+                              int64_t n, float *den, float p, float scale_p, float *out, int64_t ldo, cudaStream_t st) {
     if (n <= 512) {
         dim3 grid(static_cast<unsigned>(ceil_div<int64_t>(C, 8)), static_cast<unsigned>(K));
         const size_t smem = size_t(n) * 8 + size_t(n) * 8 * 4;       // t, rows, and a column per warp
         if (n <= 256)
-            rank_sorted_warp_kernel<8><<<grid, 256, smem, st>>>(P, ldp, int(C), idx, vals, K, int(n), base_part, p, scale_p, out, ldo);
+            rank_sorted_warp_kernel<8><<<grid, 256, smem, st>>>(P, ldp, int(C), idx, vals, K, int(n), den, p, scale_p, out, ldo);
         else
-            rank_sorted_warp_kernel<16><<<grid, 256, smem, st>>>(P, ldp, int(C), idx, vals, K, int(n), base_part, p, scale_p, out, ldo);
+            rank_sorted_warp_kernel<16><<<grid, 256, smem, st>>>(P, ldp, int(C), idx, vals, K, int(n), den, p, scale_p, out, ldo);
         return check_launch();
     }
     int npad = 1024;
@@ -318,24 +324,44 @@ static int launch_rank_sorted(const float *P, int64_t ldp, int64_t C, const int3
     if (cpb < 1) cpb = 1;
     if (cpb > 16) cpb = 16;
     dim3 grid(static_cast<unsigned>(ceil_div<int64_t>(C, cpb)), static_cast<unsigned>(K));
-    rank_sorted_cta_kernel<<<grid, 256, smem, st>>>(P, ldp, int(C), idx, vals, K, int(n), npad, cpb, base_part, p, scale_p, out, ldo);
+    rank_sorted_cta_kernel<<<grid, 256, smem, st>>>(P, ldp, int(C), idx, vals, K, int(n), npad, cpb, den, p, scale_p, out, ldo);
+    return check_launch();
+}
+
+static int launch_rank_normalize(const float *base_part, const float *den, int64_t K, int64_t C, int64_t n, float *out,
+                                 int64_t ldo, cudaStream_t st) {
+    dim3 grid(static_cast<unsigned>(ceil_div<int64_t>(C, 256)), static_cast<unsigned>(K));
+    rank_normalize_kernel<<<grid, 256, 0, st>>>(base_part, den, int(C), int(n), out, ldo);
     return check_launch();
 }
 
 }  // namespace mcd
 
-extern "C" int mcd_rank_reorder_f32(const float *P, int64_t ldp, int64_t N, int64_t C, const int32_t *idx,
-                                    const float *vals, int64_t K, int64_t top_n, const int32_t *perms, float p,
-                                    float scale_p, float *baseline_ws, float *out, int64_t ldo, mcd_stream_t stream) {
-    using namespace mcd;
-    if (!P || !idx || !vals || !perms || !baseline_ws || !out || N < 1 || C < 1 || K < 1 || top_n < 1 || ldp < C || ldo < C)
-        return MCD_ERR_INVALID_ARGUMENT;
-    if (top_n > kRankMaxSort || K > 65535 || C > (1 << 24)) return MCD_ERR_UNSUPPORTED;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    rank_perm_given_kernel<<<static_cast<unsigned>(K * 5), 128, 0, st>>>(vals, K, int(top_n), perms, p, baseline_ws);
-    int rc = check_launch();
-    if (rc != MCD_OK) return rc;
-    return launch_rank_sorted(P, ldp, C, idx, vals, K, top_n, baseline_ws, p, scale_p, out, ldo, st);
+namespace mcd {
+struct RankWs {
+    float *base_part;      // [5 K]  per (neuron, permutation) partial sums of the baseline
+    float *den;            // [K C]  (mean cosine)^scale_p
+    int32_t *scratch;      // [5 K top_n]  working arrays of the device-side shuffles
+    size_t total;
+};
+static RankWs rank_ws(void *workspace, int64_t K, int64_t top_n, int64_t C) {
+    auto up = [](size_t b) { return (b + 255) / 256 * 256; };
+    char *w = static_cast<char *>(workspace);
+    RankWs r;
+    const size_t o1 = up(size_t(K) * 5 * sizeof(float)), o2 = o1 + up(size_t(K) * size_t(C) * sizeof(float));
+    r.base_part = reinterpret_cast<float *>(w);
+    r.den = reinterpret_cast<float *>(w + o1);
+    r.scratch = reinterpret_cast<int32_t *>(w + o2);
+    r.total = o2 + size_t(K) * 5 * size_t(top_n) * sizeof(int32_t);
+    return r;
+}
+static bool rank_args_ok(int64_t C, int64_t K, int64_t top_n) { return C >= 1 && K >= 1 && top_n >= 1; }
+static bool rank_supported(int64_t C, int64_t K, int64_t top_n) { return top_n <= kRankMaxSort && K <= 65535 && C <= (1 << 24); }
+}  // namespace mcd
+
+extern "C" size_t mcd_rank_reorder_workspace_bytes(int64_t K, int64_t top_n, int64_t C) {
+    if (K < 1 || top_n < 1 || C < 1) return 0;
+    return mcd::rank_ws(nullptr, K, top_n, C).total;
 }
 
 extern "C" int mcd_mt19937_draws(uint32_t *state_io, int64_t count, uint32_t *draws, mcd_stream_t stream) {
@@ -345,26 +371,69 @@ extern "C" int mcd_mt19937_draws(uint32_t *state_io, int64_t count, uint32_t *dr
     return check_launch();
 }
 
-extern "C" size_t mcd_rank_reorder_workspace_bytes(int64_t K, int64_t top_n) {
-    if (K < 1 || top_n < 1) return 0;
-    return size_t(K) * 5 * sizeof(float) + 256 + size_t(K) * 5 * size_t(top_n) * sizeof(int32_t);
+extern "C" int mcd_rank_baseline_draws_f32(const float *vals, int64_t K, int64_t top_n, int64_t C, const uint32_t *draws,
+                                           float p, void *workspace, size_t workspace_bytes, mcd_stream_t stream) {
+    using namespace mcd;
+    if (!vals || !draws || !workspace || !rank_args_ok(C, K, top_n)) return MCD_ERR_INVALID_ARGUMENT;
+    if (!rank_supported(C, K, top_n)) return MCD_ERR_UNSUPPORTED;
+    const RankWs w = rank_ws(workspace, K, top_n, C);
+    if (workspace_bytes < w.total) return MCD_ERR_WORKSPACE;
+    rank_perm_baseline_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(K * 5, 128)), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        vals, K, int(top_n), draws, p, w.scratch, w.base_part);
+    return check_launch();
+}
+
+extern "C" int mcd_rank_baseline_perms_f32(const float *vals, int64_t K, int64_t top_n, int64_t C, const int32_t *perms,
+                                           float p, void *workspace, size_t workspace_bytes, mcd_stream_t stream) {
+    using namespace mcd;
+    if (!vals || !perms || !workspace || !rank_args_ok(C, K, top_n)) return MCD_ERR_INVALID_ARGUMENT;
+    if (!rank_supported(C, K, top_n)) return MCD_ERR_UNSUPPORTED;
+    const RankWs w = rank_ws(workspace, K, top_n, C);
+    if (workspace_bytes < w.total) return MCD_ERR_WORKSPACE;
+    rank_perm_given_kernel<<<static_cast<unsigned>(K * 5), 128, 0, static_cast<cudaStream_t>(stream)>>>(vals, K, int(top_n), perms, p,
+                                                                                                        w.base_part);
+    return check_launch();
+}
+
+extern "C" int mcd_rank_errors_f32(const float *P, int64_t ldp, int64_t N, int64_t C, const int32_t *idx, const float *vals,
+                                   int64_t K, int64_t top_n, float p, float scale_p, void *workspace, size_t workspace_bytes,
+                                   float *out, int64_t ldo, mcd_stream_t stream) {
+    using namespace mcd;
+    if (!P || !idx || !vals || !workspace || !out || N < 1 || !rank_args_ok(C, K, top_n) || ldp < C || ldo < C)
+        return MCD_ERR_INVALID_ARGUMENT;
+    if (!rank_supported(C, K, top_n)) return MCD_ERR_UNSUPPORTED;
+    const RankWs w = rank_ws(workspace, K, top_n, C);
+    if (workspace_bytes < w.total) return MCD_ERR_WORKSPACE;
+    return launch_rank_sorted(P, ldp, C, idx, vals, K, top_n, w.den, p, scale_p, out, ldo, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int mcd_rank_finish_f32(int64_t K, int64_t C, int64_t top_n, void *workspace, size_t workspace_bytes, float *out,
+                                   int64_t ldo, mcd_stream_t stream) {
+    using namespace mcd;
+    if (!workspace || !out || !rank_args_ok(C, K, top_n) || ldo < C) return MCD_ERR_INVALID_ARGUMENT;
+    if (!rank_supported(C, K, top_n)) return MCD_ERR_UNSUPPORTED;
+    const RankWs w = rank_ws(workspace, K, top_n, C);
+    if (workspace_bytes < w.total) return MCD_ERR_WORKSPACE;
+    return launch_rank_normalize(w.base_part, w.den, K, C, top_n, out, ldo, static_cast<cudaStream_t>(stream));
+}
+
+// the three steps on one stream
+extern "C" int mcd_rank_reorder_f32(const float *P, int64_t ldp, int64_t N, int64_t C, const int32_t *idx,
+                                    const float *vals, int64_t K, int64_t top_n, const int32_t *perms, float p,
+                                    float scale_p, void *workspace, size_t workspace_bytes, float *out, int64_t ldo,
+                                    mcd_stream_t stream) {
+    int rc = mcd_rank_baseline_perms_f32(vals, K, top_n, C, perms, p, workspace, workspace_bytes, stream);
+    if (rc == MCD_OK) rc = mcd_rank_errors_f32(P, ldp, N, C, idx, vals, K, top_n, p, scale_p, workspace, workspace_bytes, out, ldo, stream);
+    if (rc == MCD_OK) rc = mcd_rank_finish_f32(K, C, top_n, workspace, workspace_bytes, out, ldo, stream);
+    return rc;
 }
 
 extern "C" int mcd_rank_reorder_draws_f32(const float *P, int64_t ldp, int64_t N, int64_t C, const int32_t *idx,
                                           const float *vals, int64_t K, int64_t top_n, const uint32_t *draws, float p,
                                           float scale_p, void *workspace, size_t workspace_bytes, float *out, int64_t ldo,
                                           mcd_stream_t stream) {
-    using namespace mcd;
-    if (!P || !idx || !vals || !draws || !workspace || !out || N < 1 || C < 1 || K < 1 || top_n < 1 || ldp < C || ldo < C)
-        return MCD_ERR_INVALID_ARGUMENT;
-    if (top_n > kRankMaxSort || K > 65535 || C > (1 << 24)) return MCD_ERR_UNSUPPORTED;
-    if (workspace_bytes < mcd_rank_reorder_workspace_bytes(K, top_n)) return MCD_ERR_WORKSPACE;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    float *base_part = static_cast<float *>(workspace);
-    int32_t *scratch = reinterpret_cast<int32_t *>(static_cast<char *>(workspace) + (size_t(K) * 5 * sizeof(float) + 255) / 256 * 256);
-    rank_perm_baseline_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(K * 5, 128)), 128, 0, st>>>(vals, K, int(top_n), draws, p,
-                                                                                                    scratch, base_part);
-    int rc = check_launch();
-    if (rc != MCD_OK) return rc;
-    return launch_rank_sorted(P, ldp, C, idx, vals, K, top_n, base_part, p, scale_p, out, ldo, st);
+    int rc = mcd_rank_baseline_draws_f32(vals, K, top_n, C, draws, p, workspace, workspace_bytes, stream);
+    if (rc == MCD_OK) rc = mcd_rank_errors_f32(P, ldp, N, C, idx, vals, K, top_n, p, scale_p, workspace, workspace_bytes, out, ldo, stream);
+    if (rc == MCD_OK) rc = mcd_rank_finish_f32(K, C, top_n, workspace, workspace_bytes, out, ldo, stream);
+    return rc;
 }

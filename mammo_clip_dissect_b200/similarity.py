@@ -647,6 +647,15 @@ def _replay_works():
 
 
 _device_replay_ok = {}
+_side_streams = {}
+
+
+def _side_stream(dev):
+    key_ = (dev.type, dev.index)
+    if key_ not in _side_streams:
+        # high priority: its few CTAs (generator, shuffles) must get SM slots while the rank pass has thousands queued
+        _side_streams[key_] = torch.cuda.Stream(device=dev, priority=-1)
+    return _side_streams[key_]
 
 
 def _device_replay_works(dev):
@@ -697,42 +706,55 @@ def rank_reorder(clip_feats, target_feats, device="cuda", p=3, top_fraction=0.05
         if top_n > 8192 or K > 65535:
             raise NotImplementedError("rank_reorder on the B200 path supports top_n <= 8192 and K <= 65535 "
                                       "(got top_n=%d, K=%d)" % (top_n, K))
-        (vals, _), idx32 = topk_cols(A, top_n, dev, want_values=True, want_int32=True)
         out = torch.empty((K, C), dtype=torch.float32, device=dev)
-        if top_n > 1 and _replay_works():
-            count = K * 5 * (top_n - 1)
-            ws = _workspace(int(lib.mcd_rank_reorder_workspace_bytes(K, top_n)), dev)
-            pending = None
-            if _device_replay_works(dev):
-                # the generator continues on the device (MT19937 kernel); its final state comes back while the scoring
-                # kernels are being enqueued and is put into the CPU generator before this function returns
-                gen = torch.default_generator
-                state = gen.get_state()
-                key, pos = _mt_state_to_numpy(state)
-                st_dev = torch.from_numpy(np.append(key, np.uint32(pos)).view(np.int32)).to(dev)
-                draws = torch.empty((count,), dtype=torch.int32, device=dev)
-                _lib.check(lib.mcd_mt19937_draws(_ptr(st_dev), count, _ptr(draws), _stream(dev)), "mcd_mt19937_draws")
-                back = torch.empty((_MT_N + 1,), dtype=torch.int32, pin_memory=True)
+        ws = _workspace(int(lib.mcd_rank_reorder_workspace_bytes(K, top_n, C)), dev)
+        count = K * 5 * (top_n - 1)
+        pending = None
+        main = torch.cuda.current_stream(dev)
+        if top_n > 1 and _replay_works() and _device_replay_works(dev):
+            # The generator continues on the device (MT19937 kernel) on a side stream, beside the column top-k and the
+            # rank pass; its final state comes back while those are being enqueued and is put into the CPU generator
+            # before this function returns.
+            side = _side_stream(dev)
+            gen = torch.default_generator
+            state = gen.get_state()
+            key, pos = _mt_state_to_numpy(state)
+            st_dev = torch.from_numpy(np.append(key, np.uint32(pos)).view(np.int32)).to(dev)
+            draws = torch.empty((count,), dtype=torch.int32, device=dev)
+            back = torch.empty((_MT_N + 1,), dtype=torch.int32, pin_memory=True)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                _lib.check(lib.mcd_mt19937_draws(_ptr(st_dev), count, _ptr(draws), side.cuda_stream), "mcd_mt19937_draws")
                 back.copy_(st_dev, non_blocking=True)
                 done = torch.cuda.Event()
-                done.record()
-                pending = (gen, state, back, done)
-            else:
-                draws = torch.from_numpy(_raw_draws(count).view(np.int32)).to(dev)
-            _lib.check(lib.mcd_rank_reorder_draws_f32(_ptr(P), _ld(P), N, C, _ptr(idx32), _ptr(vals), K, top_n, _ptr(draws),
-                                                      float(p), float(scale_p), _ptr(ws), ws.numel(), _ptr(out), _ld(out),
-                                                      _stream(dev)), "mcd_rank_reorder_draws_f32")
-            if pending is not None:
-                gen, state, back, done = pending
-                done.synchronize()
-                words = back.numpy().view(np.uint32)
-                gen.set_state(_mt_state_from_numpy(state, words[:_MT_N], int(words[_MT_N])))
-            return out
-        # the reference's RNG stream call by call: for every neuron, five permutations of range(top_n)
-        perms = torch.stack([torch.stack([torch.randperm(top_n) for _ in range(5)]) for _ in range(K)]).to(torch.int32)
-        perms = perms.to(dev)
-        base = torch.empty((K * 5,), dtype=torch.float32, device=dev)
-        _lib.check(lib.mcd_rank_reorder_f32(_ptr(P), _ld(P), N, C, _ptr(idx32), _ptr(vals), K, top_n, _ptr(perms), float(p),
-                                            float(scale_p), _ptr(base), _ptr(out), _ld(out), _stream(dev)),
-                   "mcd_rank_reorder_f32")
+                done.record(side)
+            pending = (gen, state, back, done, side, draws)
+        (vals, _), idx32 = topk_cols(A, top_n, dev, want_values=True, want_int32=True)
+        if pending is not None:
+            side, draws = pending[4], pending[5]
+            side.wait_stream(main)                                  # the baseline needs the top-n activations
+            with torch.cuda.stream(side):
+                _lib.check(lib.mcd_rank_baseline_draws_f32(_ptr(vals), K, top_n, C, _ptr(draws), float(p), _ptr(ws), ws.numel(),
+                                                           side.cuda_stream), "mcd_rank_baseline_draws_f32")
+        elif top_n > 1 and _replay_works():
+            draws = torch.from_numpy(_raw_draws(count).view(np.int32)).to(dev)
+            _lib.check(lib.mcd_rank_baseline_draws_f32(_ptr(vals), K, top_n, C, _ptr(draws), float(p), _ptr(ws), ws.numel(),
+                                                       _stream(dev)), "mcd_rank_baseline_draws_f32")
+        else:
+            # the reference's RNG stream call by call: for every neuron, five permutations of range(top_n)
+            perms = torch.stack([torch.stack([torch.randperm(top_n) for _ in range(5)]) for _ in range(K)]).to(torch.int32)
+            perms = perms.to(dev)
+            _lib.check(lib.mcd_rank_baseline_perms_f32(_ptr(vals), K, top_n, C, _ptr(perms), float(p), _ptr(ws), ws.numel(),
+                                                       _stream(dev)), "mcd_rank_baseline_perms_f32")
+        _lib.check(lib.mcd_rank_errors_f32(_ptr(P), _ld(P), N, C, _ptr(idx32), _ptr(vals), K, top_n, float(p), float(scale_p),
+                                           _ptr(ws), ws.numel(), _ptr(out), _ld(out), _stream(dev)), "mcd_rank_errors_f32")
+        if pending is not None:
+            main.wait_stream(pending[4])
+        _lib.check(lib.mcd_rank_finish_f32(K, C, top_n, _ptr(ws), ws.numel(), _ptr(out), _ld(out), _stream(dev)),
+                   "mcd_rank_finish_f32")
+        if pending is not None:
+            gen, state, back, done = pending[:4]
+            done.synchronize()
+            words = back.numpy().view(np.uint32)
+            gen.set_state(_mt_state_from_numpy(state, words[:_MT_N], int(words[_MT_N])))
     return out
