@@ -74,7 +74,7 @@ int mcd_device_check(void) {
 }
 
 int mcd_set_tunable(const char *name, int64_t value) {
-    static const char *names[] = {"topk_splits", "accum_tile", "topk_variant", "accum_unroll", "topk_cols", "topk_stages", "topk_occ", "gemm_variant", "topk_pre", "topk_small", "topk_filter", "filter_stages", "filter_chunk_tiles", "pipe_chunks", "filter_order", "accum_pad_kb"};
+    static const char *names[] = {"topk_splits", "accum_tile", "topk_variant", "accum_unroll", "topk_cols", "topk_stages", "topk_occ", "gemm_variant", "topk_pre", "topk_small", "topk_filter", "filter_stages", "filter_chunk_tiles", "pipe_chunks", "filter_order", "accum_pad_kb", "gemm_tiles_per_cta", "gemm_debug_terms"};
     constexpr int n_names = sizeof(names) / sizeof(names[0]);
     if (!name) return MCD_ERR_INVALID_ARGUMENT;
     for (int i = 0; i < n_names; ++i)

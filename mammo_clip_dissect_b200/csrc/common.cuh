@@ -14,7 +14,7 @@ void count_launch(int n = 1);          // abi.cu
 int64_t tunable(int which);            // abi.cu
 enum Tunable { kTopkSplits = 0, kAccumTile = 1, kTopkVariant = 2, kAccumUnroll = 3, kTopkCols = 4, kTopkStages = 5, kTopkOcc = 6, kGemmVariant = 7,
                kTopkPre = 8, kTopkSmall = 9, kTopkFilter = 10, kFilterStages = 11, kFilterChunkTiles = 12, kPipeChunks = 13, kFilterOrder = 14, kAccumPadKb = 15,
-               kNumTunables = 16 };
+               kGemmTilesPerCta = 16, kGemmDebugTerms = 17, kNumTunables = 18 };
 int num_sms();                         // abi.cu (cached cudaDevAttrMultiProcessorCount)
 
 int debug_sync_check();                // abi.cu: MCD_DEBUG_SYNC=1 -> synchronise after every launch and report the failing one

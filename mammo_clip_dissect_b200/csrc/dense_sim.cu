@@ -243,7 +243,7 @@ namespace mcd {
 size_t sim_matrix_tc_workspace(int64_t N, int64_t C, int64_t D);                       // gemm_tf32x3.cu
 int sim_matrix_tc(const float *I, int64_t ldi, const float *T, int64_t ldt, int64_t N, int64_t C, int64_t D,
                   int normalize_rows, float *P, int64_t ldp, float *S, int64_t lds, float a, void *ws, size_t ws_bytes,
-                  cudaStream_t st);
+                  int kind, int *S_done, cudaStream_t st);
 static int g_last_gemm_path = 0;        // what the last mcd_gemm_nt_softmax_f32 call ran (mcd_last_gemm_path)
 static size_t gemm_base_workspace(int64_t N, int64_t C) {
     const size_t ldp = size_t(ceil_div<int64_t>(C, 4) * 4);
@@ -274,21 +274,22 @@ extern "C" int mcd_gemm_nt_softmax_f32(const float *I, int64_t ldi, const float 
         P = reinterpret_cast<float *>(static_cast<char *>(workspace) + off);
         ld = ceil_div<int64_t>(C, 4) * 4;
     }
-    // tensor-core path (tcgen05 kind::tf32, 3-term split) followed by the stand-alone softmax kernel.  Tunable
-    // gemm_variant = 1 forces the fp32 CUDA-core kernel; 3 selects the band kernel with the softmax fused into the
-    // GEMM epilogue -- correct, but measured 3.4x slower at N = 100k (3.05 ms against 0.77 + 0.13 ms): with one CTA
-    // per SM the exp / divide work of the four epilogue warps serialises with the tensor pipe instead of using the
-    // whole SM as the stand-alone kernel does
+    // tensor-core path (tcgen05 kind::tf32, 3-term split).  Default: the streaming kernel (a CTA walks all column tiles of
+    // its 128-row band; the epilogue of a tile runs under the MMAs of the next) followed by the stand-alone softmax.
+    // Tunable gemm_variant: 1 = the fp32 CUDA-core kernel; 2 = one CTA per output tile (round 1); 3 = the band kernel that
+    // also rescales the band inside the GEMM kernel; 4 = the streaming kernel whose epilogue keeps every row's online
+    // softmax pair + a normalising pass.  Measured at N = 100k (tools/bench_k1.py): 0.77 + 0.10 ms (default), the same
+    // (2), 3.05 ms (3), 1.03 ms (4): the fused forms are correct and tested but lose -- the exp work lands on the four
+    // epilogue warps of an SM whose other warp slots are empty, while the stand-alone kernel uses the whole machine.
     int rc = MCD_ERR_UNSUPPORTED;
     const int64_t variant = tunable(kGemmVariant);
-    bool fused = false;
     if (variant != 1) {
         char *tc_ws = static_cast<char *>(workspace) + gemm_base_workspace(N, C);
-        fused = S_out != nullptr && variant == 3;
-        rc = sim_matrix_tc(I, ldi, T, ldt, N, C, D, normalize_rows, P, ld, fused ? S_out : nullptr, lds, a, tc_ws,
-                           workspace_bytes - gemm_base_workspace(N, C), st);
-        if (rc == MCD_OK) g_last_gemm_path = fused ? 2 : 1;
-        if (rc == MCD_OK && fused) return rc;
+        int S_done = 0;
+        rc = sim_matrix_tc(I, ldi, T, ldt, N, C, D, normalize_rows, P, ld, S_out, lds, a, tc_ws,
+                           workspace_bytes - gemm_base_workspace(N, C), variant >= 2 && variant <= 4 ? int(variant) : 0, &S_done, st);
+        if (rc == MCD_OK) g_last_gemm_path = S_done ? 2 : 1;
+        if (rc == MCD_OK && S_done) return rc;
     }
     if (rc == MCD_ERR_UNSUPPORTED) {
         rc = sim_matrix_fp32(I, ldi, T, ldt, N, C, D, normalize_rows, P, ld, norms, st);

@@ -523,11 +523,22 @@ splitk_combine_kernel(const float *__restrict__ part, int splits, int64_t M, int
 
 constexpr int kFlushBlocks = 8;                          // k-blocks per accumulator group (2 accumulators x 4 k-blocks)
 
+// One CTA = `tiles_per_cta` consecutive 128-column output tiles of one 128-row band, processed back to back through the
+// same pipelines: the producer's ring and the two TMEM sets never drain between tiles, so the epilogue of a tile (TMEM ->
+// registers -> global, 64 KB of stores) runs under the MMAs of the next one.  Within a tile the k-blocks go in groups
+// of kFlushBlocks onto alternating TMEM sets; the epilogue adds every finished group into 128 fp32 registers per thread
+// (round-to-nearest adds), which bounds the tensor core's truncating accumulation to 4 k-blocks per accumulator
+// whatever the contraction length.
+//   cos / cos^3 : tiles_per_cta = 1, the contraction (probe images) split over blockIdx.z, outputs are split-K planes;
+//   K1          : tiles_per_cta = all column tiles of the band, no split.  An epilogue thread owns one output row, so it
+//                 can keep the row's online softmax pair (max, sum of exponentials of a * value) while the tiles go
+//                 by: row_stats [M][2] feeds softmax_from_stats_kernel.
 __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tf32x3_long_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                         const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
                         int64_t M, int64_t Nn, int total_kb, int kb_per_split, float *__restrict__ Cout, int64_t ldc,
-                        int64_t split_plane) {
+                        int64_t split_plane, int tiles_per_cta, int n_tiles_total, float a, float *__restrict__ row_stats,
+                        int terms) {
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     unsigned char *aligned = smem_dyn + (base - smem_u32(smem_dyn));
@@ -538,12 +549,13 @@ gemm_tf32x3_long_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+    const int n_tile0 = blockIdx.x * tiles_per_cta, m_tile = blockIdx.y;
+    const int ntiles = min(tiles_per_cta, n_tiles_total - n_tile0);
     // split-K: blockIdx.z takes k-blocks [kb_first, kb_first + num_kb) and writes its own output plane
     const int kb_first = blockIdx.z * kb_per_split;
     const int num_kb = min(kb_per_split, total_kb - kb_first);
     Cout += int64_t(blockIdx.z) * split_plane;
-    const int ngroups = (num_kb + kFlushBlocks - 1) / kFlushBlocks;
+    const int ngroups = (num_kb + kFlushBlocks - 1) / kFlushBlocks;          // per tile
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kGemmStages; ++s) {
@@ -567,85 +579,119 @@ gemm_tf32x3_long_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid
 
     if (warp == 0) {
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % kGemmStages, use = kb / kGemmStages;
-                if (use > 0) mbar_wait_bounded(&empty[s], (use - 1) & 1);
-                mbar_arrive_expect_tx(&full[s], kStageBytes);
-                const uint32_t st = base + s * kStageBytes;
-                const int kx = (kb_first + kb) * kBK;
-                tma_load_2d(st, &mapAhi, kx, m_tile * kBM, &full[s]);
-                tma_load_2d(st + kATileBytes, &mapAlo, kx, m_tile * kBM, &full[s]);
-                tma_load_2d(st + 2 * kATileBytes, &mapBhi, kx, n_tile * kBN, &full[s]);
-                tma_load_2d(st + 2 * kATileBytes + kBTileBytes, &mapBlo, kx, n_tile * kBN, &full[s]);
-            }
+            int f = 0;                           // k-block counter over all tiles: ring position and phase
+            for (int t = 0; t < ntiles; ++t)
+                for (int kb = 0; kb < num_kb; ++kb, ++f) {
+                    const int s = f % kGemmStages, use = f / kGemmStages;
+                    if (use > 0) mbar_wait_bounded(&empty[s], (use - 1) & 1);
+                    mbar_arrive_expect_tx(&full[s], kStageBytes);
+                    const uint32_t st = base + s * kStageBytes;
+                    const int kx = (kb_first + kb) * kBK;
+                    tma_load_2d(st, &mapAhi, kx, m_tile * kBM, &full[s]);
+                    tma_load_2d(st + kATileBytes, &mapAlo, kx, m_tile * kBM, &full[s]);
+                    tma_load_2d(st + 2 * kATileBytes, &mapBhi, kx, (n_tile0 + t) * kBN, &full[s]);
+                    tma_load_2d(st + 2 * kATileBytes + kBTileBytes, &mapBlo, kx, (n_tile0 + t) * kBN, &full[s]);
+                }
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int g = kb / kFlushBlocks, in_g = kb - g * kFlushBlocks, set = g & 1;
-                if (in_g == 0 && g >= 2) {                   // the epilogue has drained this set's previous group
-                    mbar_wait_bounded(&tmem_empty[set], ((g >> 1) - 1) & 1);
+            int f = 0;
+            for (int t = 0; t < ntiles; ++t)
+                for (int kb = 0; kb < num_kb; ++kb, ++f) {
+                    const int g = kb / kFlushBlocks, in_g = kb - g * kFlushBlocks;
+                    const int G = t * ngroups + g, set = G & 1;              // group counter over all tiles
+                    if (in_g == 0 && G >= 2) {               // the epilogue has drained this set's previous group
+                        mbar_wait_bounded(&tmem_empty[set], ((G >> 1) - 1) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    }
+                    const int s = f % kGemmStages, use = f / kGemmStages;
+                    mbar_wait_bounded(&full[s], use & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t st = base + s * kStageBytes;
+                    const uint64_t ahi = umma_desc_k128(st), alo = umma_desc_k128(st + kATileBytes);
+                    const uint64_t bhi = umma_desc_k128(st + 2 * kATileBytes), blo = umma_desc_k128(st + 2 * kATileBytes + kBTileBytes);
+                    const uint32_t acc = tmem_base + uint32_t(set * 2 + (in_g & 1)) * kBN;
+                    for (int kk = 0; kk < kBK / 8; ++kk) {
+                        const uint64_t adv = uint64_t((kk * 32) >> 4);
+                        umma_tf32(acc, ahi + adv, bhi + adv, in_g >= 2 || kk > 0);      // first use of the accumulator in its group: overwrite
+                        if (terms >= 3) {            // (terms = 1: measurement aid only, plain TF32)
+                            umma_tf32(acc, ahi + adv, blo + adv, true);
+                            umma_tf32(acc, alo + adv, bhi + adv, true);
+                        }
+                    }
+                    umma_commit(&empty[s]);
+                    if (in_g == kFlushBlocks - 1 || kb == num_kb - 1) umma_commit(&tmem_full[set]);
                 }
-                const int s = kb % kGemmStages, use = kb / kGemmStages;
-                mbar_wait_bounded(&full[s], use & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t st = base + s * kStageBytes;
-                const uint64_t ahi = umma_desc_k128(st), alo = umma_desc_k128(st + kATileBytes);
-                const uint64_t bhi = umma_desc_k128(st + 2 * kATileBytes), blo = umma_desc_k128(st + 2 * kATileBytes + kBTileBytes);
-                const uint32_t acc = tmem_base + uint32_t(set * 2 + (in_g & 1)) * kBN;
-                for (int kk = 0; kk < kBK / 8; ++kk) {
-                    const uint64_t adv = uint64_t((kk * 32) >> 4);
-                    umma_tf32(acc, ahi + adv, bhi + adv, in_g >= 2 || kk > 0);      // first use of the accumulator in its group: overwrite
-                    umma_tf32(acc, ahi + adv, blo + adv, true);
-                    umma_tf32(acc, alo + adv, bhi + adv, true);
-                }
-                umma_commit(&empty[s]);
-                if (in_g == kFlushBlocks - 1 || kb == num_kb - 1) umma_commit(&tmem_full[set]);
-            }
         }
     } else {
         const int quarter = warp & 3;
-        float sum[kBN];
-#pragma unroll
-        for (int i = 0; i < kBN; ++i) sum[i] = 0.f;
-#pragma unroll 1
-        for (int g = 0; g < ngroups; ++g) {
-            const int set = g & 1;
-            mbar_wait_bounded(&tmem_full[set], (g >> 1) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const bool two = num_kb - g * kFlushBlocks >= 2;                         // the group used both accumulators
-            const uint32_t t0 = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(set * 2) * kBN;
-#pragma unroll
-            for (int c = 0; c < kBN; c += 32) {
-                float v[32];
-                tmem_ld_32x32(t0 + uint32_t(c), v);
-                if (two) {
-                    float w[32];
-                    tmem_ld_32x32(t0 + uint32_t(kBN + c), w);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __fadd_rn(v[i], w[i]);
-                }
-#pragma unroll
-                for (int i = 0; i < 32; ++i) sum[c + i] = __fadd_rn(sum[c + i], v[i]);
-            }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[set]);
-        }
         const int64_t row = int64_t(m_tile) * kBM + quarter * 32 + lane;
-        const int64_t col0 = int64_t(n_tile) * kBN;
-        if (row < M) {
-            float *dst = Cout + row * ldc + col0;
-            const bool vec_ok = (ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(Cout) % 16 == 0) && col0 + kBN <= Nn;
-            if (vec_ok) {
+        float sum[kBN];
+        float smax = -INFINITY, ssum = 0.f;                  // online softmax pair of this thread's row
+#pragma unroll 1
+        for (int t = 0; t < ntiles; ++t) {
 #pragma unroll
-                for (int i = 0; i < kBN; i += 4) *reinterpret_cast<float4 *>(dst + i) = make_float4(sum[i], sum[i + 1], sum[i + 2], sum[i + 3]);
-            } else {
+            for (int i = 0; i < kBN; ++i) sum[i] = 0.f;
+#pragma unroll 1
+            for (int g = 0; g < ngroups; ++g) {
+                const int G = t * ngroups + g, set = G & 1;
+                mbar_wait_bounded(&tmem_full[set], (G >> 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const bool two = num_kb - g * kFlushBlocks >= 2;                         // the group used both accumulators
+                const uint32_t t0 = tmem_base + (uint32_t(quarter * 32) << 16) + uint32_t(set * 2) * kBN;
 #pragma unroll
-                for (int i = 0; i < kBN; ++i)
-                    if (col0 + i < Nn) dst[i] = sum[i];
+                for (int c = 0; c < kBN; c += 32) {
+                    uint32_t v[32], w[32];
+                    tmem_ld_32x32_issue(t0 + uint32_t(c), v);
+                    if (two) tmem_ld_32x32_issue(t0 + uint32_t(kBN + c), w);
+                    tmem_ld_wait();
+                    if (two) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            sum[c + i] = __fadd_rn(sum[c + i], __fadd_rn(__uint_as_float(v[i]), __uint_as_float(w[i])));
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) sum[c + i] = __fadd_rn(sum[c + i], __uint_as_float(v[i]));
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tmem_empty[set]);
             }
+            // the tile is complete in registers: store it (the MMAs of the next tile are already running)
+            const int64_t col0 = int64_t(n_tile0 + t) * kBN;
+            if (row < M) {
+                float *dst = Cout + row * ldc + col0;
+                const bool whole = col0 + kBN <= Nn;
+                const bool vec_ok = (ldc % 4 == 0) && (reinterpret_cast<uintptr_t>(Cout) % 16 == 0) && whole;
+                if (vec_ok) {
+#pragma unroll
+                    for (int i = 0; i < kBN; i += 4) *reinterpret_cast<float4 *>(dst + i) = make_float4(sum[i], sum[i + 1], sum[i + 2], sum[i + 3]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < kBN; ++i)
+                        if (col0 + i < Nn) dst[i] = sum[i];
+                }
+                if (row_stats != nullptr) {
+                    float mx = -INFINITY;
+#pragma unroll
+                    for (int i = 0; i < kBN; ++i) {
+                        sum[i] = (whole || col0 + i < Nn) ? __fmul_rn(a, sum[i]) : -INFINITY;
+                        mx = fmaxf(mx, sum[i]);
+                    }
+                    if (mx > smax) {
+                        ssum *= (smax == -INFINITY) ? 0.f : expf(smax - mx);
+                        smax = mx;
+                    }
+                    const float ms = (smax == -INFINITY) ? 0.f : smax;
+#pragma unroll
+                    for (int i = 0; i < kBN; ++i) ssum += expf(__fsub_rn(sum[i], ms));       // exp(-inf) = 0 for the padding
+                }
+            }
+        }
+        if (row_stats != nullptr && row < M) {
+            row_stats[row * 2] = smax;
+            row_stats[row * 2 + 1] = ssum;
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     }
@@ -654,6 +700,20 @@ gemm_tf32x3_long_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
     }
+}
+
+// S = exp(a * P - max) / sum from the row pairs left by the GEMM epilogue: per element the reference's operation
+// sequence (separately rounded a * P, expf, true division); warp per row, coalesced.
+__global__ void __launch_bounds__(256)
+softmax_from_stats_kernel(const float *__restrict__ P, int64_t ldp, const float *__restrict__ row_stats, int64_t n_rows,
+                          int n_cols, float a, float *__restrict__ S, int64_t lds) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const float rm = row_stats[row * 2], rs = row_stats[row * 2 + 1];
+    const float *src = P + row * ldp;
+    float *dst = S + row * lds;
+    for (int c = lane; c < lds; c += 32) dst[c] = c < n_cols ? __fdiv_rn(expf(__fsub_rn(__fmul_rn(a, src[c]), rm)), rs) : 0.f;
 }
 
 // ---- host ---------------------------------------------------------------------------------------------------------
@@ -687,21 +747,28 @@ static bool make_operand_map(CUtensorMap *map, const float *X, int64_t rows, int
 
 size_t sim_matrix_tc_workspace(int64_t N, int64_t C, int64_t D) {
     const int64_t Np = ceil_div<int64_t>(N, kBM) * kBM, Cp = ceil_div<int64_t>(C, kBN) * kBN, Dp = ceil_div<int64_t>(D, kBK) * kBK;
-    return size_t(Np + Cp) * size_t(Dp) * 2 * sizeof(float) + 1024;
+    return size_t(Np + Cp) * size_t(Dp) * 2 * sizeof(float) + size_t(Np) * 2 * sizeof(float) /*row softmax pairs*/ + 1024;
 }
 
-// returns MCD_ERR_UNSUPPORTED when the tensor-map encoder is unavailable (caller then uses the CUDA-core kernel)
+// returns MCD_ERR_UNSUPPORTED when the tensor-map encoder is unavailable (caller then uses the CUDA-core kernel).
+// kind: 0 = the streaming kernel (a CTA walks all column tiles of its 128-row band); the caller runs the stand-alone softmax;
+//       2 = one CTA per output tile (round 1's kernel), ditto;
+//       3 = the band kernel that also rescales the band inside the GEMM kernel;
+//       4 = the streaming kernel whose epilogue keeps the row softmax pairs + softmax_from_stats_kernel.
+// *S_done = 1 when S has been produced.
 int sim_matrix_tc(const float *I, int64_t ldi, const float *T, int64_t ldt, int64_t N, int64_t C, int64_t D,
                   int normalize_rows, float *P, int64_t ldp, float *S, int64_t lds, float a, void *ws, size_t ws_bytes,
-                  cudaStream_t st) {
+                  int kind, int *S_done, cudaStream_t st) {
     const int64_t Np = ceil_div<int64_t>(N, kBM) * kBM, Cp = ceil_div<int64_t>(C, kBN) * kBN, Dp = ceil_div<int64_t>(D, kBK) * kBK;
+    *S_done = 0;
     if (ws_bytes < sim_matrix_tc_workspace(N, C, D)) return MCD_ERR_WORKSPACE;
-    if (Np / kBM > 65535 && S == nullptr) return MCD_ERR_UNSUPPORTED;
+    if (Np / kBM > 65535) return MCD_ERR_UNSUPPORTED;
     char *w = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(ws) + 1023) & ~uintptr_t(1023));
     float *Ihi = reinterpret_cast<float *>(w);
     float *Ilo = Ihi + Np * Dp;
     float *Thi = Ilo + Np * Dp;
     float *Tlo = Thi + Cp * Dp;
+    float *row_stats = Tlo + Cp * Dp;
     CUtensorMap mAhi, mAlo, mBhi, mBlo;
     if (!make_operand_map(&mAhi, Ihi, Np, Dp, kBM) || !make_operand_map(&mAlo, Ilo, Np, Dp, kBM) ||
         !make_operand_map(&mBhi, Thi, Cp, Dp, kBN) || !make_operand_map(&mBlo, Tlo, Cp, Dp, kBN))
@@ -709,18 +776,40 @@ int sim_matrix_tc(const float *I, int64_t ldi, const float *T, int64_t ldt, int6
     prepare_rows_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(Np, 8)), 256, 0, st>>>(I, ldi, N, D, normalize_rows, Ihi, Ilo, Np, Dp);
     prepare_rows_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(Cp, 8)), 256, 0, st>>>(T, ldt, C, D, normalize_rows, Thi, Tlo, Cp, Dp);
     count_launch(2);
-    if (S != nullptr) {
-        // one CTA per 128-row band, softmax fused (opt-in: tunable gemm_variant = 3, see dense_sim.cu)
+    const int n_tiles = static_cast<int>(Cp / kBN), num_kb = static_cast<int>(Dp / kBK);
+    if (kind == 3 && S != nullptr) {
         if (cudaFuncSetAttribute(gemm_tf32x3_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTcSmemBytes)) != cudaSuccess)
             return MCD_ERR_CUDA;
         gemm_tf32x3_band_kernel<<<static_cast<unsigned>(Np / kBM), kTcThreads, kTcSmemBytes, st>>>(
-            mAhi, mAlo, mBhi, mBlo, N, C, static_cast<int>(Dp / kBK), static_cast<int>(Cp / kBN), P, ldp, S, lds, a);
+            mAhi, mAlo, mBhi, mBlo, N, C, num_kb, n_tiles, P, ldp, S, lds, a);
+        *S_done = 1;
         return check_launch();
     }
-    if (cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTcSmemBytes)) != cudaSuccess)
+    if (kind == 2 || kind == 3) {
+        if (cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTcSmemBytes)) != cudaSuccess)
+            return MCD_ERR_CUDA;
+        dim3 grid(static_cast<unsigned>(n_tiles), static_cast<unsigned>(Np / kBM));
+        gemm_tf32x3_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(mAhi, mAlo, mBhi, mBlo, N, C, num_kb, P, ldp);
+        return check_launch();
+    }
+    if (cudaFuncSetAttribute(gemm_tf32x3_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTcSmemBytes)) != cudaSuccess)
         return MCD_ERR_CUDA;
-    dim3 grid(static_cast<unsigned>(Cp / kBN), static_cast<unsigned>(Np / kBM));
-    gemm_tf32x3_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(mAhi, mAlo, mBhi, mBlo, N, C, static_cast<int>(Dp / kBK), P, ldp);
+    const int64_t tpc = tunable(kGemmTilesPerCta);
+    const bool stats = kind == 4 && S != nullptr;
+    // with the row pairs the whole band must pass through one CTA; without, any tile count per CTA will do
+    // (default: half a band per CTA -- 3 tiles for the 763-concept set; measured at N = 100k: 1 tile 0.80 ms, 2: 0.75,
+    // 3: 0.73, 6: 0.77: fewer, longer CTAs save pipeline fills, more of them balance the last wave)
+    int tiles_per_cta = n_tiles >= 4 ? (n_tiles + 1) / 2 : n_tiles;
+    if (stats) tiles_per_cta = n_tiles;
+    else if (tpc > 0 && tpc <= n_tiles) tiles_per_cta = static_cast<int>(tpc);
+    dim3 grid(static_cast<unsigned>(ceil_div<int64_t>(n_tiles, tiles_per_cta)), static_cast<unsigned>(Np / kBM), 1);
+    gemm_tf32x3_long_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(mAhi, mAlo, mBhi, mBlo, N, C, num_kb, num_kb, P, ldp, 0,
+                                                                    tiles_per_cta, n_tiles, a, stats ? row_stats : nullptr,
+                                                                    tunable(kGemmDebugTerms) == 1 ? 1 : 3);
+    int rc = check_launch();
+    if (rc != MCD_OK || !stats) return rc;
+    softmax_from_stats_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(N, 8)), 256, 0, st>>>(P, ldp, row_stats, N, int(C), a, S, lds);
+    *S_done = 1;
     return check_launch();
 }
 
@@ -823,11 +912,11 @@ int cos_similarity_tc(const float *P, int64_t ldp, const float *A, int64_t lda, 
         dim3 grid(static_cast<unsigned>(l.Cp / kBN), static_cast<unsigned>(kp / kBM), static_cast<unsigned>(l.splits));
         if (l.splits == 1) {
             gemm_tf32x3_long_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(mAhi, mAlo, mBhi, mBlo, kn, C, total_kb, l.kb_per_split,
-                                                                            out + k0 * ldo, ldo, 0);
+                                                                            out + k0 * ldo, ldo, 0, 1, int(l.Cp / kBN), 1.f, nullptr, 3);
             if ((rc = check_launch()) != MCD_OK) return rc;
         } else {
             gemm_tf32x3_long_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(mAhi, mAlo, mBhi, mBlo, kn, C, total_kb, l.kb_per_split,
-                                                                            part, l.Cp, l.Kp * l.Cp);
+                                                                            part, l.Cp, l.Kp * l.Cp, 1, int(l.Cp / kBN), 1.f, nullptr, 3);
             if ((rc = check_launch()) != MCD_OK) return rc;
             dim3 cgrid(static_cast<unsigned>(ceil_div<int64_t>(C, 256)), static_cast<unsigned>(kn));
             splitk_combine_kernel<<<cgrid, 256, 0, st>>>(part, l.splits, kn, C, l.Cp, l.Kp * l.Cp, out + k0 * ldo, ldo);

@@ -700,7 +700,7 @@ def test_similarity_matrix_tensor_core_vs_fp32(sim, N, C, D, normalize):
     scale = ref.abs().max().item()
     n0 = _lib.launch_count()
     P_tc = features.similarity_matrix(I, T, device=DEV, normalize=normalize).cpu()
-    assert _lib.launch_count() - n0 == 3                 # 2 x prepare_rows + gemm_tf32x3
+    assert _lib.launch_count() - n0 == 3                 # 2 x prepare_rows + the streaming GEMM
     assert features.last_gemm_path() == "tcgen05"        # ... and the library says which GEMM it ran (the CUDA-core
     try:                                                 # fallback is 3 launches too: 2 x row_norm + sgemm)
         _lib.set_tunable("gemm_variant", 1)
@@ -720,22 +720,45 @@ def test_similarity_matrix_tensor_core_vs_fp32(sim, N, C, D, normalize):
         e_s = ((S.cpu().double() - refS).abs() / refS).max().item()
         print("   softmax(10 P) max rel err through the tensor-core path: %.3g" % e_s)
         assert e_s <= 1e-5
-    # the opt-in band kernel with the softmax fused into the GEMM epilogue (gemm_variant = 3) against the default
-    # GEMM + stand-alone softmax: same P bits (same accumulation order), S within a few ulp (only the order of the row
-    # sum differs)
-    P_s, S_s = features.similarity_matrix(I, T, device=DEV, normalize=normalize, softmax_scale=10)
-    try:
-        _lib.set_tunable("gemm_variant", 3)
-        n0 = _lib.launch_count()
-        P_f, S_f = features.similarity_matrix(I, T, device=DEV, normalize=normalize, softmax_scale=10)
-        assert _lib.launch_count() - n0 == 3             # 2 x prepare_rows + the band kernel: no softmax launch
-        assert features.last_gemm_path() == "tcgen05_fused_softmax"
-    finally:
-        _lib.set_tunable("gemm_variant", 0)
-    assert torch.equal(P_f, P_s) and torch.equal(P_f.cpu(), P_tc)
-    rel = ((S_f - S_s).abs() / S_s.clamp_min(1e-30)).max().item()
-    print("   fused vs stand-alone softmax: max rel diff %.3g" % rel)
-    assert rel <= 2e-6 and abs(S_f.sum(dim=1) - 1).max().item() < 1e-5
+
+    def softmax_of(P32):
+        """The kernels' softmax of THEIR OWN P: fp32-rounded a * P and (a * P - max) as they compute them, the rest in fp64."""
+        z = P32 * 10.0
+        d = z - z.max(dim=1, keepdim=True).values
+        e = d.double().exp()
+        return e / e.sum(dim=1, keepdim=True)
+
+    # the tensor-core variants: streaming kernel + the stand-alone softmax (default), one CTA per tile + the stand-alone
+    # softmax (2), the band kernel that rescales in place (3), the streaming kernel whose epilogue keeps the row softmax
+    # pairs + a normalising pass (4)
+    got = {}
+    for variant, launches, path in ((0, 4, "tcgen05"), (2, 4, "tcgen05"), (3, 3, "tcgen05_fused_softmax"),
+                                    (4, 4, "tcgen05_fused_softmax")):
+        try:
+            _lib.set_tunable("gemm_variant", variant)
+            n0 = _lib.launch_count()
+            P_v, S_v = features.similarity_matrix(I, T, device=DEV, normalize=normalize, softmax_scale=10)
+            assert _lib.launch_count() - n0 == launches, variant
+            assert features.last_gemm_path() == path, variant
+        finally:
+            _lib.set_tunable("gemm_variant", 0)
+        P_v, S_v = P_v.cpu(), S_v.cpu()
+        assert (P_v.double() - ref).abs().max().item() / scale <= 3e-6, variant
+        want = softmax_of(P_v)
+        big = want > 1e-30                                # below that fp32 exponentials are denormal or zero
+        rel = ((S_v.double() - want).abs()[big] / want[big]).max().item()
+        assert S_v[~big].max().item() <= 2e-30 if (~big).any() else True
+        print("   variant %d: softmax against the fp64 softmax of its own P: max rel %.3g" % (variant, rel))
+        assert rel <= 2e-6 and abs(S_v.sum(dim=1) - 1).max().item() < 1e-5, (variant, rel)
+        got[variant] = P_v
+    assert torch.equal(got[0], P_tc) and torch.equal(got[4], P_tc)       # with or without the softmax: the same P bits
+    assert torch.equal(got[2], got[3])                   # the two one-tile-at-a-time kernels share their accumulation order
+    for tiles in (1, 2, 4):                              # fewer column tiles per CTA: any split gives the same bits
+        try:
+            _lib.set_tunable("gemm_tiles_per_cta", tiles)
+            assert torch.equal(features.similarity_matrix(I, T, device=DEV, normalize=normalize).cpu(), P_tc)
+        finally:
+            _lib.set_tunable("gemm_tiles_per_cta", 0)
 
 
 def test_hook_matches_reference(sim, golden):

@@ -21,7 +21,8 @@ def timeit(fn, iters=10):
 
 
 ref = (torch.nn.functional.normalize(I.double(), dim=1) @ torch.nn.functional.normalize(T.double(), dim=1).T)
-for var, name in ((0, "default"), (3, "band kernel, softmax fused"), (1, "fp32 CUDA cores")):
+for var, name in ((0, "streaming kernel (default)"), (2, "one CTA per tile"), (4, "streaming, row pairs fused"),
+                  (3, "band kernel, rescale fused"), (1, "fp32 CUDA cores")):
     _lib.set_tunable("gemm_variant", var)
     for scale in (None, 10.0):
         ms = timeit(lambda: features.similarity_matrix(I, T, device=dev, softmax_scale=scale))
@@ -34,3 +35,12 @@ for var, name in ((0, "default"), (3, "band kernel, softmax fused"), (1, "fp32 C
             line += "   max rel |S - fp64| %.2e" % ((out[1].double() - S64).abs() / S64).max().item()
         print(line, flush=True)
 _lib.set_tunable("gemm_variant", 0)
+# measurement aid: the same pipeline with one MMA term instead of three (plain TF32: wrong digits, same operand traffic
+# through TMA, a third of the tensor-core work and of its shared-memory operand reads)
+_lib.set_tunable("gemm_debug_terms", 1)
+print("streaming kernel, 1 of 3 MMA terms: %.3f ms" % timeit(lambda: features.similarity_matrix(I, T, device=dev)), flush=True)
+_lib.set_tunable("gemm_debug_terms", 0)
+for tiles in (1, 2, 3):
+    _lib.set_tunable("gemm_tiles_per_cta", tiles)
+    print("streaming kernel, %d column tiles per CTA: %.3f ms" % (tiles, timeit(lambda: features.similarity_matrix(I, T, device=dev))), flush=True)
+_lib.set_tunable("gemm_tiles_per_cta", 0)
