@@ -536,7 +536,7 @@ def run_ours(args):
                           "sample_select + filter scan + select + redo) with CUDA events, so the fraction is a lower bound "
                           "for the scan kernel itself",
                 "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
-                "traffic": tr.get("filter_scan_kernel"), "peak_source": peak_src, "ms_per_launch": round(topk_ms, 4),
+                "traffic": (tr.get("filter_scan_kernel") * K_local / 32768.0 if tr.get("filter_scan_kernel") else None), "peak_source": peak_src, "ms_per_launch": round(topk_ms, 4),
                 "algorithmic_bytes_per_launch": alg_topk}
     ach_path = alg_path / (ms_step / 1e3) / 1e9
     cfg = workload_config(world)
