@@ -195,6 +195,9 @@ int pmi_logsums(const float *P, int64_t ldp, const float *A, int64_t lda, int64_
     // What IS worth a second stream: the softmax (K1b) beside the sample pass and the scan when the neuron shard is narrow
     // (a rank of the 8-GPU call: 4096 neurons) -- the softmax over all N images does not shrink with the shard and would
     // otherwise be a third of the rank's step; at full width both are HBM-bound and the overlap is neutral.
+    // (At full width the softmax was also tried beside the list SELECT -- instruction-bound, DRAM at 16 % -- and split
+    // between the threshold select and the list select: 2.98 / 3.00 ms against 2.98 ms for the plain sequence on the same
+    // box, i.e. nothing: both kernels are issue-heavy.  Removed.)
     const bool side_softmax = tunable(kPipeChunks) == 0 && N * C >= (int64_t(1) << 23) && K <= 16384;
     PipeRes *pr = (tunable(kPipeChunks) > 0 || side_softmax) ? pipe_resources() : nullptr;
     int rc = pr ? topk_filter_prepare(A, lda, N, K, k, w + l.topk_off, workspace_bytes - l.topk_off, &call) : MCD_ERR_UNSUPPORTED;

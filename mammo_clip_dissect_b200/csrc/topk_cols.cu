@@ -974,10 +974,10 @@ static bool make_plan(int64_t N, int64_t K, int64_t k64, TopkPlan *p) {
             const int64_t tiles_total = N / p->f_rows, nblk = ceil_div<int64_t>(K, kFCols);
             int64_t ct = tunable(kFilterChunkTiles);
             if (ct <= 0) {
-                // a work item = one single-warp CTA; ~32 items per resident warp (8 per SM): the tail of the launch and the
-                // pipeline fill / drain of an item stay at a few per cent
-                ct = ceil_div<int64_t>(tiles_total * nblk, sms * 8 * 32);
-                if (ct < 48) ct = 48;
+                // a work item = one CTA (scanner + drainer warp); ~80 items per resident CTA (11 per SM): short items keep
+                // the last wave balanced (measured at c4: 31 tiles 2.19 ms, 62: 2.20, 85: 2.21, 124: 2.24 for the stage)
+                ct = ceil_div<int64_t>(tiles_total * nblk, sms * 11 * 80);
+                if (ct < 24) ct = 24;
             }
             if (ct > tiles_total) ct = tiles_total;
             if (ct < 1) ct = 1;

@@ -32,7 +32,7 @@ namespace mcd {
 
 constexpr int kFCols = 128;                          // columns per work item = TMA box width (a lane owns 4)
 constexpr int kFRows = 8;                            // rows per tile (default; filter_scan_kernel<16> is the 16-row variant)
-constexpr int kFThreads = 32;                        // one warp per CTA
+constexpr int kFThreads = 64;                        // two warps per CTA: the scanner and the drainer of its bags
 constexpr int kFBagCap = 8;                          // entries of one half of a lane-private bag (an entry = 4 values of one row)
 constexpr int kFBagStep = 4;                         // 4 rows append at most 4 entries per lane
 constexpr int kFMaxStages = 8;
@@ -45,6 +45,9 @@ struct FilterTail {
     float4 bagv[2][kFBagCap][32];                    // two halves: the row's 4 values of a lane with a passing element
     uint32_t bagr[2][kFBagCap][32];                  // ... and the row
     uint64_t full[kFMaxStages];
+    uint64_t ready[2], drained[2];                   // a half handed to the drainer warp / given back
+    int pub_cnt[2][32];                              // entries per lane in a handed-over half
+    int pub_last[2];                                 // 1: the item's last hand-over
 };
 __host__ __device__ inline size_t filter_smem_bytes(int nstage, int rows) { return size_t(nstage) * rows * kFRowBytes + sizeof(FilterTail); }
 
@@ -92,7 +95,7 @@ filter_scan_kernel(const __grid_constant__ CUtensorMap tmap, const FilterArgs a)
     constexpr uint32_t kFTileBytes = ROWS * kFRowBytes;
     extern __shared__ __align__(1024) unsigned char fsm[];
     FilterTail &t = *reinterpret_cast<FilterTail *>(fsm + size_t(a.nstage) * kFTileBytes);
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31;
     const uint32_t ring_addr = smem_u32(fsm), full_addr = smem_u32(&t.full[0]);
     const int nstage = a.nstage;
     const int64_t c0 = a.col_begin + int64_t(blockIdx.x) * kFCols;
@@ -103,13 +106,17 @@ filter_scan_kernel(const __grid_constant__ CUtensorMap tmap, const FilterArgs a)
     const uint64_t policy = l2_policy_evict_first();
     const int tx = static_cast<int>(c0), ty0 = static_cast<int>(tile0 * ROWS);
 
-    if (lane == 0) {
+    if (threadIdx.x == 0) {
         for (int i = 0; i < nstage; ++i) mbar_init(&t.full[i], 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&t.ready[i], 1);
+            mbar_init(&t.drained[i], 1);
+        }
         fence_mbar_init();
     }
-    __syncwarp();
+    __syncthreads();
     // prologue: start the stream before touching anything else
-    if (lane == 0) {
+    if (threadIdx.x == 0) {
         for (int i = 0; i < nstage && i < ntile; ++i) {
             mbar_arrive_expect_tx_addr(full_addr + i * 8, kFTileBytes);
             tma_tile_g2s(ring_addr + i * kFTileBytes, &tmap, tx, ty0 + i * ROWS, full_addr + i * 8, policy);
@@ -123,55 +130,73 @@ filter_scan_kernel(const __grid_constant__ CUtensorMap tmap, const FilterArgs a)
     tau4.z = cur_col + 2 < a.col_end ? __ldg(a.tau + cur_col + 2) : INFINITY;
     tau4.w = cur_col + 3 < a.col_end ? __ldg(a.tau + cur_col + 3) : INFINITY;
 
+    const int cap = a.cap;
+    if (threadIdx.x >= 32) {
+        // ---- drainer warp: empties the bag halves the scanner hands over (lane l takes lane l's entries): which of an
+        // entry's four values passed is recomputed against tau, the lane's survivors are counted per column, ONE
+        // atomicAdd per column with entries reserves the list slots, then the words go out.  Nothing here is on the
+        // scanner's critical path: the stream never waits for an L2 round trip or for the scattered stores.
+        unsigned long long *list = a.lists + cur_col * cap;
+        int *cnt = a.cnt + cur_col;
+#pragma unroll 1
+        for (int s = 0;; ++s) {
+            const int h = s & 1;
+            mbar_wait_bounded(smem_u32(&t.ready[h]), uint32_t(s >> 1) & 1u);
+            const int c = t.pub_cnt[h][lane];
+            const int last = t.pub_last[h];
+            const int mx = __reduce_max_sync(0xffffffffu, c);
+            if (mx) {
+                int n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+#pragma unroll 1
+                for (int i = 0; i < mx; ++i) {
+                    if (i < c) {
+                        const float4 v = t.bagv[h][i][lane];
+                        n0 += !(v.x <= tau4.x);
+                        n1 += !(v.y <= tau4.y);
+                        n2 += !(v.z <= tau4.z);
+                        n3 += !(v.w <= tau4.w);
+                    }
+                }
+                int o0 = 0, o1 = 0, o2 = 0, o3 = 0;
+                if (n0) o0 = atomicAdd(cnt + 0, n0);
+                if (n1) o1 = atomicAdd(cnt + 1, n1);
+                if (n2) o2 = atomicAdd(cnt + 2, n2);
+                if (n3) o3 = atomicAdd(cnt + 3, n3);
+#pragma unroll 1
+                for (int i = 0; i < mx; ++i) {
+                    if (i < c) {
+                        const float4 v = t.bagv[h][i][lane];
+                        const uint32_t nrow = ~t.bagr[h][i][lane];
+                        if (!(v.x <= tau4.x)) { if (o0 < cap) list[o0] = pack_key(ordered_key(v.x), nrow); ++o0; }
+                        if (!(v.y <= tau4.y)) { if (o1 < cap) list[int64_t(cap) + o1] = pack_key(ordered_key(v.y), nrow); ++o1; }
+                        if (!(v.z <= tau4.z)) { if (o2 < cap) list[int64_t(cap) * 2 + o2] = pack_key(ordered_key(v.z), nrow); ++o2; }
+                        if (!(v.w <= tau4.w)) { if (o3 < cap) list[int64_t(cap) * 3 + o3] = pack_key(ordered_key(v.w), nrow); ++o3; }
+                    }
+                }
+            }
+            __syncwarp();                            // every lane is done reading the half
+            if (lane == 0) mbar_arrive(&t.drained[h]);
+            if (last) break;
+        }
+        return;
+    }
+
+    // ---- scanner warp ----
     const uint32_t bagv0 = smem_u32(&t.bagv[0][0][lane]), bagr0 = smem_u32(&t.bagr[0][0][lane]);
     constexpr uint32_t kHalfV = kFBagCap * kFBagValBytes, kHalfR = kFBagCap * kFBagRowBytes;
-    int half = 0;
+    int half = 0, handed = 0;                        // handed = hand-overs so far; hand-over number s uses half s & 1
     uint32_t pv = bagv0, pr = bagr0;
-    const int cap = a.cap;
-    // pending half: entries counted, slots reserved (o0..o3 = first slot per column), not yet placed
-    int pend_c = 0, pend_mx = 0, pend_half = 0, o0 = 0, o1 = 0, o2 = 0, o3 = 0;
     uint32_t half_limit = bagr0 + uint32_t(kFBagCap - kFBagStep) * kFBagRowBytes;
 
-    auto place = [&]() {
-        unsigned long long *list = a.lists + cur_col * cap;
-#pragma unroll 1
-        for (int i = 0; i < pend_mx; ++i) {
-            if (i < pend_c) {
-                const float4 v = t.bagv[pend_half][i][lane];
-                const uint32_t nrow = ~t.bagr[pend_half][i][lane];
-                if (!(v.x <= tau4.x)) { if (o0 < cap) list[o0] = pack_key(ordered_key(v.x), nrow); ++o0; }
-                if (!(v.y <= tau4.y)) { if (o1 < cap) list[int64_t(cap) + o1] = pack_key(ordered_key(v.y), nrow); ++o1; }
-                if (!(v.z <= tau4.z)) { if (o2 < cap) list[int64_t(cap) * 2 + o2] = pack_key(ordered_key(v.z), nrow); ++o2; }
-                if (!(v.w <= tau4.w)) { if (o3 < cap) list[int64_t(cap) * 3 + o3] = pack_key(ordered_key(v.w), nrow); ++o3; }
-            }
-        }
-        pend_mx = 0;
-    };
-    auto flush_issue = [&]() {
-        if (pend_mx) place();
-        const int c = static_cast<int>((pr - (bagr0 + half * kHalfR)) / kFBagRowBytes);
-        const int mx = __reduce_max_sync(0xffffffffu, c);
-        if (mx == 0) return;
-        int n0 = 0, n1 = 0, n2 = 0, n3 = 0;
-#pragma unroll 1
-        for (int i = 0; i < mx; ++i) {
-            if (i < c) {
-                const float4 v = t.bagv[half][i][lane];
-                n0 += !(v.x <= tau4.x);
-                n1 += !(v.y <= tau4.y);
-                n2 += !(v.z <= tau4.z);
-                n3 += !(v.w <= tau4.w);
-            }
-        }
-        int *cnt = a.cnt + cur_col;
-        if (n0) o0 = atomicAdd(cnt + 0, n0);
-        if (n1) o1 = atomicAdd(cnt + 1, n1);
-        if (n2) o2 = atomicAdd(cnt + 2, n2);
-        if (n3) o3 = atomicAdd(cnt + 3, n3);
-        pend_c = c;
-        pend_mx = mx;
-        pend_half = half;
+    // hand the current half to the drainer and continue in the other one (waiting, rarely, until it has been drained)
+    auto hand_over = [&](int last) {
+        t.pub_cnt[half][lane] = static_cast<int>((pr - (bagr0 + half * kHalfR)) / kFBagRowBytes);
+        if (lane == 0) t.pub_last[half] = last;
+        __syncwarp();                                // the bag entries and counts of all lanes, before the arrival
+        if (lane == 0) mbar_arrive(&t.ready[half]);
+        ++handed;
         half ^= 1;
+        if (handed >= 2 && !last) mbar_wait_bounded(smem_u32(&t.drained[half]), uint32_t((handed - 2) >> 1) & 1u);
         pv = bagv0 + half * kHalfV;
         pr = bagr0 + half * kHalfR;
         half_limit = pr + uint32_t(kFBagCap - kFBagStep) * kFBagRowBytes;
@@ -234,11 +259,10 @@ filter_scan_kernel(const __grid_constant__ CUtensorMap tmap, const FilterArgs a)
                 for (int i = 12; i < 16; ++i) append(v[i < ROWS ? i : 0], row0, i);
             }
             // 4 rows add at most 4 entries per lane: switch halves when a lane has fewer than 4 free slots left
-            if (__any_sync(0xffffffffu, pr > half_limit)) flush_issue();
+            if (__any_sync(0xffffffffu, pr > half_limit)) hand_over(0);
         }
     }
-#pragma unroll 1
-    for (int rep = 0; rep < 2; ++rep) flush_issue();       // the second call places what the first one reserved
+    hand_over(1);
 }
 
 // The last N % 8 rows of the matrix (the scan streams whole 8-row tiles only): thread per column.
