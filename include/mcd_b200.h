@@ -223,7 +223,7 @@ int mcd_last_cos_path(void);
  *              generator's raw 32-bit outputs (torch.randperm = Fisher-Yates with z = draw % (n - i); shuffles on the
  *              device), or from perms [K, 5, top_n] int32 drawn on the host;
  *        mcd_rank_errors_f32    the gather + rank pass: leaves mean_r |.|^p in out and (mean cosine)^scale_p in the workspace;
- *        mcd_rank_finish_f32    out = -((e / baseline) / den), the reference's operation order (similarity.py:126-129).
+ *        mcd_rank_finish_f32    out = -((e / baseline) / den), the reference's operation order (similarity.py:128-129).
  *      mcd_rank_reorder_f32 / mcd_rank_reorder_draws_f32 run the three on one stream.
  *      mcd_mt19937_draws produces the raw draws themselves: it continues MT19937 (the engine of torch's CPU generator) on
  *      the device.  state_io: 624 state words + 1 word "index of the next output" (624 = twist before the next draw); on

@@ -162,15 +162,32 @@ filter_scan_kernel(const __grid_constant__ CUtensorMap tmap, const FilterArgs a)
                 if (n1) o1 = atomicAdd(cnt + 1, n1);
                 if (n2) o2 = atomicAdd(cnt + 2, n2);
                 if (n3) o3 = atomicAdd(cnt + 3, n3);
+                // One store instruction per entry slot for the whole warp (a second one only where an entry has two passing
+                // values): the stream pays for every store INSTRUCTION the drainer issues, not for bytes or sectors
+                // (profiles/r2_k2_history.md), so the four per-column stores of an entry are folded into one.
 #pragma unroll 1
                 for (int i = 0; i < mx; ++i) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    uint32_t nrow = 0u;
+                    unsigned m = 0u;                 // which of the entry's four values passed
                     if (i < c) {
-                        const float4 v = t.bagv[h][i][lane];
-                        const uint32_t nrow = ~t.bagr[h][i][lane];
-                        if (!(v.x <= tau4.x)) { if (o0 < cap) list[o0] = pack_key(ordered_key(v.x), nrow); ++o0; }
-                        if (!(v.y <= tau4.y)) { if (o1 < cap) list[int64_t(cap) + o1] = pack_key(ordered_key(v.y), nrow); ++o1; }
-                        if (!(v.z <= tau4.z)) { if (o2 < cap) list[int64_t(cap) * 2 + o2] = pack_key(ordered_key(v.z), nrow); ++o2; }
-                        if (!(v.w <= tau4.w)) { if (o3 < cap) list[int64_t(cap) * 3 + o3] = pack_key(ordered_key(v.w), nrow); ++o3; }
+                        v = t.bagv[h][i][lane];
+                        nrow = ~t.bagr[h][i][lane];
+                        m = unsigned(!(v.x <= tau4.x)) | (unsigned(!(v.y <= tau4.y)) << 1) | (unsigned(!(v.z <= tau4.z)) << 2) |
+                            (unsigned(!(v.w <= tau4.w)) << 3);
+                    }
+                    while (__any_sync(0xffffffffu, m != 0u)) {
+                        if (m) {
+                            const int b = __ffs(m) - 1;
+                            m &= m - 1u;
+                            const float x = b == 0 ? v.x : (b == 1 ? v.y : (b == 2 ? v.z : v.w));
+                            const int pos = b == 0 ? o0 : (b == 1 ? o1 : (b == 2 ? o2 : o3));
+                            o0 += b == 0;
+                            o1 += b == 1;
+                            o2 += b == 2;
+                            o3 += b == 3;
+                            if (pos < cap) list[int64_t(cap) * b + pos] = pack_key(ordered_key(x), nrow);
+                        }
                     }
                 }
             }
