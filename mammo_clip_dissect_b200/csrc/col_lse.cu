@@ -19,6 +19,7 @@ constexpr int kLseThreads = 128;
 __global__ void __launch_bounds__(kLseThreads)
 col_lse_partials_kernel(const float *__restrict__ L, int64_t ldl, int64_t K, int C, float *__restrict__ partials,
                         const int32_t *__restrict__ block_tab) {
+    pdl_enter();
     const int c = blockIdx.x * kLseThreads + threadIdx.x;
     const int64_t b = blockIdx.y;
     if (c >= C) return;
@@ -56,14 +57,17 @@ col_lse_partials_kernel(const float *__restrict__ L, int64_t ldl, int64_t K, int
     partials[(b * 2 + 1) * C + c] = s;
 }
 
-// 32 columns x 8 block-slices per CTA: slice s reduces blocks s, s+8, ... (independent loads in flight instead of
-// one long dependent chain), then thread (c, 0) folds the 8 slice results in slice order -- a fixed order, so the
-// result is still independent of how the neurons were sharded.
-__global__ void __launch_bounds__(256)
+// 32 columns x 32 block-slices per CTA: slice s reduces blocks s, s+32, ... (many independent loads in flight instead of
+// one long dependent chain: 128 blocks at c4 are 4 per thread), then thread (c, 0) folds the slice results in slice
+// order -- a fixed order, so the result is still independent of how the neurons were sharded.
+constexpr int kLseSlices = 32;
+
+__global__ void __launch_bounds__(32 * kLseSlices)
 lse_combine_kernel(const float *__restrict__ partials, int64_t n_blocks, int C, double log_count,
                    float *__restrict__ prob_d, const int32_t *__restrict__ seg_tab, const double *__restrict__ seg_log) {
-    __shared__ float s_max[8][33];
-    __shared__ double s_sum[8][33];
+    pdl_enter();
+    __shared__ float s_max[kLseSlices][33];
+    __shared__ double s_sum[kLseSlices][33];
     const int cx = threadIdx.x & 31, sl = threadIdx.x >> 5;
     const int c = blockIdx.x * 32 + cx;
     if (seg_tab) {       // segment (layer) blockIdx.y: its own run of blocks, its own neuron count, its own output row
@@ -73,25 +77,29 @@ lse_combine_kernel(const float *__restrict__ partials, int64_t n_blocks, int C, 
         prob_d += int64_t(blockIdx.y) * C;
     }
     float big = -INFINITY;
-    if (c < C)
-        for (int64_t b = sl; b < n_blocks; b += 8) big = fmaxf(big, partials[(b * 2) * C + c]);
+    if (c < C) {
+#pragma unroll 4
+        for (int64_t b = sl; b < n_blocks; b += kLseSlices) big = fmaxf(big, __ldg(partials + (b * 2) * C + c));
+    }
     s_max[sl][cx] = big;
     __syncthreads();
     float all = s_max[0][cx];
 #pragma unroll
-    for (int q = 1; q < 8; ++q) all = fmaxf(all, s_max[q][cx]);
+    for (int q = 1; q < kLseSlices; ++q) all = fmaxf(all, s_max[q][cx]);
     const float bs = isinf(all) ? 0.f : all;
     // block weights exp(m_b - M) in fp32 (an fp64 exp dominated this kernel), accumulation in fp64
     double total = 0.0;
-    if (c < C)
-        for (int64_t b = sl; b < n_blocks; b += 8)
-            total += double(partials[(b * 2 + 1) * C + c]) * double(expf(partials[(b * 2) * C + c] - bs));
+    if (c < C) {
+#pragma unroll 4
+        for (int64_t b = sl; b < n_blocks; b += kLseSlices)
+            total += double(__ldg(partials + (b * 2 + 1) * C + c)) * double(expf(__ldg(partials + (b * 2) * C + c) - bs));
+    }
     s_sum[sl][cx] = total;
     __syncthreads();
     if (sl == 0 && c < C) {
         double t = s_sum[0][cx];
 #pragma unroll
-        for (int q = 1; q < 8; ++q) t += s_sum[q][cx];
+        for (int q = 1; q < kLseSlices; ++q) t += s_sum[q][cx];
         prob_d[c] = static_cast<float>(double(bs) + log(t) - log_count);
     }
 }
@@ -100,6 +108,7 @@ lse_combine_kernel(const float *__restrict__ partials, int64_t n_blocks, int C, 
 __global__ void __launch_bounds__(256)
 pmi_finalize_kernel(const float *__restrict__ L, int64_t ldl, int64_t K, int C, const float *__restrict__ prob_d,
                     float lam, float *__restrict__ out, int64_t ldo) {
+    pdl_enter();
     const int c = blockIdx.x * 256 + threadIdx.x;
     if (c >= C) return;
     const float shift = __fmul_rn(lam, prob_d[c]);
@@ -110,6 +119,7 @@ pmi_finalize_kernel(const float *__restrict__ L, int64_t ldl, int64_t K, int C, 
 __global__ void __launch_bounds__(256)
 pmi_finalize_seg_kernel(const float *__restrict__ L, int64_t ldl, int C, const float *__restrict__ prob_d /*[n_seg][C]*/,
                         const int32_t *__restrict__ block_tab, float lam, float *__restrict__ out, int64_t ldo) {
+    pdl_enter();
     const int c = blockIdx.x * 256 + threadIdx.x;
     if (c >= C) return;
     const int64_t j0 = block_tab[blockIdx.y * 3 + 0], j1 = j0 + block_tab[blockIdx.y * 3 + 1];
@@ -129,6 +139,7 @@ struct PeerDests {
 __global__ void __launch_bounds__(256)
 pmi_finalize_bcast_kernel(const float *__restrict__ L, int64_t total, int C, const float *__restrict__ prob_d, float lam,
                           PeerDests dst, int n_dst) {
+    pdl_enter();
     const int64_t nvec = total / 4;
     const int64_t stride = int64_t(gridDim.x) * blockDim.x;
     int64_t e = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -172,6 +183,7 @@ __global__ void __launch_bounds__(kFinTopWarps * 32)
 pmi_finalize_topk_kernel(const float *__restrict__ L, int64_t ldl, int64_t K, int C, const float *__restrict__ prob_d,
                          const int32_t *__restrict__ row_seg, float lam, float *__restrict__ out, int64_t ldo, int t,
                          float *__restrict__ top_vals, int64_t *__restrict__ top_idx) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int64_t row = int64_t(blockIdx.x) * kFinTopWarps + (threadIdx.x >> 5);
     if (row >= K) return;
@@ -218,11 +230,11 @@ static int launch_finalize_topk(const float *L, int64_t ldl, int64_t K, int64_t 
     const unsigned grid = static_cast<unsigned>(ceil_div<int64_t>(K, kFinTopWarps));
     const int Ci = static_cast<int>(C), ti = static_cast<int>(t);
     if (C <= 32 * 8)
-        pmi_finalize_topk_kernel<8><<<grid, kFinTopWarps * 32, 0, st>>>(L, ldl, K, Ci, prob_d, row_seg, lam, out, ldo, ti, top_vals, top_idx);
+        launch_pdl((pmi_finalize_topk_kernel<8>), dim3(grid), dim3(kFinTopWarps * 32), 0, st, L, ldl, K, Ci, prob_d, row_seg, lam, out, ldo, ti, top_vals, top_idx);
     else if (C <= 32 * 24)
-        pmi_finalize_topk_kernel<24><<<grid, kFinTopWarps * 32, 0, st>>>(L, ldl, K, Ci, prob_d, row_seg, lam, out, ldo, ti, top_vals, top_idx);
+        launch_pdl((pmi_finalize_topk_kernel<24>), dim3(grid), dim3(kFinTopWarps * 32), 0, st, L, ldl, K, Ci, prob_d, row_seg, lam, out, ldo, ti, top_vals, top_idx);
     else
-        pmi_finalize_topk_kernel<32><<<grid, kFinTopWarps * 32, 0, st>>>(L, ldl, K, Ci, prob_d, row_seg, lam, out, ldo, ti, top_vals, top_idx);
+        launch_pdl((pmi_finalize_topk_kernel<32>), dim3(grid), dim3(kFinTopWarps * 32), 0, st, L, ldl, K, Ci, prob_d, row_seg, lam, out, ldo, ti, top_vals, top_idx);
     return check_launch();
 }
 
@@ -235,7 +247,7 @@ extern "C" int mcd_col_lse_partials_f32(const float *L, int64_t ldl, int64_t K, 
     const int64_t nb = ceil_div<int64_t>(K, MCD_LSE_BLOCK);
     if (nb > 65535) return MCD_ERR_UNSUPPORTED;
     dim3 grid(static_cast<unsigned>(ceil_div<int64_t>(C, kLseThreads)), static_cast<unsigned>(nb));
-    col_lse_partials_kernel<<<grid, kLseThreads, 0, static_cast<cudaStream_t>(stream)>>>(L, ldl, K, int(C), partials, nullptr);
+    launch_pdl((col_lse_partials_kernel), dim3(grid), dim3(kLseThreads), 0, static_cast<cudaStream_t>(stream), L, ldl, K, int(C), partials, nullptr);
     return check_launch();
 }
 
@@ -247,8 +259,7 @@ extern "C" int mcd_pmi_finalize_f32(const float *L, int64_t ldl, int64_t K, int6
         K_total < 1 || C > (1 << 24))
         return MCD_ERR_INVALID_ARGUMENT;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    lse_combine_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(C, 32)), 256, 0, st>>>(
-        partials_all, n_blocks_total, int(C), log(double(K_total)), prob_d_out, nullptr, nullptr);
+    launch_pdl((lse_combine_kernel), dim3(static_cast<unsigned>(ceil_div<int64_t>(C, 32))), dim3(32 * kLseSlices), 0, st, partials_all, n_blocks_total, int(C), log(double(K_total)), prob_d_out, nullptr, nullptr);
     int rc = check_launch();
     if (rc != MCD_OK) return rc;
     int64_t rows = int64_t(num_sms()) * 16 / ceil_div<int64_t>(C, 256);
@@ -256,7 +267,7 @@ extern "C" int mcd_pmi_finalize_f32(const float *L, int64_t ldl, int64_t K, int6
     if (rows > 65535) rows = 65535;
     if (rows < 1) rows = 1;
     dim3 grid(static_cast<unsigned>(ceil_div<int64_t>(C, 256)), static_cast<unsigned>(rows));
-    pmi_finalize_kernel<<<grid, 256, 0, st>>>(L, ldl, K, int(C), prob_d_out, lam, out, ldo);
+    launch_pdl((pmi_finalize_kernel), dim3(grid), dim3(256), 0, st, L, ldl, K, int(C), prob_d_out, lam, out, ldo);
     return check_launch();
 }
 
@@ -269,8 +280,7 @@ extern "C" int mcd_pmi_finalize_topk_f32(const float *L, int64_t ldl, int64_t K,
         n_blocks_total < 1 || K_total < 1)
         return MCD_ERR_INVALID_ARGUMENT;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    lse_combine_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(C, 32)), 256, 0, st>>>(
-        partials_all, n_blocks_total, int(C), log(double(K_total)), prob_d_out, nullptr, nullptr);
+    launch_pdl((lse_combine_kernel), dim3(static_cast<unsigned>(ceil_div<int64_t>(C, 32))), dim3(32 * kLseSlices), 0, st, partials_all, n_blocks_total, int(C), log(double(K_total)), prob_d_out, nullptr, nullptr);
     int rc = check_launch();
     if (rc != MCD_OK) return rc;
     return launch_finalize_topk(L, ldl, K, C, prob_d_out, nullptr, lam, out, ldo, t, top_vals_out, top_idx_out, st);
@@ -294,8 +304,7 @@ extern "C" int mcd_pmi_finalize_bcast_f32(const float *L, int64_t K, int64_t C, 
     }
     if (reinterpret_cast<uintptr_t>(L) % 16 != 0) return MCD_ERR_UNSUPPORTED;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    lse_combine_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(C, 32)), 256, 0, st>>>(
-        partials_all, n_blocks_total, int(C), log(double(K_total)), prob_d_out, nullptr, nullptr);
+    launch_pdl((lse_combine_kernel), dim3(static_cast<unsigned>(ceil_div<int64_t>(C, 32))), dim3(32 * kLseSlices), 0, st, partials_all, n_blocks_total, int(C), log(double(K_total)), prob_d_out, nullptr, nullptr);
     int rc = check_launch();
     if (rc != MCD_OK) return rc;
     const int64_t total = K * C;
@@ -314,7 +323,7 @@ extern "C" int mcd_col_lse_partials_seg_f32(const float *L, int64_t ldl, int64_t
     if (!L || !partials || !block_tab || C < 1 || ldl < C || C > (1 << 24) || n_blocks < 1) return MCD_ERR_INVALID_ARGUMENT;
     if (n_blocks > 65535) return MCD_ERR_UNSUPPORTED;
     dim3 grid(static_cast<unsigned>(ceil_div<int64_t>(C, kLseThreads)), static_cast<unsigned>(n_blocks));
-    col_lse_partials_kernel<<<grid, kLseThreads, 0, static_cast<cudaStream_t>(stream)>>>(L, ldl, 0, int(C), partials, block_tab);
+    launch_pdl((col_lse_partials_kernel), dim3(grid), dim3(kLseThreads), 0, static_cast<cudaStream_t>(stream), L, ldl, 0, int(C), partials, block_tab);
     return check_launch();
 }
 
@@ -329,11 +338,11 @@ extern "C" int mcd_pmi_finalize_seg_f32(const float *L, int64_t ldl, int64_t C, 
     if (n_blocks > 65535 || n_seg > 65535) return MCD_ERR_UNSUPPORTED;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     dim3 cgrid(static_cast<unsigned>(ceil_div<int64_t>(C, 32)), static_cast<unsigned>(n_seg));
-    lse_combine_kernel<<<cgrid, 256, 0, st>>>(partials, 0, int(C), 0.0, prob_d_out, seg_tab, seg_log_count);
+    launch_pdl((lse_combine_kernel), dim3(cgrid), dim3(32 * kLseSlices), 0, st, partials, 0, int(C), 0.0, prob_d_out, seg_tab, seg_log_count);
     int rc = check_launch();
     if (rc != MCD_OK) return rc;
     dim3 fgrid(static_cast<unsigned>(ceil_div<int64_t>(C, 256)), static_cast<unsigned>(n_blocks));
-    pmi_finalize_seg_kernel<<<fgrid, 256, 0, st>>>(L, ldl, int(C), prob_d_out, block_tab, lam, out, ldo);
+    launch_pdl((pmi_finalize_seg_kernel), dim3(fgrid), dim3(256), 0, st, L, ldl, int(C), prob_d_out, block_tab, lam, out, ldo);
     return check_launch();
 }
 
@@ -349,7 +358,7 @@ extern "C" int mcd_pmi_finalize_seg_topk_f32(const float *L, int64_t ldl, int64_
     if (n_seg > 65535) return MCD_ERR_UNSUPPORTED;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     dim3 cgrid(static_cast<unsigned>(ceil_div<int64_t>(C, 32)), static_cast<unsigned>(n_seg));
-    lse_combine_kernel<<<cgrid, 256, 0, st>>>(partials, 0, int(C), 0.0, prob_d_out, seg_tab, seg_log_count);
+    launch_pdl((lse_combine_kernel), dim3(cgrid), dim3(32 * kLseSlices), 0, st, partials, 0, int(C), 0.0, prob_d_out, seg_tab, seg_log_count);
     int rc = check_launch();
     if (rc != MCD_OK) return rc;
     return launch_finalize_topk(L, ldl, K, C, prob_d_out, row_seg, lam, out, ldo, t, top_vals_out, top_idx_out, st);

@@ -47,6 +47,31 @@ __device__ __forceinline__ unsigned long long pack_key(uint32_t hi, uint32_t lo)
     return (static_cast<unsigned long long>(hi) << 32) | lo;
 }
 
+// ---- programmatic dependent launch (the kernels of one call form a chain on one stream) ---------------------------------
+// Every kernel of the chain starts with pdl_enter(): it waits until the grid in front of it has completed and its writes
+// are visible (a no-op for a normally launched kernel), then lets the grid behind it be scheduled as soon as all CTAs of
+// this one are resident or done.  The successor's CTAs are then already on the SMs, parked in their own pdl_enter(), when
+// this grid's last CTAs retire: no launch latency and no empty-machine ramp between two dependent kernels (11 per call).
+// EVERY CTA must pass pdl_enter() before it returns or touches global memory -- the guarantee is transitive only then.
+__device__ __forceinline__ void pdl_enter() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);       // errors surface in check_launch()
+}
+
 // ---- PTX: mbarrier + bulk async copy (TMA engine, 1-D) ----------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

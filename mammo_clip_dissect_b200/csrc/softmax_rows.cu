@@ -17,6 +17,7 @@ template <int PER, int kFull>   // register-resident rows up to 32*PER columns; 
 __global__ void __launch_bounds__(kSoftmaxWarps * 32)
 softmax_rows_kernel(const float *__restrict__ P, int64_t ldp, float *__restrict__ S, int64_t lds, int64_t n_rows,
                     int n_cols, float a) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int64_t row = int64_t(blockIdx.x) * kSoftmaxWarps + (threadIdx.x >> 5);
     if (row >= n_rows) return;
@@ -73,6 +74,7 @@ softmax_rows_kernel(const float *__restrict__ P, int64_t ldp, float *__restrict_
 __global__ void __launch_bounds__(kSoftmaxWarps * 32)
 softmax_rows_wide_kernel(const float *__restrict__ P, int64_t ldp, float *__restrict__ S, int64_t lds,
                          int64_t n_rows, int64_t n_cols, float a) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int64_t row = int64_t(blockIdx.x) * kSoftmaxWarps + (threadIdx.x >> 5);
     if (row >= n_rows) return;
@@ -104,14 +106,14 @@ extern "C" int mcd_softmax_rows_f32(const float *P, int64_t ldp, float *S, int64
     const int threads = kSoftmaxWarps * 32;
     const int nc = static_cast<int>(n_cols);
     if (n_cols <= 32 * 4)
-        softmax_rows_kernel<4, 0><<<grid, threads, 0, st>>>(P, ldp, S, lds, n_rows, nc, a);
+        launch_pdl((softmax_rows_kernel<4, 0>), dim3(grid), dim3(threads), 0, st, P, ldp, S, lds, n_rows, nc, a);
     else if (n_cols <= 32 * 22)
-        softmax_rows_kernel<24, 0><<<grid, threads, 0, st>>>(P, ldp, S, lds, n_rows, nc, a);
+        launch_pdl((softmax_rows_kernel<24, 0>), dim3(grid), dim3(threads), 0, st, P, ldp, S, lds, n_rows, nc, a);
     else if (n_cols <= 32 * 24)          // the 763-concept set: 22 full register slots, bounds checks on the last two
-        softmax_rows_kernel<24, 22><<<grid, threads, 0, st>>>(P, ldp, S, lds, n_rows, nc, a);
+        launch_pdl((softmax_rows_kernel<24, 22>), dim3(grid), dim3(threads), 0, st, P, ldp, S, lds, n_rows, nc, a);
     else if (n_cols <= 32 * 64)
-        softmax_rows_kernel<64, 0><<<grid, threads, 0, st>>>(P, ldp, S, lds, n_rows, nc, a);
+        launch_pdl((softmax_rows_kernel<64, 0>), dim3(grid), dim3(threads), 0, st, P, ldp, S, lds, n_rows, nc, a);
     else
-        softmax_rows_wide_kernel<<<grid, threads, 0, st>>>(P, ldp, S, lds, n_rows, n_cols, a);
+        launch_pdl((softmax_rows_wide_kernel), dim3(grid), dim3(threads), 0, st, P, ldp, S, lds, n_rows, n_cols, a);
     return check_launch();
 }

@@ -92,6 +92,7 @@ struct FilterArgs {
 template <int ROWS>
 __global__ void __launch_bounds__(kFThreads)
 filter_scan_kernel(const __grid_constant__ CUtensorMap tmap, const FilterArgs a) {
+    pdl_enter();
     constexpr uint32_t kFTileBytes = ROWS * kFRowBytes;
     extern __shared__ __align__(1024) unsigned char fsm[];
     FilterTail &t = *reinterpret_cast<FilterTail *>(fsm + size_t(a.nstage) * kFTileBytes);
@@ -287,6 +288,7 @@ __global__ void __launch_bounds__(256)
 filter_tail_rows_kernel(const float *__restrict__ A, int64_t lda, int64_t row_begin, int64_t N, int64_t col_begin,
                         int64_t col_end, const float *__restrict__ tau, int *__restrict__ cnt,
                         unsigned long long *__restrict__ lists, int cap) {
+    pdl_enter();
     const int64_t col = col_begin + int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (col >= col_end) return;
     const float th = tau[col];
@@ -338,6 +340,7 @@ topk_select_kernel(const unsigned long long *__restrict__ lists, const int *__re
                    int64_t col_first, int64_t col_end, int64_t K, const float *__restrict__ A, int64_t lda,
                    int64_t *__restrict__ idx64, int32_t *__restrict__ idx32, float *__restrict__ vals,
                    int *__restrict__ flags) {
+    pdl_enter();
     __shared__ SelSmem sm;
     __shared__ unsigned long long sortbuf[kSelWarps][32 * PER];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

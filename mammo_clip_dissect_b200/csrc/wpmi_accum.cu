@@ -74,6 +74,7 @@ __global__ void __launch_bounds__(kAccumThreads)
 wpmi_accum_kernel(const float *__restrict__ S, int64_t lds, int C, const int32_t *__restrict__ idx, int64_t idx_ld,
                   int64_t K, int k, const float *__restrict__ p, float eps, float *__restrict__ L, int64_t ldl,
                   int n_groups) {
+    pdl_enter();
     static_assert(U == 8, "two groups of four ranks per iteration");
     constexpr int NPB = kAccumThreads / TPN;
     // the gathered rows of S are re-read ~k*K/N (33 at c4) times: ask L2 to keep them (evict-last), measured
@@ -223,13 +224,13 @@ static int launch_accum(const float *S, int64_t lds, int C, const int32_t *idx, 
     const size_t sm = size_t(NPB + 2) * size_t((k + 3) & ~3) * 4 + pad_smem;
     const int ng = static_cast<int>(n_groups);
     if (grouped && mode != 2)
-        wpmi_accum_kernel<TPN, 8, SOFT, VEC, true, true, true><<<nb, kAccumThreads, sm, st>>>(S, lds, C, idx, idx_ld, K, k, p, eps, L, ldl, ng);
+        launch_pdl((wpmi_accum_kernel<TPN, 8, SOFT, VEC, true, true, true>), dim3(nb), dim3(kAccumThreads), sm, st, S, lds, C, idx, idx_ld, K, k, p, eps, L, ldl, ng);
     else if (grouped)
-        wpmi_accum_kernel<TPN, 8, SOFT, VEC, true, true, false><<<nb, kAccumThreads, sm, st>>>(S, lds, C, idx, idx_ld, K, k, p, eps, L, ldl, ng);
+        launch_pdl((wpmi_accum_kernel<TPN, 8, SOFT, VEC, true, true, false>), dim3(nb), dim3(kAccumThreads), sm, st, S, lds, C, idx, idx_ld, K, k, p, eps, L, ldl, ng);
     else if (ftz)
-        wpmi_accum_kernel<TPN, 8, SOFT, VEC, true, false, false><<<nb, kAccumThreads, sm, st>>>(S, lds, C, idx, idx_ld, K, k, p, eps, L, ldl, ng);
+        launch_pdl((wpmi_accum_kernel<TPN, 8, SOFT, VEC, true, false, false>), dim3(nb), dim3(kAccumThreads), sm, st, S, lds, C, idx, idx_ld, K, k, p, eps, L, ldl, ng);
     else
-        wpmi_accum_kernel<TPN, 8, SOFT, VEC, false, false, false><<<nb, kAccumThreads, sm, st>>>(S, lds, C, idx, idx_ld, K, k, p, eps, L, ldl, ng);
+        launch_pdl((wpmi_accum_kernel<TPN, 8, SOFT, VEC, false, false, false>), dim3(nb), dim3(kAccumThreads), sm, st, S, lds, C, idx, idx_ld, K, k, p, eps, L, ldl, ng);
     return check_launch();
 }
 
