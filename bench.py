@@ -263,12 +263,17 @@ def sharded_parity(similarity, mdist, dev, world, rank):
     shard = A[:, b[rank]:b[rank + 1]].contiguous()
     res = {}
     backend = mdist.CudaBackend(dev)
-    modes = ["nccl", "copy", "fused"]
+    modes = ["nccl", "copy", "fused", "peer_partials+nccl", "peer_partials+copy"]
     for mode in modes:
         try:
-            ex = None if mode == "nccl" else mdist.PeerScoreExchange(sizes, C, dev, mode=mode)
-            got = mdist.soft_wpmi_sharded(P, shard, sizes, top_k=TOP_K, device=dev, backend=backend, exchange=ex)
-            ok = int(torch.equal(got, want))
+            score_mode = mode.split("+")[-1]
+            ex = None if score_mode == "nccl" else mdist.PeerScoreExchange(sizes, C, dev, mode=score_mode)
+            pex = mdist.PeerPartialsExchange(sizes, C, dev) if mode.startswith("peer_partials") else None
+            ok = 1
+            for _ in range(3 if pex is not None else 1):      # the partials tables alternate: go round more than once
+                got = mdist.soft_wpmi_sharded(P, shard, sizes, top_k=TOP_K, device=dev, backend=backend, exchange=ex,
+                                              partials_exchange=pex)
+                ok = min(ok, int(torch.equal(got, want)))
         except Exception as exc:                              # no symmetric memory on this box: reported, not hidden
             sys.stderr.write("rank %d: exchange mode %s unavailable: %s\n" % (rank, mode, str(exc)[:200]))
             ok = -1
@@ -276,7 +281,11 @@ def sharded_parity(similarity, mdist, dev, world, rank):
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         res[mode] = {1: "bit-identical to the single-GPU call on every rank", 0: "MISMATCH", -1: "unavailable"}[int(t.item())]
         torch.cuda.synchronize(dev)
-    local = mdist.soft_wpmi_sharded(P, shard, sizes, top_k=TOP_K, device=dev, backend=backend, gather_scores=False)
+    pex = None
+    if res.get("peer_partials+nccl", "").startswith("bit-identical"):
+        pex = mdist.PeerPartialsExchange(sizes, C, dev)
+    local = mdist.soft_wpmi_sharded(P, shard, sizes, top_k=TOP_K, device=dev, backend=backend, gather_scores=False,
+                                    partials_exchange=pex)
     t = torch.tensor([int(torch.equal(local, want[b[rank]:b[rank + 1]]))], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     res["own_shard_only"] = "bit-identical" if int(t.item()) == 1 else "MISMATCH"
@@ -352,13 +361,28 @@ def run_ours(args):
         if int(flag.item()) == 0:
             exchange, xmode = None, "nccl"
 
+    # the LSE partials go through symmetric memory too (one small kernel + the signal-pad barrier instead of an NCCL
+    # all_gather); MCD_PARTIALS=nccl keeps the collective
+    pexchange, pmode = None, os.environ.get("MCD_PARTIALS", "peer")
+    if world > 1 and pmode != "nccl":
+        try:
+            pexchange = mdist.PeerPartialsExchange(sizes, C_CONCEPTS, dev)
+            ok = 1
+        except Exception as exc:
+            sys.stderr.write("rank %d: peer partials exchange unavailable (%s); using NCCL all_gather\n" % (rank, exc))
+            ok = 0
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            pexchange, pmode = None, "nccl"
+
     def step(P_in, A_in, gather=False):
         """One full soft_wpmi over the 32768 neurons: every rank ends with its finalized [K/N, C] shard (gather=False) or
         with the whole [K, C] matrix."""
         if world == 1:
             return similarity.soft_wpmi(P_in, A_in, top_k=TOP_K, device=dev)
         return mdist.soft_wpmi_sharded(P_in, A_in, sizes, top_k=TOP_K, device=dev, backend=backend, gather_scores=gather,
-                                       exchange=exchange if gather else None)
+                                       exchange=exchange if gather else None, partials_exchange=pexchange)
 
     def timed(fn, steps, warm):
         for _ in range(warm):
@@ -430,7 +454,11 @@ def run_ours(args):
         torch.cuda.empty_cache()
         A = torch.randn(N_IMG, K_NEURONS, generator=torch.Generator(device=dev).manual_seed(2 + 1000 * rank), device=dev)
         wsizes = [K_NEURONS] * world
-        wfn = lambda: mdist.soft_wpmi_sharded(P, A, wsizes, top_k=TOP_K, device=dev, backend=backend, gather_scores=False)  # noqa: E731
+        wpex = None
+        if pexchange is not None:
+            wpex = mdist.PeerPartialsExchange(wsizes, C_CONCEPTS, dev)
+        wfn = lambda: mdist.soft_wpmi_sharded(P, A, wsizes, top_k=TOP_K, device=dev, backend=backend, gather_scores=False,  # noqa: E731
+                                              partials_exchange=wpex)
         wsampler = ClockSampler(local_rank)
         if rank == 0:
             wsampler.start()
@@ -541,6 +569,9 @@ def run_ours(args):
     ach_path = alg_path / (ms_step / 1e3) / 1e9
     cfg = workload_config(world)
     cfg["score_exchange"] = "none (one GPU)" if world == 1 else "shards stay on their rank in `value`; see with_score_exchange"
+    if world > 1:
+        cfg["partials_exchange"] = ("symmetric-memory stores + signal-pad barrier" if pexchange is not None
+                                    else "NCCL all_gather")
     line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": warm, "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,

@@ -152,6 +152,11 @@ int mcd_pmi_finalize_bcast_f32(const float *L, int64_t K, int64_t C, const float
                                int64_t n_blocks_total, int64_t K_total, float lam,
                                float *prob_d_out, float *const *dest_bases, int n_dest,
                                int64_t row_offset, mcd_stream_t stream);
+/* n floats of src to dest_bases[p] + dest_offset for every p (device pointers: peer-mapped buffers and / or local ones).
+ * The multi-GPU exchange of the LSE partials: every rank stores its [blocks_g, 2, C] slice into all ranks' tables, then
+ * the ranks meet at a symmetric-memory barrier.  No reference counterpart (the reference is single-GPU). */
+int mcd_bcast_f32(const float *src, int64_t n, float *const *dest_bases, int n_dest, int64_t dest_offset,
+                  mcd_stream_t stream);
 
 /* ---- K3b's finalize fused with the per-neuron top concepts: out = L - lam log p(d) as above, and in the same pass
  *      (a warp per neuron row, the finalized values still in registers) the t <= 64 best (value, concept) pairs of

@@ -37,6 +37,7 @@ SIGNATURES = {
     "mcd_wpmi_accum_prob_f32": (_i32, [_p, _i64, _i64, _i64, _p, _i64, _i64, _p, _f32, _p, _i64, _p]),
     "mcd_col_lse_partials_f32": (_i32, [_p, _i64, _i64, _i64, _p, _p]),
     "mcd_pmi_finalize_f32": (_i32, [_p, _i64, _i64, _i64, _p, _i64, _i64, _f32, _p, _p, _i64, _p]),
+    "mcd_bcast_f32": (_i32, [_p, _i64, _p, _i32, _i64, _p]),
     "mcd_pmi_finalize_bcast_f32": (_i32, [_p, _i64, _i64, _p, _i64, _i64, _f32, _p, _p, _i32, _i64, _p]),
     "mcd_pmi_scores_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64]),
     "mcd_pmi_scores_f32": (_i32, [_p, _i64, _p, _i64, _i64, _i64, _i64, _i64, _f32, _f32, _p, _f32, _p, _i64, _p, _sz, _p]),

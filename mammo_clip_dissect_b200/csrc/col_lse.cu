@@ -171,6 +171,21 @@ pmi_finalize_bcast_kernel(const float *__restrict__ L, int64_t total, int C, con
     }
 }
 
+// n floats to the same offset of several buffers (this rank's LSE partials into every peer's [blocks, 2, C] table through
+// peer-mapped memory: replaces an NCCL all_gather of a few kilobytes, whose launch and protocol latency -- ~60 us -- is a
+// tenth of a rank's whole step at 8 GPUs, by one small kernel + the symmetric-memory barrier).
+__global__ void __launch_bounds__(256)
+bcast_kernel(const float *__restrict__ src, int64_t n, PeerDests dst, int n_dst) {
+    pdl_enter();
+    const int64_t stride = int64_t(gridDim.x) * blockDim.x;
+    for (int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float v = __ldg(src + i);
+#pragma unroll
+        for (int p = 0; p < kMaxPeers; ++p)
+            if (p < n_dst) dst.ptr[p][i] = v;
+    }
+}
+
 // K3b's finalize fused with the callers' per-neuron top concepts (describe_broad_neurons.py:101: torch.topk(sim, 10, 1);
 // describe_clip_neurons.py:64: torch.max(sim, 1)): one warp per neuron row computes out = L - lam * log p(d) (the same
 // two roundings as pmi_finalize_kernel), stores the row, and -- the values still in registers -- emits the row's t
@@ -362,4 +377,18 @@ extern "C" int mcd_pmi_finalize_seg_topk_f32(const float *L, int64_t ldl, int64_
     int rc = check_launch();
     if (rc != MCD_OK) return rc;
     return launch_finalize_topk(L, ldl, K, C, prob_d_out, row_seg, lam, out, ldo, t, top_vals_out, top_idx_out, st);
+}
+
+extern "C" int mcd_bcast_f32(const float *src, int64_t n, float *const *dest_bases, int n_dest, int64_t dest_offset,
+                             mcd_stream_t stream) {
+    using namespace mcd;
+    if (!src || !dest_bases || n < 1 || n_dest < 1 || n_dest > kMaxPeers || dest_offset < 0) return MCD_ERR_INVALID_ARGUMENT;
+    PeerDests dst;
+    for (int p = 0; p < kMaxPeers; ++p) dst.ptr[p] = p < n_dest ? dest_bases[p] + dest_offset : nullptr;
+    for (int p = 0; p < n_dest; ++p)
+        if (!dest_bases[p]) return MCD_ERR_INVALID_ARGUMENT;
+    int64_t blocks = ceil_div<int64_t>(n, 256);
+    if (blocks > 4 * int64_t(num_sms())) blocks = 4 * int64_t(num_sms());
+    launch_pdl((bcast_kernel), dim3(static_cast<unsigned>(blocks)), dim3(256), 0, static_cast<cudaStream_t>(stream), src, n, dst, n_dest);
+    return check_launch();
 }

@@ -191,6 +191,43 @@ class PeerScoreExchange:
         return out.wait() if wait else out
 
 
+class PeerPartialsExchange:
+    """The all-gather of the LSE partials through symmetric memory: every rank stores its [blocks_g, 2, C] slice into all
+    ranks' [blocks_total, 2, C] tables with one small kernel (NVLink stores) and the ranks meet at the signal-pad
+    barrier.  Two tables used in turn: a rank may still be combining table b of call i while a faster rank already writes
+    table b ^ 1 of call i + 1; nobody can write table b again before every rank has passed the barrier of call i + 1, i.e.
+    has finished call i.  Same values as the NCCL all_gather (a copy), so the result stays bit-identical."""
+
+    def __init__(self, shard_sizes: Sequence[int], C: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        self.sizes = [int(x) for x in shard_sizes]
+        self.nblocks = [(s + LSE_BLOCK - 1) // LSE_BLOCK for s in self.sizes]
+        self.C = int(C)
+        self.device = torch.device(device)
+        self.blk0 = sum(self.nblocks[: self.rank])
+        self.total = sum(self.nblocks)
+        self.bufs, self.hdls = [], []
+        for _ in range(2):
+            t = symm_mem.empty((self.total, 2, self.C), dtype=torch.float32, device=self.device)
+            self.hdls.append(symm_mem.rendezvous(t, self.group))
+            self.bufs.append(t)
+        self.turn = 0
+
+    def gather(self, part, sim):
+        b = self.turn
+        self.turn ^= 1
+        hdl, buf = self.hdls[b], self.bufs[b]
+        with torch.no_grad(), torch.cuda.device(self.device):
+            if part.shape[0] != self.nblocks[self.rank] or (part.shape[0] and part.shape[2] != self.C):
+                raise RuntimeError("PeerPartialsExchange was built for other shard sizes")
+            if part.shape[0] > 0:
+                sim.bcast_rows(part.contiguous(), list(hdl.buffer_ptrs), self.blk0 * 2 * self.C)
+            hdl.barrier(channel=0)
+        return buf
+
+
 def _all_gather_var(t: torch.Tensor, sizes: Sequence[int], group) -> torch.Tensor:
     """all_gather of tensors whose leading dimension differs per rank (sizes known to all ranks)."""
     world = dist.get_world_size(group)
@@ -207,13 +244,15 @@ def _all_gather_var(t: torch.Tensor, sizes: Sequence[int], group) -> torch.Tenso
 
 
 def pmi_scores_sharded(clip_feats, target_shard, shard_sizes: Sequence[int], top_k, a, lam, min_prob, ramp,
-                       backend, group=None, gather_scores: bool = True, exchange=None, wait: bool = True):
+                       backend, group=None, gather_scores: bool = True, exchange=None, wait: bool = True,
+                       partials_exchange=None):
     """Scores for this rank's neurons (and, with gather_scores, for all neurons [K, C]).
 
     target_shard : [N, K_g] activations of this rank's neurons
     shard_sizes  : K_g of every rank, in rank order (interior boundaries multiples of 256)
     exchange     : a PeerScoreExchange for the score all-gather (default: NCCL all_gather); with wait=False the
                    result is a GatheredScores handle
+    partials_exchange : a PeerPartialsExchange for the all-gather of the LSE partials (default: NCCL all_gather)
     """
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
@@ -236,7 +275,12 @@ def pmi_scores_sharded(clip_feats, target_shard, shard_sizes: Sequence[int], top
         L = backend.log_sums(clip_feats, target_shard, top_k, a, min_prob, ramp)
         part = backend.lse_partials(L)
     nblocks = [(s + LSE_BLOCK - 1) // LSE_BLOCK for s in shard_sizes]
-    part_all = _all_gather_var(part, nblocks, group) if world > 1 else part
+    if world > 1 and partials_exchange is not None:
+        if list(partials_exchange.sizes) != [int(x) for x in shard_sizes] or partials_exchange.C != C:
+            raise RuntimeError("PeerPartialsExchange was built for other shard sizes")
+        part_all = partials_exchange.gather(part, backend.sim)
+    else:
+        part_all = _all_gather_var(part, nblocks, group) if world > 1 else part
     if exchange is not None and gather_scores and world > 1:
         if list(exchange.sizes) != [int(x) for x in shard_sizes] or exchange.C != L.shape[1]:
             raise RuntimeError("PeerScoreExchange was built for other shard sizes")
@@ -253,17 +297,17 @@ def pmi_scores_sharded(clip_feats, target_shard, shard_sizes: Sequence[int], top
 
 def soft_wpmi_sharded(clip_feats, target_shard, shard_sizes, top_k=100, a=10, lam=1, device='cuda',
                       min_prob=1e-7, p_start=0.998, p_end=0.97, group=None, gather_scores=True, backend=None,
-                      exchange=None, wait=True):
+                      exchange=None, wait=True, partials_exchange=None):
     """Neuron-sharded soft_wpmi (reference similarity.py:49-73 semantics over the union of shards)."""
     from .similarity import _reference_ramp
     backend = backend or CudaBackend(device)
     return pmi_scores_sharded(clip_feats, target_shard, shard_sizes, top_k, a, lam, min_prob,
                               _reference_ramp(int(top_k), p_start, p_end), backend, group, gather_scores,
-                              exchange, wait)
+                              exchange, wait, partials_exchange)
 
 
 def wpmi_sharded(clip_feats, target_shard, shard_sizes, top_k=28, a=2, lam=0.6, device='cuda', min_prob=1e-7,
-                 group=None, gather_scores=True, backend=None, exchange=None, wait=True):
+                 group=None, gather_scores=True, backend=None, exchange=None, wait=True, partials_exchange=None):
     backend = backend or CudaBackend(device)
     return pmi_scores_sharded(clip_feats, target_shard, shard_sizes, top_k, a, lam, min_prob, None, backend, group,
-                              gather_scores, exchange, wait)
+                              gather_scores, exchange, wait, partials_exchange)

@@ -286,6 +286,20 @@ def pmi_finalize_bcast(L, partials_all, K_total, lam, dest_ptrs, row_offset):
     return prob_d
 
 
+def bcast_rows(src, dest_ptrs, dest_offset):
+    """src (contiguous fp32 CUDA tensor) to element offset `dest_offset` of every buffer in dest_ptrs (device pointers:
+    the peers' symmetric buffers and this rank's own)."""
+    import ctypes
+    if not src.is_contiguous() or src.dtype != torch.float32 or not src.is_cuda:
+        raise RuntimeError("bcast_rows needs a contiguous fp32 CUDA tensor")
+    if src.numel() == 0:
+        return
+    with torch.cuda.device(src.device):
+        arr = (ctypes.c_void_p * len(dest_ptrs))(*[int(p) for p in dest_ptrs])
+        _lib.check(_lib.lib().mcd_bcast_f32(_ptr(src), src.numel(), arr, len(dest_ptrs), int(dest_offset), _stream(src.device)),
+                   "mcd_bcast_f32")
+
+
 def pmi_logsums(clip_feats, target_feats, top_k, a, device, min_prob, ramp):
     """(L [K, C], partials [ceil(K/256), 2, C]) of one device's neurons behind one FFI entry point
     (mcd_pmi_logsums_f32: softmax -> column top-k -> gather / log-sum -> block partials, column chunks pipelined) --
