@@ -294,6 +294,26 @@ def sharded_parity(similarity, mdist, dev, world, rank):
     return res
 
 
+def bind_to_gpu_cpus(local_rank):
+    """Several ranks stream gigabytes from pinned host memory at once (the e2e leg): run this rank on the CPUs next to its
+    GPU, so that the pages it pins are first touched -- and therefore placed -- on that NUMA node.  Returns a short
+    description, or None when NVML does not say (nothing is changed then)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return "%d CPUs next to GPU %d" % (len(cpus), local_rank)
+    except Exception:
+        return None
+
+
 def run_ours(args):
     from mammo_clip_dissect_b200 import _lib, similarity
     from mammo_clip_dissect_b200 import distributed as mdist
@@ -308,6 +328,7 @@ def run_ours(args):
         raise SystemExit("--gpus must divide %d" % N_PIECES)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_cpus(local_rank) if world > 1 else None      # pinned host buffers on the GPU's own NUMA node
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -511,7 +532,7 @@ def run_ours(args):
         e2e = {"value": round(K_NEURONS / (ms_e2e / 1e3), 1), "unit": UNIT,
                "h2d_bytes_per_step": int(P_h.numel() * 4 + A_h.numel() * 4), "d2h_bytes_per_step": int(res_h.numel() * 4),
                "ms_per_step": round(ms_e2e, 3), "steps": e2e_steps,
-               "pcie_h2d_gbs_plain_copy": round(A_h.numel() * 4 / pcie_ms / 1e6, 1),
+               "pcie_h2d_gbs_plain_copy": round(A_h.numel() * 4 / pcie_ms / 1e6, 1), "cpu_binding": numa,
                "note": "PCIe-bound: per rank %.2f GB in, %.3f GB out per step; the scoring itself is %.1f ms of it"
                        % ((P_h.numel() + A_h.numel()) * 4 / 1e9, res_h.numel() * 4 / 1e9, ms_step),
                "api": ("similarity.soft_wpmi" if world == 1 else "distributed.soft_wpmi_sharded(gather_scores=False)") +

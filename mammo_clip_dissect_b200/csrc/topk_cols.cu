@@ -448,7 +448,11 @@ sample_tilemax_kernel(const float *__restrict__ A, int64_t lda, int64_t K, int64
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t c = int64_t(blockIdx.x) * kSampleCols + lane * 4;
     const int64_t r0 = int64_t(blockIdx.y) * tile_row_stride;
-    uint32_t m[4] = {0u, 0u, 0u, 0u};
+    // the maximum in float arithmetic (fmaxf drops NaN) and a NaN flag beside it: 3 instructions per element instead of the
+    // 8 of an ordered-key maximum; the key is formed once per column at the end (NaN counts as the largest value)
+    float fm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    bool nan_seen[4] = {false, false, false, false};
+#pragma unroll
     for (int r = warp; r < kSampleRows; r += kSampleThreads / 32) {
         const float *src = A + (r0 + r) * lda + c;
         float v[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -461,10 +465,13 @@ sample_tilemax_kernel(const float *__restrict__ A, int64_t lda, int64_t K, int64
                 if (c + e < K) v[e] = __ldg(src + e);
         }
 #pragma unroll
-        for (int e = 0; e < 4; ++e) m[e] = max(m[e], ordered_key(v[e]));
+        for (int e = 0; e < 4; ++e) {
+            fm[e] = fmaxf(fm[e], v[e]);
+            nan_seen[e] |= v[e] != v[e];
+        }
     }
 #pragma unroll
-    for (int e = 0; e < 4; ++e) red[warp][lane * 4 + e] = m[e];
+    for (int e = 0; e < 4; ++e) red[warp][lane * 4 + e] = nan_seen[e] ? 0xFFFFFFFFu : ordered_key(fm[e]);
     __syncthreads();
     if (threadIdx.x < kSampleCols) {
         uint32_t best = red[0][threadIdx.x];
