@@ -52,6 +52,9 @@ def test_workspace_queries_are_pure_host_functions(lib):
     assert lib.mcd_pool_nchw_workspace_bytes(4, 24, 760, 456) > 0      # large planes are split
     assert lib.mcd_pool_nchw_workspace_bytes(64, 512, 12, 9) == 0      # small planes, many of them: no partials in either memory order
     assert lib.mcd_gemm_nt_softmax_workspace_bytes(2000, 763, 512) >= (2000 + 763) * 4
+    # rank_reorder: baseline partials + the [K, C] denominators + the shuffles' working arrays
+    assert lib.mcd_rank_reorder_workspace_bytes(512, 250, 763) >= 512 * 5 * 4 + 512 * 763 * 4 + 512 * 5 * 250 * 4
+    assert lib.mcd_rank_reorder_workspace_bytes(0, 250, 763) == 0
 
 
 def test_argument_validation_happens_before_any_launch(lib):
@@ -61,6 +64,10 @@ def test_argument_validation_happens_before_any_launch(lib):
     assert lib.mcd_wpmi_accum_f32(None, 4, 4, 4, None, 1, 1, None, 1e-7, None, 4, None) == -1
     assert lib.mcd_pool_nchw(None, 0, 1, 1, 1, 1, 0, None, None, 0, None) == -1
     assert lib.mcd_set_tunable(b"no_such_knob", 1) == -1
+    assert lib.mcd_mt19937_draws(None, 10, None, None) == -1
+    assert lib.mcd_bcast_f32(None, 4, None, 1, 0, None) == -1
+    assert lib.mcd_rank_errors_f32(None, 4, 4, 4, None, None, 1, 1, 3.0, 0.5, None, 0, None, 4, None) == -1
+    assert lib.mcd_rank_finish_f32(1, 4, 1, None, 0, None, 4, None) == -1
     assert lib.mcd_launch_count() == n0
 
 
