@@ -38,6 +38,7 @@ constexpr size_t kTcSmemBytes = size_t(kGemmStages) * kStageBytes + 1024 /*align
 __global__ void __launch_bounds__(256)
 prepare_rows_kernel(const float *__restrict__ X, int64_t ldx, int64_t R, int64_t D, int normalize,
                     float *__restrict__ Xhi, float *__restrict__ Xlo, int64_t Rpad, int64_t Dpad) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int64_t r = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
     if (r >= Rpad) return;
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                    const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
                    int64_t M, int64_t Nn, int num_kb, float *__restrict__ P, int64_t ldp) {
+    pdl_enter();
     extern __shared__ unsigned char smem_dyn[];
     // 128-byte swizzle needs 1024-byte aligned tiles
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
@@ -258,6 +260,7 @@ gemm_tf32x3_band_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid
                         const __grid_constant__ CUtensorMap mapBhi, const __grid_constant__ CUtensorMap mapBlo,
                         int64_t M, int64_t Nn, int num_kb, int n_tiles, float *__restrict__ P, int64_t ldp,
                         float *__restrict__ S, int64_t lds, float a) {
+    pdl_enter();
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     unsigned char *aligned = smem_dyn + (base - smem_u32(smem_dyn));
@@ -427,20 +430,28 @@ enum { kPrepCos = 1, kPrepCos3 = 2 };
 // for the 763-concept matrix): grid (column groups of 32, row chunks); a block reduces its chunk over 8 row lanes and
 // writes one partial per column, part[chunk][column]; consumers add the chunks in order (fixed order: deterministic).
 //   STAT 0: sum x                      STAT 1: sum x^2                      STAT 2: sum ((x - mean)^3)^2
+struct ColSrc {
+    const float *X;            // [N, M] row-major
+    int64_t ldx, M;
+    const float *sum_part;     // STAT 2: the folded column sums (row 0)
+    float *part;               // [chunks][M]
+};
+
+// both matrices of the call in one launch: blockIdx.z picks the source (the narrower one leaves its surplus CTAs idle)
 template <int STAT>
 __global__ void __launch_bounds__(256)
-col_partial_kernel(const float *__restrict__ X, int64_t ldx, int64_t N, int64_t M, int64_t rows_per_chunk,
-                   const float *__restrict__ sum_part, int n_chunks, float *__restrict__ part) {
+col_partial_kernel(ColSrc s0, ColSrc s1, int64_t N, int64_t rows_per_chunk) {
+    pdl_enter();
     __shared__ float red[8][33];
+    const ColSrc &src = blockIdx.z == 0 ? s0 : s1;
+    const float *__restrict__ X = src.X;
+    const int64_t ldx = src.ldx, M = src.M;
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
     const int64_t m = int64_t(blockIdx.x) * 32 + cx;
+    if (int64_t(blockIdx.x) * 32 >= M) return;
     const int64_t r0 = int64_t(blockIdx.y) * rows_per_chunk, r1 = min(N, r0 + rows_per_chunk);
     float mean = 0.f;
-    if (STAT == 2 && m < M) {
-        float t = 0.f;
-        for (int q = 0; q < n_chunks; ++q) t += sum_part[int64_t(q) * M + m];
-        mean = t / static_cast<float>(N);
-    }
+    if (STAT == 2 && m < M) mean = (0.f + src.sum_part[m]) / static_cast<float>(N);
     float s = 0.f;
     if (m < M)
         for (int64_t i = r0 + ry; i < r1; i += 8) {
@@ -457,8 +468,24 @@ col_partial_kernel(const float *__restrict__ X, int64_t ldx, int64_t N, int64_t 
         float t = red[0][cx];
 #pragma unroll
         for (int q = 1; q < 8; ++q) t += red[q][cx];
-        part[int64_t(blockIdx.y) * M + m] = t;
+        src.part[int64_t(blockIdx.y) * M + m] = t;
     }
+}
+
+// part[0][m] = sum over the chunks of part[q][m], in chunk order (the sum every consumer used to redo per CTA: the 157
+// row-tile CTAs of a column block each re-added 37 partials per column before touching their 1024 elements -- 34 us for a
+// 31 MB transpose at c5).  Consumers then read one row: 0 + total == total, the same bits as before.  Both matrices in one
+// launch (blockIdx.y).
+__global__ void __launch_bounds__(256)
+col_fold_kernel(float *__restrict__ part0, int64_t M0, float *__restrict__ part1, int64_t M1, int n_chunks) {
+    pdl_enter();
+    float *part = blockIdx.y == 0 ? part0 : part1;
+    const int64_t M = blockIdx.y == 0 ? M0 : M1;
+    const int64_t m = int64_t(blockIdx.x) * 256 + threadIdx.x;
+    if (m >= M) return;
+    float t = 0.f;
+    for (int q = 0; q < n_chunks; ++q) t += part[int64_t(q) * M + m];
+    part[m] = t;
 }
 
 template <int MODE>
@@ -466,6 +493,7 @@ __global__ void __launch_bounds__(256)
 prepare_cols_kernel(const float *__restrict__ X, int64_t ldx, int64_t N, int64_t M, const float *__restrict__ sum_part,
                     const float *__restrict__ sq_part, int n_chunks, int64_t part_ld, float min_norm,
                     float *__restrict__ Thi, float *__restrict__ Tlo, int64_t Npad) {
+    pdl_enter();
     __shared__ float s_hi[32][33], s_lo[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int64_t m0 = int64_t(blockIdx.x) * 32, i0 = int64_t(blockIdx.y) * 32;
@@ -514,6 +542,7 @@ prepare_cols_kernel(const float *__restrict__ X, int64_t ldx, int64_t N, int64_t
 __global__ void __launch_bounds__(256)
 splitk_combine_kernel(const float *__restrict__ part, int splits, int64_t M, int64_t Nn, int64_t ldpart, int64_t plane,
                       float *__restrict__ out, int64_t ldo) {
+    pdl_enter();
     const int64_t n = int64_t(blockIdx.x) * 256 + threadIdx.x, m = blockIdx.y;
     if (n >= Nn) return;
     float t = part[m * ldpart + n];
@@ -539,6 +568,7 @@ gemm_tf32x3_long_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid
                         int64_t M, int64_t Nn, int total_kb, int kb_per_split, float *__restrict__ Cout, int64_t ldc,
                         int64_t split_plane, int tiles_per_cta, int n_tiles_total, float a, float *__restrict__ row_stats,
                         int terms) {
+    pdl_enter();
     extern __shared__ unsigned char smem_dyn[];
     const uint32_t base = (smem_u32(smem_dyn) + 1023u) & ~1023u;
     unsigned char *aligned = smem_dyn + (base - smem_u32(smem_dyn));
@@ -707,6 +737,7 @@ gemm_tf32x3_long_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid
 __global__ void __launch_bounds__(256)
 softmax_from_stats_kernel(const float *__restrict__ P, int64_t ldp, const float *__restrict__ row_stats, int64_t n_rows,
                           int n_cols, float a, float *__restrict__ S, int64_t lds) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int64_t row = int64_t(blockIdx.x) * 8 + (threadIdx.x >> 5);
     if (row >= n_rows) return;
@@ -773,15 +804,14 @@ int sim_matrix_tc(const float *I, int64_t ldi, const float *T, int64_t ldt, int6
     if (!make_operand_map(&mAhi, Ihi, Np, Dp, kBM) || !make_operand_map(&mAlo, Ilo, Np, Dp, kBM) ||
         !make_operand_map(&mBhi, Thi, Cp, Dp, kBN) || !make_operand_map(&mBlo, Tlo, Cp, Dp, kBN))
         return MCD_ERR_UNSUPPORTED;
-    prepare_rows_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(Np, 8)), 256, 0, st>>>(I, ldi, N, D, normalize_rows, Ihi, Ilo, Np, Dp);
-    prepare_rows_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(Cp, 8)), 256, 0, st>>>(T, ldt, C, D, normalize_rows, Thi, Tlo, Cp, Dp);
+    launch_pdl((prepare_rows_kernel), dim3(static_cast<unsigned>(ceil_div<int64_t>(Np, 8))), dim3(256), 0, st, I, ldi, N, D, normalize_rows, Ihi, Ilo, Np, Dp);
+    launch_pdl((prepare_rows_kernel), dim3(static_cast<unsigned>(ceil_div<int64_t>(Cp, 8))), dim3(256), 0, st, T, ldt, C, D, normalize_rows, Thi, Tlo, Cp, Dp);
     count_launch(2);
     const int n_tiles = static_cast<int>(Cp / kBN), num_kb = static_cast<int>(Dp / kBK);
     if (kind == 3 && S != nullptr) {
         if (cudaFuncSetAttribute(gemm_tf32x3_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTcSmemBytes)) != cudaSuccess)
             return MCD_ERR_CUDA;
-        gemm_tf32x3_band_kernel<<<static_cast<unsigned>(Np / kBM), kTcThreads, kTcSmemBytes, st>>>(
-            mAhi, mAlo, mBhi, mBlo, N, C, num_kb, n_tiles, P, ldp, S, lds, a);
+        launch_pdl((gemm_tf32x3_band_kernel), dim3(static_cast<unsigned>(Np / kBM)), dim3(kTcThreads), kTcSmemBytes, st, mAhi, mAlo, mBhi, mBlo, N, C, num_kb, n_tiles, P, ldp, S, lds, a);
         *S_done = 1;
         return check_launch();
     }
@@ -789,7 +819,7 @@ int sim_matrix_tc(const float *I, int64_t ldi, const float *T, int64_t ldt, int6
         if (cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTcSmemBytes)) != cudaSuccess)
             return MCD_ERR_CUDA;
         dim3 grid(static_cast<unsigned>(n_tiles), static_cast<unsigned>(Np / kBM));
-        gemm_tf32x3_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(mAhi, mAlo, mBhi, mBlo, N, C, num_kb, P, ldp);
+        launch_pdl((gemm_tf32x3_kernel), dim3(grid), dim3(kTcThreads), kTcSmemBytes, st, mAhi, mAlo, mBhi, mBlo, N, C, num_kb, P, ldp);
         return check_launch();
     }
     if (cudaFuncSetAttribute(gemm_tf32x3_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTcSmemBytes)) != cudaSuccess)
@@ -803,12 +833,12 @@ int sim_matrix_tc(const float *I, int64_t ldi, const float *T, int64_t ldt, int6
     if (stats) tiles_per_cta = n_tiles;
     else if (tpc > 0 && tpc <= n_tiles) tiles_per_cta = static_cast<int>(tpc);
     dim3 grid(static_cast<unsigned>(ceil_div<int64_t>(n_tiles, tiles_per_cta)), static_cast<unsigned>(Np / kBM), 1);
-    gemm_tf32x3_long_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(mAhi, mAlo, mBhi, mBlo, N, C, num_kb, num_kb, P, ldp, 0,
+    launch_pdl((gemm_tf32x3_long_kernel), dim3(grid), dim3(kTcThreads), kTcSmemBytes, st, mAhi, mAlo, mBhi, mBlo, N, C, num_kb, num_kb, P, ldp, 0,
                                                                     tiles_per_cta, n_tiles, a, stats ? row_stats : nullptr,
                                                                     tunable(kGemmDebugTerms) == 1 ? 1 : 3);
     int rc = check_launch();
     if (rc != MCD_OK || !stats) return rc;
-    softmax_from_stats_kernel<<<static_cast<unsigned>(ceil_div<int64_t>(N, 8)), 256, 0, st>>>(P, ldp, row_stats, N, int(C), a, S, lds);
+    launch_pdl((softmax_from_stats_kernel), dim3(static_cast<unsigned>(ceil_div<int64_t>(N, 8))), dim3(256), 0, st, P, ldp, row_stats, N, int(C), a, S, lds);
     *S_done = 1;
     return check_launch();
 }
@@ -856,10 +886,10 @@ static CosLayout cos_layout(int64_t N, int64_t K, int64_t C) {
 size_t cos_similarity_tc_workspace(int64_t N, int64_t K, int64_t C) { return cos_layout(N, K, C).total; }
 
 template <int STAT>
-static int launch_col_partial(const float *X, int64_t ldx, int64_t N, int64_t M, const CosLayout &l, const float *sum_part,
-                              float *part, cudaStream_t st) {
-    dim3 grid(static_cast<unsigned>(ceil_div<int64_t>(M, 32)), static_cast<unsigned>(l.chunks));
-    col_partial_kernel<STAT><<<grid, 256, 0, st>>>(X, ldx, N, M, l.rows_per_chunk, sum_part, l.chunks, part);
+static int launch_col_partial(const ColSrc &s0, const ColSrc &s1, int64_t N, const CosLayout &l, cudaStream_t st) {
+    const int64_t widest = s0.M > s1.M ? s0.M : s1.M;
+    dim3 grid(static_cast<unsigned>(ceil_div<int64_t>(widest, 32)), static_cast<unsigned>(l.chunks), 2);
+    launch_pdl((col_partial_kernel<STAT>), grid, dim3(256), 0, st, s0, s1, N, l.rows_per_chunk);
     return check_launch();
 }
 
@@ -880,22 +910,27 @@ int cos_similarity_tc(const float *P, int64_t ldp, const float *A, int64_t lda, 
     float *part = reinterpret_cast<float *>(w + l.part_off - 1024);
     int rc;
     // ---- column statistics of both matrices ----
+    auto fold = [&](float *p0, float *p1) {
+        dim3 fgrid(static_cast<unsigned>(ceil_div<int64_t>(C > K ? C : K, 256)), 2);
+        launch_pdl((col_fold_kernel), fgrid, dim3(256), 0, st, p0, C, p1, K, l.chunks);
+        return check_launch();
+    };
     if (cubed) {
-        if ((rc = launch_col_partial<0>(P, ldp, N, C, l, nullptr, sumP, st)) != MCD_OK) return rc;
-        if ((rc = launch_col_partial<0>(A, lda, N, K, l, nullptr, sumA, st)) != MCD_OK) return rc;
-        if ((rc = launch_col_partial<2>(P, ldp, N, C, l, sumP, sqP, st)) != MCD_OK) return rc;
-        if ((rc = launch_col_partial<2>(A, lda, N, K, l, sumA, sqA, st)) != MCD_OK) return rc;
+        if ((rc = launch_col_partial<0>(ColSrc{P, ldp, C, nullptr, sumP}, ColSrc{A, lda, K, nullptr, sumA}, N, l, st)) != MCD_OK) return rc;
+        if ((rc = fold(sumP, sumA)) != MCD_OK) return rc;
+        if ((rc = launch_col_partial<2>(ColSrc{P, ldp, C, sumP, sqP}, ColSrc{A, lda, K, sumA, sqA}, N, l, st)) != MCD_OK) return rc;
     } else {
-        if ((rc = launch_col_partial<1>(P, ldp, N, C, l, nullptr, sqP, st)) != MCD_OK) return rc;
-        if ((rc = launch_col_partial<1>(A, lda, N, K, l, nullptr, sqA, st)) != MCD_OK) return rc;
+        if ((rc = launch_col_partial<1>(ColSrc{P, ldp, C, nullptr, sqP}, ColSrc{A, lda, K, nullptr, sqA}, N, l, st)) != MCD_OK) return rc;
     }
+    if ((rc = fold(sqP, sqA)) != MCD_OK) return rc;
+    const int folded = 1;                        // consumers read one row of the (folded) partial arrays
     if (cudaFuncSetAttribute(gemm_tf32x3_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kTcSmemBytes)) != cudaSuccess)
         return MCD_ERR_CUDA;
     CUtensorMap mBhi, mBlo;
     if (!make_operand_map(&mBhi, Phi, l.Cp, l.Np, kBN) || !make_operand_map(&mBlo, Plo, l.Cp, l.Np, kBN)) return MCD_ERR_UNSUPPORTED;
     dim3 pgrid(static_cast<unsigned>(l.Cp / 32), static_cast<unsigned>(l.Np / 32));
-    if (cubed) prepare_cols_kernel<kPrepCos3><<<pgrid, 256, 0, st>>>(P, ldp, N, C, sumP, sqP, l.chunks, C, min_norm, Phi, Plo, l.Np);
-    else prepare_cols_kernel<kPrepCos><<<pgrid, 256, 0, st>>>(P, ldp, N, C, nullptr, sqP, l.chunks, C, min_norm, Phi, Plo, l.Np);
+    if (cubed) launch_pdl((prepare_cols_kernel<kPrepCos3>), pgrid, dim3(256), 0, st, P, ldp, N, C, sumP, sqP, folded, C, min_norm, Phi, Plo, l.Np);
+    else launch_pdl((prepare_cols_kernel<kPrepCos>), pgrid, dim3(256), 0, st, P, ldp, N, C, static_cast<const float *>(nullptr), sqP, folded, C, min_norm, Phi, Plo, l.Np);
     if ((rc = check_launch()) != MCD_OK) return rc;
     const int total_kb = static_cast<int>(l.Np / kBK);
     for (int64_t k0 = 0; k0 < K; k0 += kCosSlab) {
@@ -905,21 +940,21 @@ int cos_similarity_tc(const float *P, int64_t ldp, const float *A, int64_t lda, 
         dim3 agrid(static_cast<unsigned>(kp / 32), static_cast<unsigned>(l.Np / 32));
         // (the partial arrays are indexed by the column inside the whole matrix: offset pointer, full width K)
         if (cubed)
-            prepare_cols_kernel<kPrepCos3><<<agrid, 256, 0, st>>>(A + k0, lda, N, kn, sumA + k0, sqA + k0, l.chunks, K, min_norm, Ahi, Alo, l.Np);
+            launch_pdl((prepare_cols_kernel<kPrepCos3>), agrid, dim3(256), 0, st, A + k0, lda, N, kn, sumA + k0, sqA + k0, folded, K, min_norm, Ahi, Alo, l.Np);
         else
-            prepare_cols_kernel<kPrepCos><<<agrid, 256, 0, st>>>(A + k0, lda, N, kn, nullptr, sqA + k0, l.chunks, K, min_norm, Ahi, Alo, l.Np);
+            launch_pdl((prepare_cols_kernel<kPrepCos>), agrid, dim3(256), 0, st, A + k0, lda, N, kn, static_cast<const float *>(nullptr), sqA + k0, folded, K, min_norm, Ahi, Alo, l.Np);
         if ((rc = check_launch()) != MCD_OK) return rc;
         dim3 grid(static_cast<unsigned>(l.Cp / kBN), static_cast<unsigned>(kp / kBM), static_cast<unsigned>(l.splits));
         if (l.splits == 1) {
-            gemm_tf32x3_long_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(mAhi, mAlo, mBhi, mBlo, kn, C, total_kb, l.kb_per_split,
+            launch_pdl((gemm_tf32x3_long_kernel), dim3(grid), dim3(kTcThreads), kTcSmemBytes, st, mAhi, mAlo, mBhi, mBlo, kn, C, total_kb, l.kb_per_split,
                                                                             out + k0 * ldo, ldo, 0, 1, int(l.Cp / kBN), 1.f, nullptr, 3);
             if ((rc = check_launch()) != MCD_OK) return rc;
         } else {
-            gemm_tf32x3_long_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(mAhi, mAlo, mBhi, mBlo, kn, C, total_kb, l.kb_per_split,
+            launch_pdl((gemm_tf32x3_long_kernel), dim3(grid), dim3(kTcThreads), kTcSmemBytes, st, mAhi, mAlo, mBhi, mBlo, kn, C, total_kb, l.kb_per_split,
                                                                             part, l.Cp, l.Kp * l.Cp, 1, int(l.Cp / kBN), 1.f, nullptr, 3);
             if ((rc = check_launch()) != MCD_OK) return rc;
             dim3 cgrid(static_cast<unsigned>(ceil_div<int64_t>(C, 256)), static_cast<unsigned>(kn));
-            splitk_combine_kernel<<<cgrid, 256, 0, st>>>(part, l.splits, kn, C, l.Cp, l.Kp * l.Cp, out + k0 * ldo, ldo);
+            launch_pdl((splitk_combine_kernel), cgrid, dim3(256), 0, st, part, l.splits, kn, C, l.Cp, l.Kp * l.Cp, out + k0 * ldo, ldo);
             if ((rc = check_launch()) != MCD_OK) return rc;
         }
     }
