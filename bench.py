@@ -253,7 +253,7 @@ def sharded_parity(similarity, mdist, dev, world, rank):
     """N > 1, before timing: the neuron-sharded call on a small problem must reproduce the single-GPU bits (every rank
     also runs the unsharded call) for every score-exchange mode."""
     import torch.distributed as dist
-    N, K, C = 30000, 256 * 3 * world + 100, C_CONCEPTS        # long columns: the bench's kernels (filter scan)
+    N, K, C = 40000, 256 * 3 * world + 100, C_CONCEPTS        # long columns: the bench's kernels (filter scan)
     g = torch.Generator(device=dev).manual_seed(5)
     P = torch.randn(N, C, generator=g, device=dev) * 0.05
     A = torch.randn(N, K, generator=g, device=dev)

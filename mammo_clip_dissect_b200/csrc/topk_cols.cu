@@ -974,10 +974,18 @@ static bool make_plan(int64_t N, int64_t K, int64_t k64, TopkPlan *p) {
     p->filter = 0;
     p->f_cap = p->f_chunk_tiles = p->f_chunks = p->f_nstage = p->f_rows = 0;
     p->f_cnt_bytes = p->f_list_bytes = 0;
-    // Taken when the 1-in-32 sample applies (N >= ~24 000 rows): measured on B200 at K = 8192 .. 9216 the filter form wins
-    // from N = 40 000 (0.42 against 0.75 ms) and loses at N <= 20 000 (1.37 against 0.62 ms), where the denser samples
-    // (1 tile in 16 .. 4) cost as much as the scan itself and the kept-set scan's start-up is still cheap.
-    if (p->pre_stride == 32 && N < (int64_t(1) << 30) && tunable(kTopkFilter) != 1 && tunable(kTopkVariant) == 0 &&
+    // Taken whenever a row sample applies (N >= ~10 000 rows at k = 100): measured on B200 at K = 8192 .. 9216 against the
+    // kept-set scan with the same start threshold: 0.25 / 0.67 ms at N = 10 000, 0.29 / 0.60 at 20 000, 0.33 / 0.74 at
+    // 40 000; 0.10 / 0.81 ms at 20 000 x 512 (tools/time_k2_crossover.py).
+    // The threshold is the j-th largest of `ntile` tile maxima: a fraction r = j / ntile of the tile maxima lies above it,
+    // hence a fraction -ln(1 - r) / 32 of the ELEMENTS, i.e. stride * j * m(r) survivors per column with
+    // m(r) = -ln(1 - r) / r (1.11 at c4, r = 18 / 97; 1.9 at N = 10 000, r = 60 / 78; -> 1 only for j << ntile).  The list
+    // capacity below carries that factor.  (Without it the lists of short columns overflowed and the exact redo took
+    // over -- which is what had made the filter form look slower than the kept-set scan below N = 40 000: 1.37 against
+    // 0.62 ms at N = 20 000.  With it: 0.29 against 0.60 ms there, 0.25 against 0.67 ms at 10 000 x 9216.)
+    const int64_t pre_ntile = p->pre_rows / kSampleRows;
+    if (p->pre_stride > 0 && N < (int64_t(1) << 30) &&
+        tunable(kTopkFilter) != 1 && tunable(kTopkVariant) == 0 &&
         tunable(kTopkSplits) <= 0) {
         // the number of column elements above the j-th largest of a 1/stride sample is ~ stride * Gamma(j): the list
         // holds stride * x elements with P(Gamma(j) > x) = P(Poisson(x) <= j - 1) <= 1e-10 (x = 59.25 for j = 18: 3.3 x the
@@ -991,7 +999,10 @@ static bool make_plan(int64_t N, int64_t K, int64_t k64, TopkPlan *p) {
             }
             if (cdf <= 1e-10 || x > 40.0 * p->pre_k) break;
         }
-        int cap = static_cast<int>(x * p->pre_stride) + 31;
+        double r = double(p->pre_k) / double(pre_ntile > p->pre_k ? pre_ntile : p->pre_k + 1);
+        if (r > 0.9) r = 0.9;
+        const double m_r = -log(1.0 - r) / r;            // survivors per column = stride * Gamma(j) * m(r)
+        int cap = static_cast<int>(x * p->pre_stride * m_r) + 31;
         if (cap < 2 * k + 64) cap = 2 * k + 64;
         cap = cap / 32 * 32;
         const size_t list_bytes = size_t(K) * size_t(cap) * 8;

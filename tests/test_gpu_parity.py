@@ -210,7 +210,7 @@ def _filter_case(kind, N, K, seed=77):
 
 @pytest.mark.parametrize("kind", ["randn", "spikes_on_sampled_rows", "overflow", "relu", "const", "nan_cols", "sorted_up",
                                   "sorted_down", "round1", "mixed"])
-@pytest.mark.parametrize("N,K,k", [(30000, 200, 100), (17017, 131, 28), (33333, 260, 10), (60000, 100, 256)])
+@pytest.mark.parametrize("N,K,k", [(40000, 200, 100), (25017, 131, 28), (33333, 260, 10), (60000, 100, 256)])
 def test_topk_filter_form(sim, kind, N, K, k):
     """Long TMA-aligned columns take the filter form (sample threshold -> filter scan -> select, exact redo of flagged
     column groups).  Same bits as the oracle and as the kept-set scan (tunable topk_filter = 1), values included."""
@@ -244,7 +244,7 @@ def test_topk_filter_form_beyond_128_sampled_tiles(sim, kind):
 @pytest.mark.parametrize("stages,chunk_tiles", [(2, 1), (3, 1000000), (4, 7)])
 def test_topk_filter_ring_and_item_shapes(sim, stages, chunk_tiles):
     from mammo_clip_dissect_b200 import _lib
-    A = _filter_case("mixed", 30011, 388, seed=5)
+    A = _filter_case("mixed", 40011, 388, seed=5)
     ref = orc.topk_cols(A, 100)[1]
     try:
         _lib.set_tunable("filter_stages", stages)
@@ -260,7 +260,7 @@ def test_pipelined_call_equals_the_staged_path(sim, chunks):
     """mcd_pmi_scores_f32 cuts the neurons into column chunks and runs chunk q's select + K3 + partials on a side stream
     under the scan of chunk q + 1: same bits as the staged single-stream path, for any chunk count."""
     from mammo_clip_dissect_b200 import _lib
-    N, K, C = 30000, 2304, 763
+    N, K, C = 40000, 2304, 763
     A = torch.randn(N, K, generator=gen(91)).to(DEV)
     A[:, 700] = 1.0                                       # a flagged column inside a chunk
     P = (torch.randn(N, C, generator=gen(92)) * 0.05).to(DEV)
