@@ -452,13 +452,22 @@ def run_ours(args):
                                   "nccl": "NCCL all_gather"}[xmode]}
 
     # ---- staged pass: per-stage CUDA events (the kernels one after the other on one stream) --------------------------
-    similarity.PROFILE = []
-    for _ in range(5):
+    def staged_call():
         if world == 1:
             similarity.pmi_scores(P, A, TOP_K, 10, 1, dev, 1e-7,
                                   similarity._device_ramp(similarity._reference_ramp(TOP_K, 0.998, 0.97), TOP_K, 0.998, 0.97, dev))
         else:
             step(P, A)
+
+    # (the staged kernels keep their own cached workspaces: two untimed calls first, so that no allocation of the 0.6 GB
+    # K2 workspace lands between a stage's events)
+    similarity.PROFILE = []
+    for _ in range(2):
+        staged_call()
+    torch.cuda.synchronize(dev)
+    similarity.PROFILE = []
+    for _ in range(5):
+        staged_call()
     stage_ms = similarity.profile_summary()
     similarity.PROFILE = None
     stage_ms = {k: max_over_ranks(v) for k, v in sorted(stage_ms.items())}
@@ -488,6 +497,9 @@ def run_ours(args):
         if rank == 0:
             time.sleep(0.1)
         wclocks = wsampler.stop() if rank == 0 else None
+        similarity.PROFILE = []
+        wfn()                                        # untimed: first use of the staged kernels' workspaces at this width
+        torch.cuda.synchronize(dev)
         similarity.PROFILE = []
         for _ in range(3):
             wfn()

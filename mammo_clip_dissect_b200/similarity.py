@@ -61,14 +61,15 @@ class _Stage:
 
 
 def profile_summary():
-    """Mean milliseconds per stage over everything recorded since PROFILE was set."""
+    """Median milliseconds per stage over everything recorded since PROFILE was set (a stage that happens to contain an
+    allocation or a clock ramp must not move the figure)."""
     if not PROFILE:
         return {}
     torch.cuda.synchronize()
     acc = {}
     for name, e0, e1 in PROFILE:
         acc.setdefault(name, []).append(e0.elapsed_time(e1))
-    return {k: sum(v) / len(v) for k, v in acc.items()}
+    return {k: sorted(v)[len(v) // 2] for k, v in acc.items()}
 
 
 def _ptr(t):
