@@ -47,6 +47,12 @@ def test_workspace_queries_are_pure_host_functions(lib):
     ws = lib.mcd_topk_cols_workspace_bytes(100_000, 32_768, 100)
     assert ws >= 100 * 32_768 * 8
     assert lib.mcd_topk_cols_workspace_bytes(50, 8, 100) == 0          # k > N
+    # the filter form (survivor lists: ~2000 words per column at c4, a few hundred for short columns) is planned wherever a
+    # row sample applies, not for short or wide-k problems
+    assert lib.mcd_topk_cols_workspace_bytes(100_000, 32_768, 100) >= 32_768 * 2000 * 8
+    assert lib.mcd_topk_cols_workspace_bytes(10_000, 9_216, 100) >= 9_216 * 500 * 8
+    assert lib.mcd_topk_cols_workspace_bytes(5_000, 512, 100) < 512 * 500 * 8
+    assert lib.mcd_topk_cols_workspace_bytes(40_000, 200, 300) < 200 * 1000 * 8
     assert lib.mcd_topk_cols_workspace_bytes(10_000, 8, 1000) == 1000 * 8 * 8      # k > 512: radix select, candidates only
     assert lib.mcd_topk_cols_workspace_bytes(100_000, 8, 20_000) == 0      # beyond the radix select (k <= 16384)
     assert lib.mcd_pool_nchw_workspace_bytes(4, 24, 760, 456) > 0      # large planes are split
