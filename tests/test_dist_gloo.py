@@ -45,6 +45,19 @@ class HostExchange:
         return full if wait else mdist.GatheredScores(full, None)
 
 
+class HostPartialsExchange:
+    """Stands in for PeerPartialsExchange (CUDA symmetric memory): same attributes and call, the peer stores replaced by
+    a gloo all_gather of the variable-length partial tables."""
+
+    def __init__(self, sizes, C):
+        self.sizes, self.C, self.calls = [int(x) for x in sizes], int(C), 0
+
+    def gather(self, part, sim):
+        self.calls += 1
+        nblocks = [(s + mdist.LSE_BLOCK - 1) // mdist.LSE_BLOCK for s in self.sizes]
+        return mdist._all_gather_var(part, nblocks, None)
+
+
 def _inputs(K):
     g = torch.Generator().manual_seed(3)
     return torch.randn(300, 41, generator=g) * 0.1, torch.randn(300, K, generator=g)
@@ -75,6 +88,15 @@ def _worker(rank, world, port, K, q):
         via_ex = mdist.soft_wpmi_sharded(P, shard, sizes, top_k=20, backend=be, exchange=ex)
         handle = mdist.soft_wpmi_sharded(P, shard, sizes, top_k=20, backend=be, exchange=ex, wait=False)
         assert ex.calls == 2 and torch.equal(via_ex, full) and torch.equal(handle.wait(), full)
+        pex = HostPartialsExchange(sizes, P.shape[1])
+        via_pex = mdist.soft_wpmi_sharded(P, shard, sizes, top_k=20, backend=be, partials_exchange=pex)
+        both = mdist.soft_wpmi_sharded(P, shard, sizes, top_k=20, backend=be, exchange=ex, partials_exchange=pex)
+        assert pex.calls == 2 and ex.calls == 3 and torch.equal(via_pex, full) and torch.equal(both, full)
+        try:
+            mdist.soft_wpmi_sharded(P, shard, sizes, top_k=20, backend=be, partials_exchange=HostPartialsExchange([1] * world, 41))
+            raise AssertionError("a partials exchange built for other shard sizes must be refused")
+        except RuntimeError:
+            pass
         try:
             mdist.soft_wpmi_sharded(P, shard, sizes, top_k=20, backend=be, exchange=HostExchange([1] * world, 41))
             raise AssertionError("an exchange built for other shard sizes must be refused")
