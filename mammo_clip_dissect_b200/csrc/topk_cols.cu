@@ -959,7 +959,7 @@ static bool make_plan(int64_t N, int64_t K, int64_t k64, TopkPlan *p) {
             int pk = static_cast<int>(lam + 6.0 * sqrt(lam) + 4.0 + 0.999);
             if (pk < 8) pk = 8;
             const int64_t ntile = N / (int64_t(kSampleRows) * stride);
-            if (pk <= kSelectMaxJ && 4 * ntile >= 5 * pk) {
+            if (pk <= kSelectMaxJ && 10 * ntile >= 11 * pk) {      // r = pk / ntile <= 0.91 (the list capacity carries m(r))
                 p->pre_stride = stride;
                 p->pre_k = pk;
                 p->pre_rows = ntile * kSampleRows;
@@ -974,7 +974,7 @@ static bool make_plan(int64_t N, int64_t K, int64_t k64, TopkPlan *p) {
     p->filter = 0;
     p->f_cap = p->f_chunk_tiles = p->f_chunks = p->f_nstage = p->f_rows = 0;
     p->f_cnt_bytes = p->f_list_bytes = 0;
-    // Taken whenever a row sample applies (N >= ~10 000 rows at k = 100): measured on B200 at K = 8192 .. 9216 against the
+    // Taken whenever a row sample applies (N >= 8448 rows at k = 100): measured on B200 at K = 8192 .. 9216 against the
     // kept-set scan with the same start threshold: 0.25 / 0.67 ms at N = 10 000, 0.29 / 0.60 at 20 000, 0.33 / 0.74 at
     // 40 000; 0.10 / 0.81 ms at 20 000 x 512 (tools/time_k2_crossover.py).
     // The threshold is the j-th largest of `ntile` tile maxima: a fraction r = j / ntile of the tile maxima lies above it,
@@ -1000,7 +1000,7 @@ static bool make_plan(int64_t N, int64_t K, int64_t k64, TopkPlan *p) {
             if (cdf <= 1e-10 || x > 40.0 * p->pre_k) break;
         }
         double r = double(p->pre_k) / double(pre_ntile > p->pre_k ? pre_ntile : p->pre_k + 1);
-        if (r > 0.9) r = 0.9;
+        if (r > 0.92) r = 0.92;
         const double m_r = -log(1.0 - r) / r;            // survivors per column = stride * Gamma(j) * m(r)
         int cap = static_cast<int>(x * p->pre_stride * m_r) + 31;
         if (cap < 2 * k + 64) cap = 2 * k + 64;

@@ -6,7 +6,7 @@ from mammo_clip_dissect_b200 import _lib, similarity as sim
 from tools.tune_filter import timeit
 dev = torch.device("cuda:0")
 g = torch.Generator(device=dev).manual_seed(0)
-for n, k in ((8192, 9216), (10000, 9216), (12000, 9216), (16000, 8192), (20000, 8192), (24000, 8192), (10000, 768), (20000, 512)):
+for n, k in ((8192, 9216), (8500, 9216), (9000, 9216), (10000, 9216), (12000, 9216), (16000, 8192), (20000, 8192), (24000, 8192), (40000, 8192), (10000, 768), (20000, 512)):
     A = torch.randn(n, k, generator=g, device=dev)
     ref = None
     for flt, name in ((0, "automatic"), (1, "kept-set scan"), (2, "filter form")):
